@@ -1,0 +1,134 @@
+"""ctypes binding of libbeatthis_sm100.so (C ABI in include/beatthis.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``beat_this_b200._lib.build()``
+(nvcc, sm_100a).  There is no fallback: if the shared object is missing or no sm_100 GPU is
+present, loading / ``bt_create`` fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libbeatthis_sm100.so")
+SOURCES = ["bt_api.cu", "kernels_simt.cu", "kernels_misc.cu", "kernels_tc.cu"]
+HEADERS = ["common.cuh", "epilogue.cuh", "bt_kernels.h", os.path.join("..", "..", "include", "beatthis.h")]
+
+BT_DTYPE_F32 = 0
+BT_DTYPE_BF16 = 1
+
+
+class bt_hparams(ctypes.Structure):
+    _fields_ = [
+        ("spect_dim", c_int32),
+        ("transformer_dim", c_int32),
+        ("ff_mult", c_int32),
+        ("n_layers", c_int32),
+        ("head_dim", c_int32),
+        ("stem_dim", c_int32),
+        ("sum_head", c_int32),
+        ("partial_transformers", c_int32),
+    ]
+
+
+# every symbol include/beatthis.h declares: name -> (restype, argtypes)
+PROTOTYPES = {
+    "bt_version": (c_int, []),
+    "bt_create": (c_int, [POINTER(c_void_p), c_int, POINTER(bt_hparams), c_int]),
+    "bt_set_param": (c_int, [c_void_p, c_char_p, POINTER(c_float), c_int64]),
+    "bt_finalize": (c_int, [c_void_p]),
+    "bt_destroy": (None, [c_void_p]),
+    "bt_last_error": (c_char_p, [c_void_p]),
+    "bt_num_frames": (c_int64, [c_int64]),
+    "bt_plan_chunks": (c_int64, [c_int64, POINTER(c_int64), POINTER(c_int64), c_int64]),
+    "bt_logmel": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, POINTER(c_int64), c_void_p]),
+    "bt_spect2frames": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_void_p, c_void_p]),
+    "bt_audio2frames": (
+        c_int,
+        [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_void_p, POINTER(c_int64), c_void_p],
+    ),
+    "bt_peakpick": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p],
+    ),
+    "bt_set_wave_chunks": (c_int, [c_void_p, c_int32]),
+    "bt_launch_count": (c_int64, [c_void_p]),
+    "bt_debug_request_tap": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    "bt_debug_tap_count": (c_int64, [c_void_p]),
+    "bt_debug_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "bt_debug_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+}
+
+_lib = None
+
+
+def nvcc_command(out_path: str = LIB_PATH) -> list[str]:
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    return [
+        nvcc,
+        "-gencode", "arch=compute_100a,code=sm_100a",
+        "-O3", "-lineinfo", "-std=c++17",
+        "-Xcompiler", "-fPIC", "-shared",
+        *[os.path.join(CSRC, s) for s in SOURCES],
+        "-o", out_path,
+    ]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library for sm_100a (cross-compiles without a GPU)."""
+    if force or needs_build():
+        tmp = LIB_PATH + f".tmp{os.getpid()}"
+        cmd = nvcc_command(tmp)
+        if verbose:
+            print(" ".join(cmd))
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+        os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library and declare all prototypes.  Fails loudly when absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the sm_100a CUDA library has not been built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (or beat_this_b200._lib.build()). "
+            "There is no CPU or PyTorch fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+class BTError(RuntimeError):
+    pass
+
+
+def check(lib, ctx, code: int):
+    if code != 0:
+        msg = lib.bt_last_error(ctx)
+        raise BTError(f"libbeatthis error {code}: {msg.decode() if msg else ''}")
+
+
+def i64_array(values):
+    arr = (c_int64 * len(values))(*[int(v) for v in values])
+    return arr

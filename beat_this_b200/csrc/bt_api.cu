@@ -1,0 +1,901 @@
+// C ABI (include/beatthis.h): context, packed-parameter registry, chunk planner, workspace
+// and the per-wave schedule of the BeatThis forward pass (reference
+// beat_this/model/beat_tracker.py:188-192, math restated in SURVEY.md App. A.3).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/beatthis.h"
+#include "bt_kernels.h"
+
+using namespace bt;
+
+namespace {
+
+struct Param {
+  float* f32 = nullptr;
+  void* b16 = nullptr;
+  int32_t* i32 = nullptr;
+  int64_t n = 0;
+};
+
+struct AttnW { const Param *wqkv, *wg, *bg, *wout; };
+struct FfW { const Param *w1, *b1, *w2, *b2; };
+
+// tensor-core plans for one (wave size, chunk length) geometry
+struct AttnPlans { TcGemmPlan *qkv = nullptr, *out = nullptr; TcAttnPlan* attn = nullptr; };
+struct FfPlans { TcGemmPlan *ff1 = nullptr, *ff2 = nullptr; };
+struct WavePlans {
+  AttnPlans fa[3], ta[3];
+  FfPlans ff_f[3], ff_t[3];
+  TcGemmPlan* conv[3] = {nullptr, nullptr, nullptr};
+  TcGemmPlan* lin = nullptr;
+  std::vector<AttnPlans> la;
+  std::vector<FfPlans> lf;
+};
+
+char g_create_error[512] = "";
+
+}  // namespace
+
+struct bt_ctx {
+  int device = 0;
+  bt_hparams hp{};
+  int dtype = BT_DTYPE_F32;
+  bool finalized = false;
+  std::map<std::string, Param> params;
+  mutable char err[1024] = "";
+  int64_t launches = 0;
+  bool sync_debug = false;
+
+  // workspace (sized for `wave` chunks of BT_CHUNK frames)
+  int wave = 8;
+  int ws_wave = 0;
+  float *X0 = nullptr, *X1 = nullptr, *GATES = nullptr;
+  void *XB = nullptr, *XN = nullptr, *QKV = nullptr, *VT = nullptr, *O = nullptr, *H = nullptr;
+  int64_t vt_elems = 0;
+  // spectrogram scratch for bt_audio2frames
+  float* spect_ws = nullptr;
+  int64_t spect_cap = 0;
+  // pinned staging + device tables
+  void* stage_host = nullptr;
+  size_t stage_cap = 0;
+  void* stage_dev = nullptr;
+  size_t stage_dev_cap = 0;
+  cudaEvent_t stage_ev = nullptr;
+  bool stage_pending = false;
+
+  std::map<std::pair<int, int>, WavePlans*> plans;
+
+  // debug tap
+  std::string tap_name;
+  float* tap_out = nullptr;
+  int64_t tap_cap = 0;
+  int64_t tap_count = 0;
+};
+
+namespace {
+
+int fail(const bt_ctx* c, int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  if (c) vsnprintf(c->err, sizeof(c->err), fmt, ap);
+  else vsnprintf(g_create_error, sizeof(g_create_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define BT_CUDA(ctx, call)                                                                   \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return fail(ctx, BT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                  __FILE__, __LINE__);                                                       \
+  } while (0)
+
+int check_launch(bt_ctx* c, const char* what, cudaStream_t st) {
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && c->sync_debug) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return fail(c, BT_ERR_CUDA, "kernel %s failed: %s", what, cudaGetErrorString(e));
+  return BT_OK;
+}
+#define BT_LAUNCHED(c, what, st)                 \
+  do {                                           \
+    int _r = check_launch(c, what, st);          \
+    if (_r != BT_OK) return _r;                  \
+  } while (0)
+
+const Param* find_param(const bt_ctx* c, const std::string& name) {
+  auto it = c->params.find(name);
+  return it == c->params.end() ? nullptr : &it->second;
+}
+
+int64_t chunks_for(int64_t T, int64_t* starts, int64_t* lens, int64_t cap) {
+  // split_piece (reference inference.py:119-125): starts = arange(-6, T-6, 1488); if T > 1488
+  // the last start is moved to T - 1494; chunk = frames [start, start+1500) clipped to the
+  // piece, zero padded by max(0,-start) on the left and max(0, min(6, start+1500-T)) on the right.
+  if (T <= 0) return 0;
+  const int64_t step = BT_CHUNK - 2 * BT_BORDER;
+  int64_t n = 0;
+  for (int64_t s = -BT_BORDER; s < T - BT_BORDER; s += step) ++n;
+  int64_t i = 0;
+  for (int64_t s = -BT_BORDER; s < T - BT_BORDER; s += step, ++i) {
+    int64_t st = s;
+    if (i == n - 1 && T > step) st = T - (BT_CHUNK - BT_BORDER);
+    const int64_t lo = std::max<int64_t>(st, 0), hi = std::min<int64_t>(st + BT_CHUNK, T);
+    const int64_t left = std::max<int64_t>(0, -st);
+    const int64_t right = std::max<int64_t>(0, std::min<int64_t>(BT_BORDER, st + BT_CHUNK - T));
+    if (i < cap) {
+      if (starts) starts[i] = st;
+      if (lens) lens[i] = (hi - lo) + left + right;
+    }
+  }
+  return n;
+}
+
+int ensure_stage(bt_ctx* c, size_t bytes) {
+  if (c->stage_pending) {
+    BT_CUDA(c, cudaEventSynchronize(c->stage_ev));
+    c->stage_pending = false;
+  }
+  if (bytes > c->stage_cap) {
+    if (c->stage_host) cudaFreeHost(c->stage_host);
+    c->stage_host = nullptr;
+    size_t cap = std::max<size_t>(bytes * 2, 1 << 16);
+    BT_CUDA(c, cudaMallocHost(&c->stage_host, cap));
+    c->stage_cap = cap;
+  }
+  if (bytes > c->stage_dev_cap) {
+    if (c->stage_dev) cudaFree(c->stage_dev);
+    c->stage_dev = nullptr;
+    size_t cap = std::max<size_t>(bytes * 2, 1 << 16);
+    BT_CUDA(c, cudaMalloc(&c->stage_dev, cap));
+    c->stage_dev_cap = cap;
+  }
+  return BT_OK;
+}
+
+int upload_stage(bt_ctx* c, size_t bytes, cudaStream_t st) {
+  BT_CUDA(c, cudaMemcpyAsync(c->stage_dev, c->stage_host, bytes, cudaMemcpyHostToDevice, st));
+  BT_CUDA(c, cudaEventRecord(c->stage_ev, st));
+  c->stage_pending = true;
+  return BT_OK;
+}
+
+void free_ws(bt_ctx* c) {
+  void** ptrs[] = {reinterpret_cast<void**>(&c->X0), reinterpret_cast<void**>(&c->X1),
+                   reinterpret_cast<void**>(&c->GATES), &c->XB, &c->XN, &c->QKV, &c->VT, &c->O, &c->H};
+  for (auto p : ptrs) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  c->ws_wave = 0;
+}
+
+void free_plans(bt_ctx* c) {
+  for (auto& kv : c->plans) {
+    WavePlans* w = kv.second;
+    auto fa = [](AttnPlans& a) {
+      if (a.qkv) tc_gemm_plan_destroy(a.qkv);
+      if (a.out) tc_gemm_plan_destroy(a.out);
+      if (a.attn) tc_attn_plan_destroy(a.attn);
+    };
+    auto ff = [](FfPlans& f) {
+      if (f.ff1) tc_gemm_plan_destroy(f.ff1);
+      if (f.ff2) tc_gemm_plan_destroy(f.ff2);
+    };
+    for (int i = 0; i < 3; ++i) {
+      fa(w->fa[i]); fa(w->ta[i]); ff(w->ff_f[i]); ff(w->ff_t[i]);
+      if (w->conv[i]) tc_gemm_plan_destroy(w->conv[i]);
+    }
+    if (w->lin) tc_gemm_plan_destroy(w->lin);
+    for (auto& a : w->la) fa(a);
+    for (auto& f : w->lf) ff(f);
+    delete w;
+  }
+  c->plans.clear();
+}
+
+// elements per chunk of the largest frontend activation: F*L*C is the same for all blocks
+int64_t front_elems(const bt_ctx* c) {
+  return static_cast<int64_t>(c->hp.spect_dim / 4) * BT_CHUNK * c->hp.stem_dim;
+}
+
+int ensure_ws(bt_ctx* c) {
+  if (c->ws_wave == c->wave) return BT_OK;
+  free_ws(c);
+  free_plans(c);
+  const int64_t G = c->wave;
+  const int64_t fe = front_elems(c);                                     // 1.536M
+  const int64_t D = c->hp.transformer_dim;
+  const int64_t me = static_cast<int64_t>(BT_CHUNK) * D;                 // main tokens * dim
+  const int64_t xe = std::max(fe, me);
+  const size_t act = c->dtype == BT_DTYPE_BF16 ? 2 : 4;
+  BT_CUDA(c, cudaMalloc(&c->X0, G * xe * 4));
+  BT_CUDA(c, cudaMalloc(&c->X1, G * xe * 4));
+  BT_CUDA(c, cudaMalloc(&c->GATES, G * std::max<int64_t>(fe / 32, BT_CHUNK * (D / 32)) * 4));
+  BT_CUDA(c, cudaMalloc(&c->XN, G * xe * act));
+  BT_CUDA(c, cudaMalloc(&c->QKV, G * 3 * xe * act));
+  BT_CUDA(c, cudaMalloc(&c->O, G * xe * act));
+  BT_CUDA(c, cudaMalloc(&c->H, G * 4 * xe * act));
+  if (c->dtype == BT_DTYPE_BF16) {
+    BT_CUDA(c, cudaMalloc(&c->XB, G * xe * 2));
+    // transposed V: rows (seq,head,d) x padded length; rows = tokens*C/L
+    const int64_t lpad = (BT_CHUNK + 7) / 8 * 8;
+    c->vt_elems = G * (xe / BT_CHUNK) * lpad + 64;
+    BT_CUDA(c, cudaMalloc(&c->VT, c->vt_elems * 2));
+    BT_CUDA(c, cudaMemset(c->VT, 0, c->vt_elems * 2));
+  }
+  c->ws_wave = c->wave;
+  return BT_OK;
+}
+
+struct Wave {
+  const ChunkSrc* chunks_dev;
+  int nb;
+  int L;
+};
+
+int do_tap(bt_ctx* c, const char* name, const void* buf, int64_t count, bool is_act, cudaStream_t st) {
+  if (c->tap_name.empty() || c->tap_name != name || !c->tap_out) return BT_OK;
+  if (count > c->tap_cap) return fail(c, BT_ERR_ARG, "tap %s needs %lld floats", name, (long long)count);
+  if (is_act && c->dtype == BT_DTYPE_BF16) {
+    launch_bf16_to_f32(buf, c->tap_out, count, st);
+    BT_LAUNCHED(c, "tap_convert", st);
+  } else {
+    BT_CUDA(c, cudaMemcpyAsync(c->tap_out, buf, count * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  c->tap_count = count;
+  return BT_OK;
+}
+
+GemmShape plain_shape(int planes, int L, int N, int K, int lda) {
+  GemmShape g{};
+  g.planes_out = planes; g.L = L; g.N = N; g.Kslab = K; g.nslab = 1; g.plane_mul = 1; g.lda = lda;
+  return g;
+}
+
+int run_gemm(bt_ctx* c, const void* A, const Param* W, TcGemmPlan* plan, const GemmShape& g,
+             const EpiParams& e, const char* what, cudaStream_t st) {
+  if (c->dtype == BT_DTYPE_BF16) {
+    if (launch_gemm_tc(plan, e, st) != 0) return fail(c, BT_ERR_CUDA, "tc gemm launch %s failed", what);
+  } else {
+    launch_gemm_simt(reinterpret_cast<const float*>(A), W->f32, g, e, st);
+  }
+  BT_LAUNCHED(c, what, st);
+  return BT_OK;
+}
+
+EpiParams epi_generic(const Param* bias, int gelu, const float* resid, int ldr, float* out_f32, int ldo32,
+                      void* out_act, int ldoa) {
+  EpiParams e{};
+  e.kind = 0;
+  e.bias = bias ? bias->f32 : nullptr;
+  e.gelu = gelu;
+  e.resid = resid; e.ldr = ldr;
+  e.out_f32 = out_f32; e.ldo_f32 = ldo32;
+  e.out_act = out_act; e.ldo_act = ldoa;
+  return e;
+}
+
+// x += attention(x) over `planes` planes of L tokens with dim C (reference roformer.py:114-132).
+// freq == true: sequences run over the F planes of each chunk (PartialFTTransformer attnF).
+int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool freq, const AttnW& w,
+                    AttnPlans* tp, int nb, cudaStream_t st) {
+  const bool tc = c->dtype == BT_DTYPE_BF16;
+  const int heads = C / kHeadDim;
+  const int64_t M = static_cast<int64_t>(planes) * L;
+  launch_norm_gates(X, c->XN, c->GATES, w.wg->f32, w.bg->f32, M, C, heads, tc, st);
+  BT_LAUNCHED(c, "norm_gates", st);
+  const float inv_sqrt_d = 0.17677669529663687f;  // 1/sqrt(32): SDPA default scale (roformer.py:78-80)
+  EpiParams e{};
+  e.kind = 1;
+  e.out_act = c->QKV; e.ldo_act = 3 * C;
+  e.rope_cos = find_param(c, "rope.cos")->f32;
+  e.rope_sin = find_param(c, "rope.sin")->f32;
+  e.C = C; e.heads = heads; e.posmode = freq ? 1 : 0; e.F = F;
+  const bool tc_time = tc && !freq;
+  e.qscale = tc_time ? inv_sqrt_d * 1.4426950408889634f : 1.0f;
+  const int lpad = (L + 7) / 8 * 8;
+  if (tc_time) { e.vt = c->VT; e.vt_ld = lpad; }
+  GemmShape g = plain_shape(planes, L, 3 * C, C, C);
+  int r = run_gemm(c, c->XN, w.wqkv, tp ? tp->qkv : nullptr, g, e, "gemm_qkv", st);
+  if (r != BT_OK) return r;
+  if (freq) {
+    launch_attn_freq(c->QKV, c->GATES, c->O, nb, F, L, heads, inv_sqrt_d, tc, st);
+    BT_LAUNCHED(c, "attn_freq", st);
+  } else if (tc) {
+    if (launch_attn_time_tc(tp->attn, c->GATES, c->O, st) != 0) return fail(c, BT_ERR_CUDA, "attn tc launch failed");
+    BT_LAUNCHED(c, "attn_time_tc", st);
+  } else {
+    launch_attn_time_simt(reinterpret_cast<const float*>(c->QKV), c->GATES, reinterpret_cast<float*>(c->O),
+                          planes, L, heads, st);
+    BT_LAUNCHED(c, "attn_time_simt", st);
+  }
+  GemmShape go = plain_shape(planes, L, C, C, C);
+  EpiParams eo = epi_generic(nullptr, 0, X, C, X, C, nullptr, 0);
+  return run_gemm(c, c->O, w.wout, tp ? tp->out : nullptr, go, eo, "gemm_attn_out", st);
+}
+
+// x += ff(x) (reference roformer.py:38-61); optionally also writes a bf16 copy of the result.
+int ff_block(bt_ctx* c, float* X, int planes, int L, int C, int mult, const FfW& w, FfPlans* tp, void* copy_act,
+             cudaStream_t st) {
+  const bool tc = c->dtype == BT_DTYPE_BF16;
+  const int64_t M = static_cast<int64_t>(planes) * L;
+  launch_norm_gates(X, c->XN, nullptr, nullptr, nullptr, M, C, 0, tc, st);
+  BT_LAUNCHED(c, "norm", st);
+  GemmShape g1 = plain_shape(planes, L, mult * C, C, C);
+  EpiParams e1 = epi_generic(w.b1, 1, nullptr, 0, nullptr, 0, c->H, mult * C);
+  int r = run_gemm(c, c->XN, w.w1, tp ? tp->ff1 : nullptr, g1, e1, "gemm_ff1", st);
+  if (r != BT_OK) return r;
+  GemmShape g2 = plain_shape(planes, L, C, mult * C, mult * C);
+  EpiParams e2 = epi_generic(w.b2, 0, X, C, X, C, copy_act, C);
+  return run_gemm(c, c->H, w.w2, tp ? tp->ff2 : nullptr, g2, e2, "gemm_ff2", st);
+}
+
+AttnW attn_w(const bt_ctx* c, const std::string& p) {
+  return AttnW{find_param(c, p + ".wqkv"), find_param(c, p + ".wg"), find_param(c, p + ".bg"),
+               find_param(c, p + ".wout")};
+}
+FfW ff_w(const bt_ctx* c, const std::string& p) {
+  return FfW{find_param(c, p + ".w1"), find_param(c, p + ".b1"), find_param(c, p + ".w2"),
+             find_param(c, p + ".b2")};
+}
+
+GemmShape conv_shape(int nb, int F, int L, int C) {
+  // Conv2d(C -> 2C, k(2 freq, 3 time), stride (2,1), padding (0,1)) over [nb, F, L, C] as an
+  // implicit GEMM: slab s = df*3 + dt reads plane 2*p_out + df at time t + dt - 1.
+  GemmShape g{};
+  g.planes_out = nb * F / 2; g.L = L; g.N = 2 * C; g.Kslab = C; g.nslab = 6; g.plane_mul = 2; g.lda = C;
+  for (int df = 0; df < 2; ++df)
+    for (int dt = 0; dt < 3; ++dt) { g.plane_add[df * 3 + dt] = df; g.t_shift[df * 3 + dt] = dt - 1; }
+  return g;
+}
+GemmShape lin_shape(int nb, int L, int D, int Fo, int Co) {
+  // "b c f t -> b t (c f)" + Linear: slab f reads plane Fo*b + f; W columns permuted to (f, c) on the host
+  GemmShape g{};
+  g.planes_out = nb; g.L = L; g.N = D; g.Kslab = Co; g.nslab = Fo; g.plane_mul = Fo; g.lda = Co;
+  for (int f = 0; f < Fo; ++f) { g.plane_add[f] = f; g.t_shift[f] = 0; }
+  return g;
+}
+
+int build_plans(bt_ctx* c, int nb, int L, WavePlans** out) {
+  auto key = std::make_pair(nb, L);
+  auto it = c->plans.find(key);
+  if (it != c->plans.end()) { *out = it->second; return BT_OK; }
+  if (c->plans.size() > 96) free_plans(c);
+  WavePlans* w = new WavePlans();
+  c->plans[key] = w;
+  char err[512] = "";
+  const int lpad = (L + 7) / 8 * 8;
+  auto mk = [&](const void* A, const Param* W, const GemmShape& g, int planes_in) -> TcGemmPlan* {
+    return tc_gemm_plan_create(A, W->b16, g, planes_in, err, sizeof(err));
+  };
+  auto mk_attn = [&](AttnPlans& a, const AttnW& aw, int planes, int C, bool freq) -> bool {
+    a.qkv = mk(c->XN, aw.wqkv, plain_shape(planes, L, 3 * C, C, C), planes);
+    a.out = mk(c->O, aw.wout, plain_shape(planes, L, C, C, C), planes);
+    if (!a.qkv || !a.out) return false;
+    if (!freq) {
+      a.attn = tc_attn_plan_create(c->QKV, c->VT, lpad, planes, L, C / 32, err, sizeof(err));
+      if (!a.attn) return false;
+    }
+    return true;
+  };
+  auto mk_ff = [&](FfPlans& f, const FfW& fw, int planes, int C, int mult) -> bool {
+    f.ff1 = mk(c->XN, fw.w1, plain_shape(planes, L, mult * C, C, C), planes);
+    f.ff2 = mk(c->H, fw.w2, plain_shape(planes, L, C, mult * C, mult * C), planes);
+    return f.ff1 && f.ff2;
+  };
+  bool ok = true;
+  int C = c->hp.stem_dim, F = c->hp.spect_dim / 4;
+  for (int i = 0; i < 3 && ok; ++i) {
+    const std::string p = "b" + std::to_string(i);
+    if (c->hp.partial_transformers) {
+      ok = ok && mk_attn(w->fa[i], attn_w(c, p + ".attnF"), nb * F, C, true);
+      ok = ok && mk_ff(w->ff_f[i], ff_w(c, p + ".ffF"), nb * F, C, 4);
+      ok = ok && mk_attn(w->ta[i], attn_w(c, p + ".attnT"), nb * F, C, false);
+      ok = ok && mk_ff(w->ff_t[i], ff_w(c, p + ".ffT"), nb * F, C, 4);
+    }
+    if (ok) {
+      w->conv[i] = mk(c->XB, find_param(c, p + ".conv.w"), conv_shape(nb, F, L, C), nb * F);
+      ok = w->conv[i] != nullptr;
+    }
+    C *= 2; F /= 2;
+  }
+  const int D = c->hp.transformer_dim;
+  if (ok) {
+    w->lin = mk(c->XN, find_param(c, "lin.w"), lin_shape(nb, L, D, F, C), nb * F);
+    ok = w->lin != nullptr;
+  }
+  w->la.resize(c->hp.n_layers);
+  w->lf.resize(c->hp.n_layers);
+  for (int l = 0; l < c->hp.n_layers && ok; ++l) {
+    const std::string p = "l" + std::to_string(l);
+    ok = ok && mk_attn(w->la[l], attn_w(c, p + ".attn"), nb, D, false);
+    ok = ok && mk_ff(w->lf[l], ff_w(c, p + ".ff"), nb, D, c->hp.ff_mult);
+  }
+  if (!ok) return fail(c, BT_ERR_CUDA, "tensor-core plan creation failed: %s", err);
+  *out = w;
+  return BT_OK;
+}
+
+// BeatThis.forward for one wave of nb equal-length chunks, scattering the head output.
+int run_wave(bt_ctx* c, const float* spect, const Wave& wv, float* beat, float* down, cudaStream_t st) {
+  const bool tc = c->dtype == BT_DTYPE_BF16;
+  const int nb = wv.nb, L = wv.L;
+  WavePlans* wp = nullptr;
+  if (tc) {
+    int r = build_plans(c, nb, L, &wp);
+    if (r != BT_OK) return r;
+  }
+  int r;
+  float* X = c->X0;
+  float* Xalt = c->X1;
+  int C = c->hp.stem_dim, F = c->hp.spect_dim / 4;
+  launch_stem(spect, wv.chunks_dev, nb, L, find_param(c, "stem.bn1_scale")->f32,
+              find_param(c, "stem.bn1_shift")->f32, find_param(c, "stem.w")->f32,
+              find_param(c, "stem.bias")->f32, X, st);
+  BT_LAUNCHED(c, "stem", st);
+  if ((r = do_tap(c, "stem", X, static_cast<int64_t>(nb) * F * L * C, false, st)) != BT_OK) return r;
+  for (int i = 0; i < 3; ++i) {
+    const std::string p = "b" + std::to_string(i);
+    const int planes = nb * F;
+    const int64_t elems = static_cast<int64_t>(planes) * L * C;
+    void* copy_for_conv = tc ? c->XB : nullptr;
+    if (c->hp.partial_transformers) {
+      if ((r = attention_block(c, X, planes, L, C, F, true, attn_w(c, p + ".attnF"), wp ? &wp->fa[i] : nullptr, nb, st)) != BT_OK) return r;
+      if ((r = do_tap(c, (p + ".attnF").c_str(), X, elems, false, st)) != BT_OK) return r;
+      if ((r = ff_block(c, X, planes, L, C, 4, ff_w(c, p + ".ffF"), wp ? &wp->ff_f[i] : nullptr, nullptr, st)) != BT_OK) return r;
+      if ((r = do_tap(c, (p + ".ffF").c_str(), X, elems, false, st)) != BT_OK) return r;
+      if ((r = attention_block(c, X, planes, L, C, F, false, attn_w(c, p + ".attnT"), wp ? &wp->ta[i] : nullptr, nb, st)) != BT_OK) return r;
+      if ((r = do_tap(c, (p + ".attnT").c_str(), X, elems, false, st)) != BT_OK) return r;
+      if ((r = ff_block(c, X, planes, L, C, 4, ff_w(c, p + ".ffT"), wp ? &wp->ff_t[i] : nullptr, copy_for_conv, st)) != BT_OK) return r;
+      if ((r = do_tap(c, (p + ".ffT").c_str(), X, elems, false, st)) != BT_OK) return r;
+    } else if (tc) {
+      launch_f32_to_bf16(X, c->XB, elems, st);
+      BT_LAUNCHED(c, "f32_to_bf16", st);
+    }
+    // conv C -> 2C (+ folded BN2d + GELU); the last block feeds frontend.linear (activation dtype)
+    GemmShape g = conv_shape(nb, F, L, C);
+    const bool last = i == 2;
+    EpiParams e = epi_generic(find_param(c, p + ".conv.bias"), 1, nullptr, 0, last ? nullptr : Xalt, 2 * C,
+                              last ? c->XN : nullptr, 2 * C);
+    if ((r = run_gemm(c, tc ? c->XB : static_cast<const void*>(X), find_param(c, p + ".conv.w"),
+                      wp ? wp->conv[i] : nullptr, g, e, "gemm_conv", st)) != BT_OK) return r;
+    C *= 2; F /= 2;
+    if (!last) std::swap(X, Xalt);
+    if ((r = do_tap(c, (p + ".conv").c_str(), last ? c->XN : static_cast<const void*>(X),
+                    static_cast<int64_t>(nb) * F * L * C, last, st)) != BT_OK) return r;
+  }
+  const int D = c->hp.transformer_dim;
+  {
+    GemmShape g = lin_shape(nb, L, D, F, C);
+    EpiParams e = epi_generic(find_param(c, "lin.b"), 0, nullptr, 0, X, D, nullptr, 0);
+    if ((r = run_gemm(c, c->XN, find_param(c, "lin.w"), wp ? wp->lin : nullptr, g, e, "gemm_frontend_linear", st)) != BT_OK) return r;
+    if ((r = do_tap(c, "frontend", X, static_cast<int64_t>(nb) * L * D, false, st)) != BT_OK) return r;
+  }
+  for (int l = 0; l < c->hp.n_layers; ++l) {
+    const std::string p = "l" + std::to_string(l);
+    if ((r = attention_block(c, X, nb, L, D, 1, false, attn_w(c, p + ".attn"), wp ? &wp->la[l] : nullptr, nb, st)) != BT_OK) return r;
+    if ((r = do_tap(c, (p + ".attn").c_str(), X, static_cast<int64_t>(nb) * L * D, false, st)) != BT_OK) return r;
+    if ((r = ff_block(c, X, nb, L, D, c->hp.ff_mult, ff_w(c, p + ".ff"), wp ? &wp->lf[l] : nullptr, nullptr, st)) != BT_OK) return r;
+    if ((r = do_tap(c, (p + ".ff").c_str(), X, static_cast<int64_t>(nb) * L * D, false, st)) != BT_OK) return r;
+  }
+  launch_head(X, D, find_param(c, "head.w")->f32, find_param(c, "head.b")->f32, wv.chunks_dev, nb, L, beat, down, st);
+  BT_LAUNCHED(c, "head", st);
+  return BT_OK;
+}
+
+std::vector<std::string> required_params(const bt_hparams& hp) {
+  std::vector<std::string> v = {"mel.window", "mel.twiddle", "mel.fb_start", "mel.fb_ptr", "mel.fb_w",
+                                "rope.cos", "rope.sin", "stem.bn1_scale", "stem.bn1_shift", "stem.w",
+                                "stem.bias", "lin.w", "lin.b", "head.w", "head.b"};
+  auto attn = [&](const std::string& p) { for (auto s : {".wqkv", ".wg", ".bg", ".wout"}) v.push_back(p + s); };
+  auto ff = [&](const std::string& p) { for (auto s : {".w1", ".b1", ".w2", ".b2"}) v.push_back(p + s); };
+  for (int i = 0; i < 3; ++i) {
+    const std::string p = "b" + std::to_string(i);
+    if (hp.partial_transformers) { attn(p + ".attnF"); ff(p + ".ffF"); attn(p + ".attnT"); ff(p + ".ffT"); }
+    v.push_back(p + ".conv.w");
+    v.push_back(p + ".conv.bias");
+  }
+  for (int l = 0; l < hp.n_layers; ++l) { attn("l" + std::to_string(l) + ".attn"); ff("l" + std::to_string(l) + ".ff"); }
+  return v;
+}
+
+bool is_gemm_weight(const std::string& n) {
+  auto ends = [&](const char* s) { size_t k = strlen(s); return n.size() >= k && n.compare(n.size() - k, k, s) == 0; };
+  return ends(".wqkv") || ends(".wout") || ends(".w1") || ends(".w2") || ends(".conv.w") || n == "lin.w";
+}
+
+}  // namespace
+
+// ================================================================================== C ABI
+extern "C" {
+
+int bt_version(void) { return 100; }
+
+const char* bt_last_error(const bt_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+
+int64_t bt_num_frames(int64_t n_samples) { return n_samples < 0 ? 0 : 1 + n_samples / BT_HOP; }
+
+int64_t bt_plan_chunks(int64_t T, int64_t* starts, int64_t* lens, int64_t cap) {
+  return chunks_for(T, starts, lens, cap);
+}
+
+int bt_create(bt_ctx** out, int device_ordinal, const bt_hparams* hp, int compute_dtype) {
+  if (!out || !hp) return fail(nullptr, BT_ERR_ARG, "bt_create: null argument");
+  *out = nullptr;
+  if (compute_dtype != BT_DTYPE_F32 && compute_dtype != BT_DTYPE_BF16)
+    return fail(nullptr, BT_ERR_ARG, "bt_create: compute_dtype must be BT_DTYPE_F32 or BT_DTYPE_BF16");
+  if (hp->spect_dim != 128 || hp->head_dim != 32 || hp->stem_dim != 32 || hp->transformer_dim % 64 != 0 ||
+      hp->transformer_dim < 64 || hp->transformer_dim > 1024 || hp->n_layers < 1 || hp->ff_mult < 1 ||
+      hp->ff_mult > 4 || !hp->sum_head)
+    return fail(nullptr, BT_ERR_ARG,
+                "bt_create: unsupported hyper-parameters (need spect_dim 128, head_dim 32, stem_dim 32, "
+                "transformer_dim multiple of 64 in [64,1024], sum_head)");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, BT_ERR_CUDA, "bt_create: no CUDA device (%s); this library has no CPU fallback",
+                cudaGetErrorString(e));
+  if (device_ordinal < 0 || device_ordinal >= ndev)
+    return fail(nullptr, BT_ERR_ARG, "bt_create: device %d out of range (%d devices)", device_ordinal, ndev);
+  if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess)
+    return fail(nullptr, BT_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device_ordinal);
+  if (prop.major != 10)
+    return fail(nullptr, BT_ERR_CUDA, "bt_create: device is sm_%d%d; this library is built for sm_100a only",
+                prop.major, prop.minor);
+  bt_ctx* c = new bt_ctx();
+  c->device = device_ordinal;
+  c->hp = *hp;
+  c->dtype = compute_dtype;
+  const char* dbg = getenv("BT_SYNC_DEBUG");
+  c->sync_debug = dbg && dbg[0] == '1';
+  if (cudaEventCreateWithFlags(&c->stage_ev, cudaEventDisableTiming) != cudaSuccess) {
+    delete c;
+    return fail(nullptr, BT_ERR_CUDA, "cudaEventCreate failed");
+  }
+  if (compute_dtype == BT_DTYPE_BF16) {
+    char err[512];
+    if (tc_init(err, sizeof(err)) != 0) {
+      delete c;
+      return fail(nullptr, BT_ERR_CUDA, "%s", err);
+    }
+  }
+  *out = c;
+  return BT_OK;
+}
+
+int bt_set_param(bt_ctx* c, const char* name, const float* data_host, int64_t count) {
+  if (!c || !name || !data_host || count <= 0) return fail(c, BT_ERR_ARG, "bt_set_param: bad argument");
+  if (c->finalized) return fail(c, BT_ERR_STATE, "bt_set_param after bt_finalize");
+  BT_CUDA(c, cudaSetDevice(c->device));
+  Param& p = c->params[name];
+  if (p.f32) cudaFree(p.f32);
+  if (p.i32) cudaFree(p.i32);
+  p = Param();
+  p.n = count;
+  const std::string n(name);
+  if (n == "mel.fb_start" || n == "mel.fb_ptr") {
+    std::vector<int32_t> tmp(count);
+    for (int64_t i = 0; i < count; ++i) tmp[i] = static_cast<int32_t>(lrintf(data_host[i]));
+    BT_CUDA(c, cudaMalloc(&p.i32, count * 4));
+    BT_CUDA(c, cudaMemcpy(p.i32, tmp.data(), count * 4, cudaMemcpyHostToDevice));
+  }
+  BT_CUDA(c, cudaMalloc(&p.f32, count * 4));
+  BT_CUDA(c, cudaMemcpy(p.f32, data_host, count * 4, cudaMemcpyHostToDevice));
+  return BT_OK;
+}
+
+int bt_finalize(bt_ctx* c) {
+  if (!c) return BT_ERR_ARG;
+  if (c->finalized) return BT_OK;
+  BT_CUDA(c, cudaSetDevice(c->device));
+  const bt_hparams& hp = c->hp;
+  for (const auto& n : required_params(hp))
+    if (!find_param(c, n)) return fail(c, BT_ERR_PARAM, "bt_finalize: missing parameter '%s'", n.c_str());
+  // shape checks for the GEMM weights
+  auto expect = [&](const std::string& n, int64_t cnt) -> bool {
+    const Param* p = find_param(c, n);
+    if (!p || p->n != cnt) {
+      fail(c, BT_ERR_PARAM, "parameter '%s' has %lld elements, expected %lld", n.c_str(),
+           (long long)(p ? p->n : -1), (long long)cnt);
+      return false;
+    }
+    return true;
+  };
+  auto chk_attn = [&](const std::string& p, int64_t C) {
+    return expect(p + ".wqkv", 3 * C * C) && expect(p + ".wg", C / 32 * C) && expect(p + ".bg", C / 32) &&
+           expect(p + ".wout", C * C);
+  };
+  auto chk_ff = [&](const std::string& p, int64_t C, int64_t mult) {
+    return expect(p + ".w1", mult * C * C) && expect(p + ".b1", mult * C) && expect(p + ".w2", mult * C * C) &&
+           expect(p + ".b2", C);
+  };
+  int64_t C = hp.stem_dim;
+  for (int i = 0; i < 3; ++i) {
+    const std::string p = "b" + std::to_string(i);
+    if (hp.partial_transformers)
+      if (!chk_attn(p + ".attnF", C) || !chk_ff(p + ".ffF", C, 4) || !chk_attn(p + ".attnT", C) ||
+          !chk_ff(p + ".ffT", C, 4)) return BT_ERR_PARAM;
+    if (!expect(p + ".conv.w", 2 * C * 6 * C) || !expect(p + ".conv.bias", 2 * C)) return BT_ERR_PARAM;
+    C *= 2;
+  }
+  const int64_t D = hp.transformer_dim;
+  if (!expect("lin.w", D * C * (hp.spect_dim / 32)) || !expect("lin.b", D) || !expect("head.w", 2 * D) ||
+      !expect("head.b", 2) || !expect("stem.w", 32 * 12) || !expect("mel.window", 1024) ||
+      !expect("mel.twiddle", 1024) || !expect("mel.fb_start", 128) || !expect("mel.fb_ptr", 129) ||
+      !expect("rope.cos", (int64_t)BT_CHUNK * 16) || !expect("rope.sin", (int64_t)BT_CHUNK * 16))
+    return BT_ERR_PARAM;
+  for (int l = 0; l < hp.n_layers; ++l) {
+    const std::string p = "l" + std::to_string(l);
+    if (!chk_attn(p + ".attn", D) || !chk_ff(p + ".ff", D, hp.ff_mult)) return BT_ERR_PARAM;
+  }
+  if (c->dtype == BT_DTYPE_BF16) {
+    for (auto& kv : c->params) {
+      if (!is_gemm_weight(kv.first)) continue;
+      BT_CUDA(c, cudaMalloc(&kv.second.b16, kv.second.n * 2));
+      launch_f32_to_bf16(kv.second.f32, kv.second.b16, kv.second.n, nullptr);
+    }
+    BT_CUDA(c, cudaDeviceSynchronize());
+  }
+  c->finalized = true;
+  return BT_OK;
+}
+
+void bt_destroy(bt_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  free_plans(c);
+  free_ws(c);
+  for (auto& kv : c->params) {
+    if (kv.second.f32) cudaFree(kv.second.f32);
+    if (kv.second.b16) cudaFree(kv.second.b16);
+    if (kv.second.i32) cudaFree(kv.second.i32);
+  }
+  if (c->spect_ws) cudaFree(c->spect_ws);
+  if (c->stage_host) cudaFreeHost(c->stage_host);
+  if (c->stage_dev) cudaFree(c->stage_dev);
+  if (c->stage_ev) cudaEventDestroy(c->stage_ev);
+  delete c;
+}
+
+int bt_set_wave_chunks(bt_ctx* c, int32_t chunks) {
+  if (!c || chunks < 1 || chunks > 256) return fail(c, BT_ERR_ARG, "bt_set_wave_chunks: 1..256");
+  c->wave = chunks;
+  return BT_OK;
+}
+
+int64_t bt_launch_count(const bt_ctx* c) { return c ? c->launches : 0; }
+
+int bt_debug_request_tap(bt_ctx* c, const char* tap, float* out_dev, int64_t cap) {
+  if (!c) return BT_ERR_ARG;
+  c->tap_name = tap ? tap : "";
+  c->tap_out = out_dev;
+  c->tap_cap = cap;
+  c->tap_count = 0;
+  return BT_OK;
+}
+int64_t bt_debug_tap_count(const bt_ctx* c) { return c ? c->tap_count : 0; }
+
+int bt_logmel(bt_ctx* c, const float* audio_dev, const int64_t* sample_offsets_host, int32_t n_clips,
+              float* spect_dev, const int64_t* frame_offsets_host, void* stream) {
+  if (!c) return BT_ERR_ARG;
+  for (const char* n : {"mel.window", "mel.twiddle", "mel.fb_start", "mel.fb_ptr", "mel.fb_w"})
+    if (!find_param(c, n)) return fail(c, BT_ERR_STATE, "bt_logmel: parameter '%s' not set", n);
+  if (n_clips <= 0) return BT_OK;
+  if (!audio_dev || !sample_offsets_host || !spect_dev || !frame_offsets_host)
+    return fail(c, BT_ERR_ARG, "bt_logmel: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BT_CUDA(c, cudaSetDevice(c->device));
+  for (int i = 0; i < n_clips; ++i) {
+    const int64_t len = sample_offsets_host[i + 1] - sample_offsets_host[i];
+    if (len <= BT_N_FFT / 2)
+      return fail(c, BT_ERR_ARG, "bt_logmel: clip %d has %lld samples; reflect padding needs more than %d "
+                  "(torch.stft raises for such input as well)", i, (long long)len, BT_N_FFT / 2);
+    if (frame_offsets_host[i + 1] - frame_offsets_host[i] != bt_num_frames(len))
+      return fail(c, BT_ERR_ARG, "bt_logmel: frame_offsets do not match 1 + len/441 for clip %d", i);
+  }
+  const size_t bytes = static_cast<size_t>(n_clips + 1) * 8 * 2;
+  int r = ensure_stage(c, bytes);
+  if (r != BT_OK) return r;
+  int64_t* h = static_cast<int64_t*>(c->stage_host);
+  memcpy(h, sample_offsets_host, (n_clips + 1) * 8);
+  memcpy(h + n_clips + 1, frame_offsets_host, (n_clips + 1) * 8);
+  if ((r = upload_stage(c, bytes, st)) != BT_OK) return r;
+  const int64_t* d = static_cast<const int64_t*>(c->stage_dev);
+  const int64_t f0 = frame_offsets_host[0];
+  const int64_t total = frame_offsets_host[n_clips] - f0;
+  if (f0 != 0) return fail(c, BT_ERR_ARG, "bt_logmel: frame_offsets_host[0] must be 0");
+  launch_logmel(audio_dev, d, d + n_clips + 1, n_clips, total, find_param(c, "mel.window")->f32,
+                find_param(c, "mel.twiddle")->f32, find_param(c, "mel.fb_start")->i32,
+                find_param(c, "mel.fb_ptr")->i32, find_param(c, "mel.fb_w")->f32, spect_dev, st);
+  BT_LAUNCHED(c, "logmel", st);
+  return BT_OK;
+}
+
+int bt_spect2frames(bt_ctx* c, const float* spect_dev, const int64_t* frame_offsets_host, int32_t n_clips,
+                    float* beat_dev, float* downbeat_dev, void* stream) {
+  if (!c || !c->finalized) return fail(c, BT_ERR_STATE, "bt_spect2frames: context not finalized");
+  if (n_clips <= 0) return BT_OK;
+  if (!spect_dev || !frame_offsets_host || !beat_dev || !downbeat_dev)
+    return fail(c, BT_ERR_ARG, "bt_spect2frames: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BT_CUDA(c, cudaSetDevice(c->device));
+  int r = ensure_ws(c);
+  if (r != BT_OK) return r;
+  // plan: all chunks of all clips, grouped by chunk length (1500 except for pieces <= 1488 frames)
+  struct HostChunk { ChunkSrc s; int len; };
+  std::vector<HostChunk> all;
+  std::vector<int64_t> starts, lens;
+  for (int i = 0; i < n_clips; ++i) {
+    const int64_t T = frame_offsets_host[i + 1] - frame_offsets_host[i];
+    if (T < 0) return fail(c, BT_ERR_ARG, "bt_spect2frames: negative clip length");
+    if (T == 0) continue;
+    const int64_t n = chunks_for(T, nullptr, nullptr, 0);
+    starts.resize(n); lens.resize(n);
+    chunks_for(T, starts.data(), lens.data(), n);
+    for (int64_t j = 0; j < n; ++j) {
+      HostChunk hc;
+      hc.s.frame_base = frame_offsets_host[i];
+      hc.s.out_base = frame_offsets_host[i];
+      hc.s.T = static_cast<int32_t>(T);
+      hc.s.start = static_cast<int32_t>(starts[j]);
+      // keep_first (inference.py:174-184): chunk j owns [start+6, start+len-6) minus what earlier chunks own
+      int64_t lo = starts[j] + BT_BORDER;
+      if (j > 0) lo = std::max(lo, starts[j - 1] + lens[j - 1] - BT_BORDER);
+      const int64_t hi = starts[j] + lens[j] - BT_BORDER;
+      hc.s.write_lo = static_cast<int32_t>(lo - starts[j]);
+      hc.s.write_hi = static_cast<int32_t>(std::max(lo, hi) - starts[j]);
+      hc.len = static_cast<int>(lens[j]);
+      all.push_back(hc);
+    }
+  }
+  if (all.empty()) return BT_OK;
+  std::stable_sort(all.begin(), all.end(), [](const HostChunk& a, const HostChunk& b) { return a.len > b.len; });
+  const size_t bytes = all.size() * sizeof(ChunkSrc);
+  if ((r = ensure_stage(c, bytes)) != BT_OK) return r;
+  ChunkSrc* hs = static_cast<ChunkSrc*>(c->stage_host);
+  for (size_t i = 0; i < all.size(); ++i) hs[i] = all[i].s;
+  if ((r = upload_stage(c, bytes, st)) != BT_OK) return r;
+  const ChunkSrc* ds = static_cast<const ChunkSrc*>(c->stage_dev);
+  size_t i = 0;
+  while (i < all.size()) {
+    size_t j = i;
+    while (j < all.size() && all[j].len == all[i].len && j - i < static_cast<size_t>(c->wave)) ++j;
+    Wave wv{ds + i, static_cast<int>(j - i), all[i].len};
+    if ((r = run_wave(c, spect_dev, wv, beat_dev, downbeat_dev, st)) != BT_OK) return r;
+    i = j;
+  }
+  return BT_OK;
+}
+
+int bt_audio2frames(bt_ctx* c, const float* audio_dev, const int64_t* sample_offsets_host, int32_t n_clips,
+                    float* beat_dev, float* downbeat_dev, const int64_t* frame_offsets_host, void* stream) {
+  if (!c || !c->finalized) return fail(c, BT_ERR_STATE, "bt_audio2frames: context not finalized");
+  if (n_clips <= 0) return BT_OK;
+  if (!frame_offsets_host) return fail(c, BT_ERR_ARG, "bt_audio2frames: null argument");
+  BT_CUDA(c, cudaSetDevice(c->device));
+  const int64_t total = frame_offsets_host[n_clips];
+  if (total * 128 > c->spect_cap) {
+    if (c->spect_ws) cudaFree(c->spect_ws);
+    c->spect_ws = nullptr;
+    c->spect_cap = total * 128 * 5 / 4;
+    BT_CUDA(c, cudaMalloc(&c->spect_ws, c->spect_cap * 4));
+  }
+  int r = bt_logmel(c, audio_dev, sample_offsets_host, n_clips, c->spect_ws, frame_offsets_host, stream);
+  if (r != BT_OK) return r;
+  return bt_spect2frames(c, c->spect_ws, frame_offsets_host, n_clips, beat_dev, downbeat_dev, stream);
+}
+
+int bt_peakpick(bt_ctx* c, const float* beat_dev, const float* downbeat_dev, const int64_t* frame_offsets_host,
+                int32_t n_clips, double* beat_times_dev, int32_t* n_beats_dev, double* down_times_dev,
+                int32_t* n_down_dev, int32_t max_peaks, void* stream) {
+  if (!c) return BT_ERR_ARG;
+  if (n_clips <= 0) return BT_OK;
+  if (!beat_dev || !downbeat_dev || !frame_offsets_host || !beat_times_dev || !n_beats_dev || !down_times_dev ||
+      !n_down_dev || max_peaks < 1)
+    return fail(c, BT_ERR_ARG, "bt_peakpick: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BT_CUDA(c, cudaSetDevice(c->device));
+  const size_t bytes = static_cast<size_t>(n_clips + 1) * 8;
+  int r = ensure_stage(c, bytes);
+  if (r != BT_OK) return r;
+  memcpy(c->stage_host, frame_offsets_host, bytes);
+  if ((r = upload_stage(c, bytes, st)) != BT_OK) return r;
+  launch_peakpick(beat_dev, downbeat_dev, static_cast<const int64_t*>(c->stage_dev), n_clips, beat_times_dev,
+                  n_beats_dev, down_times_dev, n_down_dev, max_peaks, st);
+  BT_LAUNCHED(c, "peakpick", st);
+  return BT_OK;
+}
+
+int bt_debug_gemm(bt_ctx* c, const float* a_dev, const float* w_dev, float* d_dev, int32_t M, int32_t N, int32_t K,
+                  void* stream) {
+  if (!c) return BT_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BT_CUDA(c, cudaSetDevice(c->device));
+  GemmShape g = plain_shape(1, M, N, K, K);
+  EpiParams e = epi_generic(nullptr, 0, nullptr, 0, d_dev, N, nullptr, 0);
+  if (c->dtype == BT_DTYPE_BF16) {
+    void *ab = nullptr, *wb = nullptr;
+    BT_CUDA(c, cudaMalloc(&ab, static_cast<size_t>(M) * K * 2));
+    BT_CUDA(c, cudaMalloc(&wb, static_cast<size_t>(N) * K * 2));
+    launch_f32_to_bf16(a_dev, ab, static_cast<int64_t>(M) * K, st);
+    launch_f32_to_bf16(w_dev, wb, static_cast<int64_t>(N) * K, st);
+    char err[512] = "";
+    TcGemmPlan* p = tc_gemm_plan_create(ab, wb, g, 1, err, sizeof(err));
+    int rc = BT_OK;
+    if (!p) rc = fail(c, BT_ERR_CUDA, "%s", err);
+    else if (launch_gemm_tc(p, e, st) != 0) rc = fail(c, BT_ERR_CUDA, "tc gemm launch failed");
+    cudaError_t se = cudaStreamSynchronize(st);
+    if (rc == BT_OK && se != cudaSuccess) rc = fail(c, BT_ERR_CUDA, "tc gemm: %s", cudaGetErrorString(se));
+    if (p) tc_gemm_plan_destroy(p);
+    cudaFree(ab); cudaFree(wb);
+    c->launches++;
+    return rc;
+  }
+  launch_gemm_simt(a_dev, w_dev, g, e, st);
+  BT_LAUNCHED(c, "debug_gemm", st);
+  return BT_OK;
+}
+
+int bt_debug_attention(bt_ctx* c, const float* q_dev, const float* k_dev, const float* v_dev, float* o_dev,
+                       int32_t seqs, int32_t L, int32_t heads, void* stream) {
+  if (!c) return BT_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BT_CUDA(c, cudaSetDevice(c->device));
+  const int C = heads * 32;
+  const int64_t M = static_cast<int64_t>(seqs) * L;
+  const bool tc = c->dtype == BT_DTYPE_BF16;
+  const size_t act = tc ? 2 : 4;
+  const int lpad = (L + 7) / 8 * 8;
+  void *qkv = nullptr, *vt = nullptr, *o = nullptr;
+  float* gates = nullptr;
+  BT_CUDA(c, cudaMalloc(&qkv, M * 3 * C * act));
+  BT_CUDA(c, cudaMalloc(&o, M * C * act));
+  BT_CUDA(c, cudaMalloc(&gates, M * heads * 4));
+  std::vector<float> ones(M * heads, 1.0f);
+  BT_CUDA(c, cudaMemcpyAsync(gates, ones.data(), M * heads * 4, cudaMemcpyHostToDevice, st));
+  int rc = BT_OK;
+  if (tc) {
+    const int64_t vte = static_cast<int64_t>(seqs) * C * lpad;
+    BT_CUDA(c, cudaMalloc(&vt, vte * 2));
+    BT_CUDA(c, cudaMemsetAsync(vt, 0, vte * 2, st));
+    launch_pack_qkv_test(q_dev, k_dev, v_dev, qkv, vt, lpad, seqs, L, heads,
+                         0.17677669529663687f * 1.4426950408889634f, 1, st);
+    char err[512] = "";
+    TcAttnPlan* p = tc_attn_plan_create(qkv, vt, lpad, seqs, L, heads, err, sizeof(err));
+    if (!p) rc = fail(c, BT_ERR_CUDA, "%s", err);
+    else {
+      launch_attn_time_tc(p, gates, o, st);
+      launch_bf16_to_f32(o, o_dev, M * C, st);
+    }
+    cudaError_t se = cudaStreamSynchronize(st);
+    if (rc == BT_OK && se != cudaSuccess) rc = fail(c, BT_ERR_CUDA, "tc attention: %s", cudaGetErrorString(se));
+    if (p) tc_attn_plan_destroy(p);
+  } else {
+    launch_pack_qkv_test(q_dev, k_dev, v_dev, qkv, nullptr, 0, seqs, L, heads, 1.0f, 0, st);
+    launch_attn_time_simt(static_cast<const float*>(qkv), gates, o_dev, seqs, L, heads, st);
+    cudaError_t se = cudaStreamSynchronize(st);
+    if (se != cudaSuccess) rc = fail(c, BT_ERR_CUDA, "simt attention: %s", cudaGetErrorString(se));
+  }
+  c->launches += 2;
+  cudaFree(qkv); cudaFree(o); cudaFree(gates);
+  if (vt) cudaFree(vt);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+// Internal kernel-launcher interface shared by the .cu files of libbeatthis_sm100.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bt {
+
+constexpr int kHeadDim = 32;
+constexpr int kMaxSlabs = 6;
+
+// A GEMM over "planes": output row m = p_out * L + t.  The A operand row for slab s is
+//   plane = p_out * plane_mul + plane_add[s],  time = t + t_shift[s]   (zero when time is
+// outside [0, L)), columns [0, Kslab) of a row-major [planes_in * L, lda] activation.
+// Plain linear: nslab 1.  Conv2d k(2,3) s(2,1) p(0,1): nslab 6 (df,dt).  frontend.linear
+// over "b c f t -> b t (c f)": nslab 4 (f).  W is [N, nslab * Kslab] row-major.
+struct GemmShape {
+  int planes_out;
+  int L;
+  int N;
+  int Kslab;
+  int nslab;
+  int plane_mul;
+  int plane_add[kMaxSlabs];
+  int t_shift[kMaxSlabs];
+  int lda;
+};
+
+// Epilogue description (shared by the fp32 CUDA-core GEMM and the bf16 tcgen05 GEMM).
+struct EpiParams {
+  int kind;            // 0 generic, 1 qkv (RoPE + scaling + optional V transpose)
+  const float* bias;   // [N] or null
+  int gelu;            // exact-erf GELU after bias
+  const float* resid;  // fp32 [M, ldr] added after activation (may alias out_f32) or null
+  int ldr;
+  float* out_f32;      // optional fp32 output [M, ldo_f32]
+  int ldo_f32;
+  void* out_act;       // optional activation-dtype output [M, ldo_act]
+  int ldo_act;
+  // kind 1 (qkv): columns [0,C) q, [C,2C) k, [2C,3C) v, head h = (c % C) / 32
+  const float* rope_cos;  // [Lmax, 16]
+  const float* rope_sin;
+  int C;
+  int heads;
+  int posmode;  // 0: position = m % L (time attention)   1: position = (m / L) % F (freq attention)
+  int F;
+  float qscale;  // multiplied into q after RoPE
+  void* vt;      // when non-null V is written transposed: vt[((seq*heads + h)*32 + d) * vt_ld + t],
+  int vt_ld;     //   seq = m / L, t = m % L  (time attention, tensor-core path)
+};
+
+// ---- fp32 CUDA-core path -------------------------------------------------------------------
+void launch_gemm_simt(const float* A, const float* W, const GemmShape& g, const EpiParams& e,
+                      cudaStream_t st);
+// qkv [seqs*L, 3C] fp32 (q,k roped; q NOT pre-scaled) -> out [seqs*L, C] (gated)
+void launch_attn_time_simt(const float* qkv, const float* gates, float* out, int seqs, int L,
+                           int heads, cudaStream_t st);
+
+// ---- shared small kernels (templated on activation dtype inside) ---------------------------
+// frequency-direction attention: tokens m = (b*F + f)*L + t, sequences over f.
+void launch_attn_freq(const void* qkv, const float* gates, void* out, int B, int F, int L,
+                      int heads, float scale, int act_bf16, cudaStream_t st);
+// RMSNorm without gamma (folded into the next weight) + optional sigmoid gates.
+void launch_norm_gates(const float* x, void* xn, float* gates, const float* wg, const float* bg,
+                       int64_t M, int C, int heads, int act_bf16, cudaStream_t st);
+// per-chunk source description for the stem (chunk gather from per-clip spectrograms)
+struct ChunkSrc {
+  int64_t frame_base;  // first frame of the clip inside the concatenated spectrogram
+  int32_t T;           // frames in the clip
+  int32_t start;       // chunk start frame (may be negative)
+  int64_t out_base;    // first frame of the clip inside the concatenated outputs
+  int32_t write_lo;    // chunk-local frame range [write_lo, write_hi) this chunk owns
+  int32_t write_hi;
+};
+void launch_stem(const float* spect, const ChunkSrc* chunks, int nchunks, int L, const float* bn1_scale,
+                 const float* bn1_shift, const float* w, const float* bias, float* out,
+                 cudaStream_t st);
+void launch_head(const float* x, int D, const float* w, const float* b, const ChunkSrc* chunks,
+                 int nchunks, int L, float* beat, float* down, cudaStream_t st);
+void launch_logmel(const float* audio, const int64_t* sample_off_dev, const int64_t* frame_off_dev,
+                   int n_clips, int64_t total_frames, const float* window, const float* twiddle,
+                   const int32_t* fb_start, const int32_t* fb_ptr, const float* fb_w, float* spect,
+                   cudaStream_t st);
+void launch_peakpick(const float* beat, const float* down, const int64_t* frame_off_dev, int n_clips,
+                     double* beat_t, int32_t* n_beat, double* down_t, int32_t* n_down,
+                     int max_peaks, cudaStream_t st);
+void launch_f32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t st);
+void launch_bf16_to_f32(const void* in, float* out, int64_t n, cudaStream_t st);
+// [seqs, L, heads*32] fp32 q,k,v -> packed qkv buffer [seqs*L, 3C] of the activation dtype,
+// bf16 path: V transposed into vt.  (test hook for bt_debug_attention)
+void launch_pack_qkv_test(const float* q, const float* k, const float* v, void* qkv, void* vt,
+                          int vt_ld, int seqs, int L, int heads, float qscale, int act_bf16,
+                          cudaStream_t st);
+
+// ---- bf16 tcgen05 path ------------------------------------------------------------------------
+struct TcGemmPlan;  // cached tensor maps + launch geometry
+TcGemmPlan* tc_gemm_plan_create(const void* A_bf16, const void* W_bf16, const GemmShape& g,
+                                int planes_in, char* err, int errlen);
+void tc_gemm_plan_destroy(TcGemmPlan*);
+int launch_gemm_tc(const TcGemmPlan* plan, const EpiParams& e, cudaStream_t st);
+
+struct TcAttnPlan;
+TcAttnPlan* tc_attn_plan_create(const void* qkv_bf16, const void* vt_bf16, int vt_ld, int seqs, int L,
+                                int heads, char* err, int errlen);
+void tc_attn_plan_destroy(TcAttnPlan*);
+int launch_attn_time_tc(const TcAttnPlan* plan, const float* gates, void* out_bf16, cudaStream_t st);
+
+int tc_init(char* err, int errlen);  // resolves cuTensorMapEncodeTiled, sets smem attributes
+
+}  // namespace bt

@@ -1,0 +1,104 @@
+// GEMM epilogues shared by the fp32 CUDA-core GEMM and the bf16 tcgen05 GEMM.
+// A thread hands over CNT consecutive accumulator columns [n0, n0+CNT) of output row m.
+#pragma once
+#include "bt_kernels.h"
+#include "common.cuh"
+
+namespace bt {
+
+template <typename TAct, int CNT>
+__device__ __forceinline__ void store_act(TAct* p, const float (&v)[CNT]);
+
+template <>
+__device__ __forceinline__ void store_act<float, 4>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ void store_act<bf16, 4>(bf16* p, const float (&v)[4]) {
+  uint2 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+template <>
+__device__ __forceinline__ void store_act<float, 32>(float* p, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+template <>
+__device__ __forceinline__ void store_act<bf16, 32>(bf16* p, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+    reinterpret_cast<uint4*>(p)[i] = u;
+  }
+}
+
+// CNT in {4, 32}; n0 % CNT == 0; for kind 1 a head (32 columns) is never split across a
+// q/k/v boundary because C % 32 == 0.
+template <typename TAct, int CNT>
+__device__ __forceinline__ void epilogue_apply(const EpiParams& e, int L, int64_t m, int n0,
+                                               float (&v)[CNT]) {
+  if (e.kind == 0) {
+    if (e.bias) {
+#pragma unroll
+      for (int i = 0; i < CNT; ++i) v[i] += __ldg(e.bias + n0 + i);
+    }
+    if (e.gelu) {
+#pragma unroll
+      for (int i = 0; i < CNT; ++i) v[i] = gelu_erf(v[i]);
+    }
+    if (e.resid) {
+      const float4* r = reinterpret_cast<const float4*>(e.resid + m * e.ldr + n0);
+#pragma unroll
+      for (int i = 0; i < CNT / 4; ++i) {
+        float4 q = r[i];
+        v[4 * i] += q.x;
+        v[4 * i + 1] += q.y;
+        v[4 * i + 2] += q.z;
+        v[4 * i + 3] += q.w;
+      }
+    }
+    if (e.out_f32) store_act<float, CNT>(e.out_f32 + m * e.ldo_f32 + n0, v);
+    if (e.out_act) store_act<TAct, CNT>(reinterpret_cast<TAct*>(e.out_act) + m * e.ldo_act + n0, v);
+  } else {
+    // qkv: RoPE on interleaved pairs (rotary_embedding_torch semantics, reference
+    // roformer.py:121-123): out[2i] = x[2i] cos - x[2i+1] sin ; out[2i+1] = x[2i+1] cos + x[2i] sin
+    const int which = n0 / e.C;          // 0 q, 1 k, 2 v
+    const int c = n0 - which * e.C;      // column inside q/k/v
+    const int t = static_cast<int>(m % L);
+    if (which < 2) {
+      const int pos = e.posmode == 0 ? t : static_cast<int>((m / L) % e.F);
+      const int d0 = c & 31;             // first head-dim index handled here (even)
+      const float* cs = e.rope_cos + pos * 16 + (d0 >> 1);
+      const float* sn = e.rope_sin + pos * 16 + (d0 >> 1);
+      const float sc = which == 0 ? e.qscale : 1.0f;
+#pragma unroll
+      for (int i = 0; i < CNT / 2; ++i) {
+        const float co = __ldg(cs + i), si = __ldg(sn + i);
+        const float x0 = v[2 * i], x1 = v[2 * i + 1];
+        v[2 * i] = (x0 * co - x1 * si) * sc;
+        v[2 * i + 1] = (x1 * co + x0 * si) * sc;
+      }
+    }
+    if (which == 2 && e.vt) {
+      // transposed V for the tensor-core attention: consecutive lanes (= consecutive t) write
+      // consecutive addresses for a fixed d.
+      const int64_t seq = m / L;
+      const int h = c >> 5;
+      TAct* base = reinterpret_cast<TAct*>(e.vt) +
+                   ((seq * e.heads + h) * 32 + (c & 31)) * static_cast<int64_t>(e.vt_ld) + t;
+#pragma unroll
+      for (int i = 0; i < CNT; ++i) base[static_cast<int64_t>(i) * e.vt_ld] = to_out<TAct>(v[i]);
+    } else {
+      store_act<TAct, CNT>(reinterpret_cast<TAct*>(e.out_act) + m * e.ldo_act + n0, v);
+    }
+  }
+}
+
+}  // namespace bt

@@ -1,0 +1,519 @@
+// HBM-bound kernels of the path: log-mel frontend, stem conv, RMSNorm(+gates),
+// frequency-direction attention, head + aggregation scatter, peak picking.
+#include "bt_kernels.h"
+#include "common.cuh"
+
+namespace bt {
+
+// ------------------------------------------------------------------------------------------
+// log-mel: reference LogMelSpect.forward (beat_this/preprocessing.py:56-59) =
+//   torch.stft(n_fft 1024, hop 441, periodic hann, center reflect, normalized) -> abs ->
+//   mel filterbank (slaney, 128 bins, 30..11000 Hz) -> log1p(1000 x).
+// One CTA (128 threads) per frame: windowed frame -> 1024-point radix-2 FFT in shared
+// memory -> |X|/32 -> sparse triangular filterbank -> log1p.  Algorithmic HBM bytes:
+// 441 new samples * 4 B read + 128 * 4 B written per frame.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+logmel_kernel(const float* __restrict__ audio, const int64_t* __restrict__ sample_off,
+              const int64_t* __restrict__ frame_off, int n_clips, const float* __restrict__ window,
+              const float2* __restrict__ twiddle, const int32_t* __restrict__ fb_start,
+              const int32_t* __restrict__ fb_ptr, const float* __restrict__ fb_w,
+              float* __restrict__ spect) {
+  __shared__ float re[1024];
+  __shared__ float im[1024];
+  __shared__ float2 tw[512];
+  const int64_t frame = blockIdx.x;
+  // locate the clip (frame_off is ascending, n_clips+1 entries)
+  int lo = 0, hi = n_clips;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (frame_off[mid] <= frame) lo = mid; else hi = mid;
+  }
+  const int clip = lo;
+  const int64_t t = frame - frame_off[clip];
+  const int64_t s0 = sample_off[clip];
+  const int64_t len = sample_off[clip + 1] - s0;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 512; i += 128) tw[i] = twiddle[i];
+  for (int n = tid; n < 1024; n += 128) {
+    int64_t i = 441 * t + n - 512;
+    if (i < 0) i = -i;                       // reflect (no edge repeat), torch pad_mode="reflect"
+    if (i >= len) i = 2 * (len - 1) - i;
+    const float v = audio[s0 + i] * window[n];
+    const int r = __brev(static_cast<unsigned>(n)) >> 22;  // 10-bit reversal
+    re[r] = v;
+    im[r] = 0.f;
+  }
+  __syncthreads();
+  // decimation-in-time butterflies; stage s has half-span h = 2^s, twiddle index (j * 512/h)
+#pragma unroll 1
+  for (int s = 0; s < 10; ++s) {
+    const int h = 1 << s;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int idx = tid + b * 128;          // butterfly id 0..511
+      const int j = idx & (h - 1);
+      const int i0 = ((idx >> s) << (s + 1)) + j;
+      const int i1 = i0 + h;
+      const float2 w = tw[j << (9 - s)];      // (cos, -sin)
+      const float xr = re[i1], xi = im[i1];
+      const float tr = xr * w.x - xi * w.y;
+      const float ti = xr * w.y + xi * w.x;
+      const float ur = re[i0], ui = im[i0];
+      re[i0] = ur + tr; im[i0] = ui + ti;
+      re[i1] = ur - tr; im[i1] = ui - ti;
+    }
+    __syncthreads();
+  }
+  // magnitudes of bins 0..512 (normalized=True -> 1/sqrt(1024)); reuse re[] (im[512] for the Nyquist bin)
+  float mags[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int k = tid + b * 128;
+    mags[b] = sqrtf(re[k] * re[k] + im[k] * im[k]) * 0.03125f;
+  }
+  const float nyq = sqrtf(re[512] * re[512] + im[512] * im[512]) * 0.03125f;
+  __syncthreads();
+#pragma unroll
+  for (int b = 0; b < 4; ++b) re[tid + b * 128] = mags[b];
+  if (tid == 0) im[0] = nyq;  // bin 512 (never inside the 30..11000 Hz filters, kept for safety)
+  __syncthreads();
+  {
+    const int m = tid;  // mel bin
+    const int p0 = fb_ptr[m], p1 = fb_ptr[m + 1];
+    const int k0 = fb_start[m];
+    float acc = 0.f;
+    for (int p = p0; p < p1; ++p) {
+      const int k = k0 + (p - p0);
+      acc = fmaf(k < 512 ? re[k] : im[0], fb_w[p], acc);
+    }
+    spect[frame * 128 + m] = log1pf(1000.0f * acc);
+  }
+}
+
+void launch_logmel(const float* audio, const int64_t* sample_off_dev, const int64_t* frame_off_dev,
+                   int n_clips, int64_t total_frames, const float* window, const float* twiddle,
+                   const int32_t* fb_start, const int32_t* fb_ptr, const float* fb_w, float* spect,
+                   cudaStream_t st) {
+  if (total_frames <= 0) return;
+  logmel_kernel<<<static_cast<unsigned>(total_frames), 128, 0, st>>>(
+      audio, sample_off_dev, frame_off_dev, n_clips, window,
+      reinterpret_cast<const float2*>(twiddle), fb_start, fb_ptr, fb_w, spect);
+}
+
+// ------------------------------------------------------------------------------------------
+// stem: BN1d(128) -> Conv2d(1->32, k(4,3), s(4,1), p(0,1), no bias) -> BN2d -> GELU
+// (reference beat_tracker.py:108-126).  BN2d is folded into w/bias on the host; BN1d cannot
+// be folded (the conv's time padding is zero *after* BN1d) and is applied to each tap.
+// Chunks are gathered straight from the per-clip spectrograms (split_piece/zeropad,
+// inference.py:90-135): frames outside the clip are zero *before* BN1d.
+// out: [B, 32 f, L, 32 c] fp32.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+stem_kernel(const float* __restrict__ spect, const ChunkSrc* __restrict__ chunks, int L,
+            const float* __restrict__ bn1_scale, const float* __restrict__ bn1_shift,
+            const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out) {
+  __shared__ float ws[32 * 12];
+  __shared__ float bs[32];
+  for (int i = threadIdx.x; i < 32 * 12; i += 128) ws[i] = w[i];
+  if (threadIdx.x < 32) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  const int f = blockIdx.y;
+  const int b = blockIdx.z;
+  if (t >= L) return;
+  const ChunkSrc cs = chunks[b];
+  float in[4][3];
+#pragma unroll
+  for (int dt = 0; dt < 3; ++dt) {
+    const int tl = t + dt - 1;
+    const bool conv_ok = tl >= 0 && tl < L;
+    const int64_t fr = static_cast<int64_t>(cs.start) + tl;
+    const bool clip_ok = fr >= 0 && fr < cs.T;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (conv_ok && clip_ok)
+      v = *reinterpret_cast<const float4*>(spect + (cs.frame_base + fr) * 128 + 4 * f);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int df = 0; df < 4; ++df)
+      in[df][dt] = conv_ok ? fmaf(vv[df], bn1_scale[4 * f + df], bn1_shift[4 * f + df]) : 0.f;
+  }
+  float* op = out + ((static_cast<int64_t>(b) * 32 + f) * L + t) * 32;
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) {
+    float r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int co = c4 * 4 + i;
+      float a = bs[co];
+#pragma unroll
+      for (int df = 0; df < 4; ++df)
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) a = fmaf(in[df][dt], ws[co * 12 + df * 3 + dt], a);
+      r[i] = gelu_erf(a);
+    }
+    reinterpret_cast<float4*>(op)[c4] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+void launch_stem(const float* spect, const ChunkSrc* chunks, int nchunks, int L, const float* bn1_scale,
+                 const float* bn1_shift, const float* w, const float* bias, float* out,
+                 cudaStream_t st) {
+  dim3 grid(ceil_div(L, 128), 32, nchunks);
+  stem_kernel<<<grid, 128, 0, st>>>(spect, chunks, L, bn1_scale, bn1_shift, w, bias, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// RMSNorm (reference roformer.py:22-32: x / max(||x||, 1e-12) * sqrt(dim) * gamma; the
+// sqrt(dim)*gamma factor is folded into the consuming weights) and the attention gates
+// sigmoid(to_gates(x_normed)) (roformer.py:127-128).  One warp per token.
+// ------------------------------------------------------------------------------------------
+template <typename TAct, int C>
+__global__ void __launch_bounds__(256)
+norm_gates_kernel(const float* __restrict__ x, TAct* __restrict__ xn, float* __restrict__ gates,
+                  const float* __restrict__ wg, const float* __restrict__ bg, int64_t M, int heads) {
+  constexpr int PER = C / 32;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + row * C;
+  float v[PER];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    v[i] = xr[lane + 32 * i];
+    ss = fmaf(v[i], v[i], ss);
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    v[i] *= inv;
+    xn[row * C + lane + 32 * i] = to_out<TAct>(v[i]);
+  }
+  if (gates) {
+    for (int h = 0; h < heads; ++h) {
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) a = fmaf(v[i], __ldg(wg + h * C + lane + 32 * i), a);
+      a = warp_sum(a);
+      if (lane == 0) gates[row * heads + h] = sigmoidf_(a + bg[h]);
+    }
+  }
+}
+
+template <typename TAct>
+static void norm_gates_dispatch(const float* x, void* xn, float* gates, const float* wg,
+                                const float* bg, int64_t M, int C, int heads, cudaStream_t st) {
+  const unsigned grid = static_cast<unsigned>(ceil_div64(M, 8));
+  TAct* o = reinterpret_cast<TAct*>(xn);
+  switch (C) {
+    case 32: norm_gates_kernel<TAct, 32><<<grid, 256, 0, st>>>(x, o, gates, wg, bg, M, heads); break;
+    case 64: norm_gates_kernel<TAct, 64><<<grid, 256, 0, st>>>(x, o, gates, wg, bg, M, heads); break;
+    case 128: norm_gates_kernel<TAct, 128><<<grid, 256, 0, st>>>(x, o, gates, wg, bg, M, heads); break;
+    case 256: norm_gates_kernel<TAct, 256><<<grid, 256, 0, st>>>(x, o, gates, wg, bg, M, heads); break;
+    case 512: norm_gates_kernel<TAct, 512><<<grid, 256, 0, st>>>(x, o, gates, wg, bg, M, heads); break;
+    case 1024: norm_gates_kernel<TAct, 1024><<<grid, 256, 0, st>>>(x, o, gates, wg, bg, M, heads); break;
+    default: break;  // validated in bt_create
+  }
+}
+
+void launch_norm_gates(const float* x, void* xn, float* gates, const float* wg, const float* bg,
+                       int64_t M, int C, int heads, int act_bf16, cudaStream_t st) {
+  if (act_bf16) norm_gates_dispatch<bf16>(x, xn, gates, wg, bg, M, C, heads, st);
+  else norm_gates_dispatch<float>(x, xn, gates, wg, bg, M, C, heads, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// frequency-direction attention (PartialFTTransformer attnF, reference
+// beat_tracker.py:292-294): sequences of F <= 32 tokens over the frequency axis for every
+// (chunk, frame, head).  Token m = (b*F + f)*L + t.  One warp per (b, t, h); lane = f.
+// ------------------------------------------------------------------------------------------
+template <typename TAct>
+__global__ void __launch_bounds__(128)
+attn_freq_kernel(const TAct* __restrict__ qkv, const float* __restrict__ gates, TAct* __restrict__ out,
+                 int B, int F, int L, int heads, float scale) {
+  __shared__ float Ks[4][32][33];
+  __shared__ float Vs[4][32][33];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t grp = static_cast<int64_t>(blockIdx.x) * 4 + wib;
+  const int64_t ngrp = static_cast<int64_t>(B) * L * heads;
+  if (grp >= ngrp) return;  // warp-uniform
+  const int h = static_cast<int>(grp % heads);
+  const int64_t bt_ = grp / heads;
+  const int t = static_cast<int>(bt_ % L);
+  const int b = static_cast<int>(bt_ / L);
+  const int C = heads * 32;
+  const bool act = lane < F;
+  const int64_t m = (static_cast<int64_t>(b) * F + (act ? lane : 0)) * L + t;
+  const TAct* rp = qkv + m * 3 * C + h * 32;
+  float q[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) {
+    q[d] = to_f32(rp[d]) * scale;
+    Ks[wib][lane][d] = act ? to_f32(rp[C + d]) : 0.f;
+    Vs[wib][lane][d] = act ? to_f32(rp[2 * C + d]) : 0.f;
+  }
+  __syncwarp();
+  float s[32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float a = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) a = fmaf(q[d], Ks[wib][j][d], a);
+    s[j] = j < F ? a : -INFINITY;
+    mx = fmaxf(mx, s[j]);
+  }
+  float l = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    s[j] = expf(s[j] - mx);
+    l += s[j];
+  }
+  float o[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) o[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+#pragma unroll
+    for (int d = 0; d < 32; ++d) o[d] = fmaf(s[j], Vs[wib][j][d], o[d]);
+  }
+  if (act) {
+    const float g = gates[m * heads + h] / l;
+    TAct* op = out + m * C + h * 32;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) op[d] = to_out<TAct>(o[d] * g);
+  }
+}
+
+void launch_attn_freq(const void* qkv, const float* gates, void* out, int B, int F, int L, int heads,
+                      float scale, int act_bf16, cudaStream_t st) {
+  const int64_t ngrp = static_cast<int64_t>(B) * L * heads;
+  const unsigned grid = static_cast<unsigned>(ceil_div64(ngrp, 4));
+  if (act_bf16)
+    attn_freq_kernel<bf16><<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), gates,
+                                                   reinterpret_cast<bf16*>(out), B, F, L, heads, scale);
+  else
+    attn_freq_kernel<float><<<grid, 128, 0, st>>>(reinterpret_cast<const float*>(qkv), gates,
+                                                    reinterpret_cast<float*>(out), B, F, L, heads, scale);
+}
+
+// ------------------------------------------------------------------------------------------
+// head: final RMSNorm (roformer.py:174,180; gamma*sqrt(D) folded into w) -> Linear(D->2) ->
+// SumHead (beat = o0 + o1 in fp32, downbeat = o1; beat_tracker.py:315-330) -> scatter into
+// the per-clip frame arrays with aggregate_prediction's keep_first rule
+// (inference.py:138-185): each chunk owns the chunk-local frames [write_lo, write_hi).
+// One warp per token.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_kernel(const float* __restrict__ x, int D, const float* __restrict__ w, const float* __restrict__ bias,
+            const ChunkSrc* __restrict__ chunks, int nchunks, int L, float* __restrict__ beat,
+            float* __restrict__ down) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= static_cast<int64_t>(nchunks) * L) return;
+  const int b = static_cast<int>(row / L), t = static_cast<int>(row % L);
+  const ChunkSrc cs = chunks[b];
+  if (t < cs.write_lo || t >= cs.write_hi) return;  // warp-uniform
+  const float* xr = x + row * D;
+  float ss = 0.f, a0 = 0.f, a1 = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    const float v = xr[i];
+    ss = fmaf(v, v, ss);
+    a0 = fmaf(v, __ldg(w + i), a0);
+    a1 = fmaf(v, __ldg(w + D + i), a1);
+  }
+  ss = warp_sum(ss); a0 = warp_sum(a0); a1 = warp_sum(a1);
+  if (lane == 0) {
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    const float o0 = a0 * inv + bias[0], o1 = a1 * inv + bias[1];
+    const int64_t fr = cs.out_base + cs.start + t;
+    beat[fr] = o0 + o1;
+    down[fr] = o1;
+  }
+}
+
+void launch_head(const float* x, int D, const float* w, const float* b, const ChunkSrc* chunks,
+                 int nchunks, int L, float* beat, float* down, cudaStream_t st) {
+  const int64_t rows = static_cast<int64_t>(nchunks) * L;
+  head_kernel<<<static_cast<unsigned>(ceil_div64(rows, 8)), 256, 0, st>>>(x, D, w, b, chunks, nchunks, L,
+                                                                           beat, down);
+}
+
+// ------------------------------------------------------------------------------------------
+// minimal postprocessor (reference model/postprocessor.py:85-136, deduplicate_peaks
+// :176-197): peak <=> x[t] == max(x[t-3..t+3]) and x[t] > 0; runs of peaks at most one
+// frame from the running mean are merged into the running mean (float64, like the Python
+// loop); times = frame / 50; every downbeat snaps to the nearest beat (first argmin); unique.
+// One CTA per clip: ordered compaction by ballot/prefix, then the short sequential part.
+// ------------------------------------------------------------------------------------------
+__device__ int compact_peaks(const float* __restrict__ x, int T, double* __restrict__ frames, int cap,
+                             int* s_warp, int* s_base) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) *s_base = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < T; t0 += 256) {
+    const int t = t0 + tid;
+    bool pk = false;
+    if (t < T) {
+      const float v = x[t];
+      float mx = v;
+#pragma unroll
+      for (int d = -3; d <= 3; ++d) {
+        const int u = t + d;
+        if (u >= 0 && u < T) mx = fmaxf(mx, x[u]);
+      }
+      pk = (v == mx) && (v > 0.f);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, pk);
+    if (lane == 0) s_warp[wid] = __popc(bal);
+    __syncthreads();
+    int off = *s_base;
+    for (int w = 0; w < wid; ++w) off += s_warp[w];
+    if (pk) {
+      const int idx = off + __popc(bal & ((1u << lane) - 1));
+      if (idx < cap) frames[idx] = static_cast<double>(t);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += s_warp[w];
+      *s_base += tot;
+    }
+    __syncthreads();
+  }
+  return *s_base;
+}
+
+__device__ int dedup_to_times(double* p, int n) {
+  // deduplicate_peaks(width=1) followed by / fps; in place (output index <= input index)
+  if (n == 0) return 0;
+  int out = 0;
+  double cur = p[0];
+  double c = 1.0;
+  for (int i = 1; i < n; ++i) {
+    const double p2 = p[i];
+    if (p2 - cur <= 1.0) {
+      c += 1.0;
+      cur += (p2 - cur) / c;
+    } else {
+      p[out++] = cur / 50.0;
+      cur = p2;
+      c = 1.0;
+    }
+  }
+  p[out++] = cur / 50.0;
+  return out;
+}
+
+__global__ void __launch_bounds__(256)
+peakpick_kernel(const float* __restrict__ beat, const float* __restrict__ down,
+                const int64_t* __restrict__ frame_off, double* __restrict__ beat_t, int32_t* __restrict__ n_beat,
+                double* __restrict__ down_t, int32_t* __restrict__ n_down, int max_peaks) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const int clip = blockIdx.x;
+  const int64_t f0 = frame_off[clip];
+  const int T = static_cast<int>(frame_off[clip + 1] - f0);
+  double* bt_ = beat_t + static_cast<int64_t>(clip) * max_peaks;
+  double* dt_ = down_t + static_cast<int64_t>(clip) * max_peaks;
+  const int nb_raw = compact_peaks(beat + f0, T, bt_, max_peaks, s_warp, &s_base);
+  __syncthreads();
+  const int nd_raw = compact_peaks(down + f0, T, dt_, max_peaks, s_warp, &s_base);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (nb_raw > max_peaks || nd_raw > max_peaks) {  // overflow: report, host retries bigger
+      n_beat[clip] = nb_raw;
+      n_down[clip] = nd_raw;
+      return;
+    }
+    const int nb = dedup_to_times(bt_, nb_raw);
+    int nd = dedup_to_times(dt_, nd_raw);
+    if (nb > 0) {
+      for (int i = 0; i < nd; ++i) {
+        const double d = dt_[i];
+        int best = 0;
+        double bd = fabs(bt_[0] - d);
+        for (int j = 1; j < nb; ++j) {
+          const double dd = fabs(bt_[j] - d);
+          if (dd < bd) { bd = dd; best = j; }
+        }
+        dt_[i] = bt_[best];
+      }
+    }
+    // np.unique: sort + drop duplicates (snapped downbeats are non-decreasing; insertion sort is a no-op then)
+    for (int i = 1; i < nd; ++i) {
+      const double v = dt_[i];
+      int j = i - 1;
+      while (j >= 0 && dt_[j] > v) { dt_[j + 1] = dt_[j]; --j; }
+      dt_[j + 1] = v;
+    }
+    int o = 0;
+    for (int i = 0; i < nd; ++i)
+      if (o == 0 || dt_[i] != dt_[o - 1]) dt_[o++] = dt_[i];
+    nd = o;
+    n_beat[clip] = nb;
+    n_down[clip] = nd;
+  }
+}
+
+void launch_peakpick(const float* beat, const float* down, const int64_t* frame_off_dev, int n_clips,
+                     double* beat_t, int32_t* n_beat, double* down_t, int32_t* n_down, int max_peaks,
+                     cudaStream_t st) {
+  if (n_clips <= 0) return;
+  peakpick_kernel<<<n_clips, 256, 0, st>>>(beat, down, frame_off_dev, beat_t, n_beat, down_t, n_down,
+                                           max_peaks);
+}
+
+// ------------------------------------------------------------------------------------------ utils
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+void launch_f32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t st) {
+  if (n <= 0) return;
+  f32_to_bf16_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, st>>>(in, reinterpret_cast<bf16*>(out), n);
+}
+void launch_bf16_to_f32(const void* in, float* out, int64_t n, cudaStream_t st) {
+  if (n <= 0) return;
+  bf16_to_f32_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, st>>>(reinterpret_cast<const bf16*>(in), out, n);
+}
+
+template <typename TAct>
+__global__ void pack_qkv_test_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                     const float* __restrict__ v, TAct* __restrict__ qkv, TAct* __restrict__ vt,
+                                     int vt_ld, int seqs, int L, int heads, float qscale) {
+  const int C = heads * 32;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t n = static_cast<int64_t>(seqs) * L * C;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % C);
+  const int64_t m = i / C;
+  qkv[m * 3 * C + c] = to_out<TAct>(q[i] * qscale);
+  qkv[m * 3 * C + C + c] = to_out<TAct>(k[i]);
+  if (vt) {
+    const int64_t seq = m / L;
+    const int t = static_cast<int>(m % L);
+    vt[((seq * heads + (c >> 5)) * 32 + (c & 31)) * vt_ld + t] = to_out<TAct>(v[i]);
+  } else {
+    qkv[m * 3 * C + 2 * C + c] = to_out<TAct>(v[i]);
+  }
+}
+void launch_pack_qkv_test(const float* q, const float* k, const float* v, void* qkv, void* vt, int vt_ld,
+                          int seqs, int L, int heads, float qscale, int act_bf16, cudaStream_t st) {
+  const int64_t n = static_cast<int64_t>(seqs) * L * heads * 32;
+  const unsigned grid = static_cast<unsigned>(ceil_div64(n, 256));
+  if (act_bf16)
+    pack_qkv_test_kernel<bf16><<<grid, 256, 0, st>>>(q, k, v, reinterpret_cast<bf16*>(qkv),
+                                                       reinterpret_cast<bf16*>(vt), vt_ld, seqs, L, heads, qscale);
+  else
+    pack_qkv_test_kernel<float><<<grid, 256, 0, st>>>(q, k, v, reinterpret_cast<float*>(qkv),
+                                                        reinterpret_cast<float*>(vt), vt_ld, seqs, L, heads, qscale);
+}
+
+}  // namespace bt

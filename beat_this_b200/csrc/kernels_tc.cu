@@ -1,0 +1,523 @@
+// bf16 tensor-core path (BT_DTYPE_BF16) for sm_100a: tcgen05.mma with TMEM accumulators,
+// TMA (cp.async.bulk.tensor) operand staging through an mbarrier ring, warp-specialised
+// roles.  Two kernels:
+//   gemm_tc_kernel  -- D = A * W^T over "planes" with shifted slabs (linear layers, the
+//                      k(2,3) frontend convolutions as implicit GEMM, frontend.linear),
+//                      persistent over output tiles, fused epilogues (epilogue.cuh).
+//   attn_tc_kernel  -- flash attention for head_dim 32 over sequences of up to 1500 frames
+//                      (time-direction attention of the frontend and the 6 main layers).
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "epilogue.cuh"
+
+namespace bt {
+
+// --------------------------------------------------------------------------- tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+static bool make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, int swizzle_bytes,
+                      char* err, int errlen) {
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx,
+                        es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu box %u,%u,%u stride0 %llu",
+             static_cast<int>(r), rank, (unsigned long long)gd[0], (unsigned long long)(rank > 1 ? gd[1] : 0),
+             (unsigned long long)(rank > 2 ? gd[2] : 0), bx[0], rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0,
+             (unsigned long long)gs[0]);
+    return false;
+  }
+  return true;
+}
+
+// =============================================================================== GEMM
+constexpr int TG_BM = 128;
+constexpr int TG_EPI_WARPS = 8;
+constexpr int TG_THREADS = 64 + 32 * TG_EPI_WARPS;  // warp0 TMA, warp1 MMA, 8 epilogue warps
+
+template <int BN, int BK>
+struct TgCfg {
+  static constexpr int A_BYTES = TG_BM * BK * 2;
+  static constexpr int W_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
+  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+  static constexpr int TCOLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SWZ = BK * 2;  // 128 or 64 byte rows
+};
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(TG_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const GemmShape g, const EpiParams e, int num_tiles, int t_tiles, int n_tiles) {
+  using Cfg = TgCfg<BN, BK>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TG_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TCOLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int kb_per_slab = g.Kslab / BK;
+  const int num_kb = g.nslab * kb_per_slab;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+        const int p_out = mt / t_tiles;
+        const int t0 = (mt - p_out * t_tiles) * TG_BM;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int s = kb / kb_per_slab;
+          const int k0 = (kb - s * kb_per_slab) * BK;
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          tma_load_3d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], k0, t0 + g.t_shift[s],
+                      p_out * g.plane_mul + g.plane_add[s]);
+          tma_load_2d(sW + stage * Cfg::W_BYTES, &tmW, &full[stage], s * g.Kslab + k0, nt * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TG_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b_base = smem_u32(sW + stage * Cfg::W_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16(d_tmem, make_kmajor_desc<Cfg::SWZ>(a_base + k * 32),
+                      make_kmajor_desc<Cfg::SWZ>(b_base + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (kb == num_kb - 1) umma_commit(&tfull[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = ew >> 2;
+    constexpr int NCH = BN / 32;
+    constexpr int SPLIT = (NCH + 1) / 2;
+    const int c_begin = half == 0 ? 0 : SPLIT;
+    const int c_end = half == 0 ? SPLIT : NCH;
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      const int p_out = mt / t_tiles;
+      const int t = (mt - p_out * t_tiles) * TG_BM + row;
+      const bool valid = t < g.L;
+      const int64_t m = static_cast<int64_t>(p_out) * g.L + t;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      for (int c = c_begin; c < c_end; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, r);
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          epilogue_apply<bf16, 32>(e, g.L, m, nt * BN + c * 32, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::TCOLS>(tmem_base);
+}
+
+struct TcGemmPlan {
+  CUtensorMap tmA, tmW;
+  GemmShape g;
+  int BN, BK;
+  int num_tiles, t_tiles, n_tiles, grid;
+};
+
+static int g_num_sms = 148;
+
+static int pick_bn(int N) {
+  const int cands[6] = {256, 192, 128, 96, 64, 32};
+  for (int i = 0; i < 6; ++i)
+    if (N % cands[i] == 0) return cands[i];
+  return 0;
+}
+
+template <int BN, int BK>
+static int gemm_tc_launch(const TcGemmPlan* p, const EpiParams& e, cudaStream_t st) {
+  using Cfg = TgCfg<BN, BK>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t r = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (r != cudaSuccess) return -1;
+    attr_set = true;
+  }
+  gemm_tc_kernel<BN, BK><<<p->grid, TG_THREADS, Cfg::SMEM, st>>>(p->tmA, p->tmW, p->g, e, p->num_tiles,
+                                                                   p->t_tiles, p->n_tiles);
+  return 0;
+}
+
+TcGemmPlan* tc_gemm_plan_create(const void* A, const void* W, const GemmShape& g, int planes_in, char* err,
+                                int errlen) {
+  TcGemmPlan* p = new TcGemmPlan();
+  p->g = g;
+  p->BK = (g.Kslab % 64 == 0) ? 64 : 32;
+  p->BN = pick_bn(g.N);
+  if (p->BN == 0 || g.Kslab % 32 != 0 || (p->BK == 32 && p->BN > 128)) {
+    snprintf(err, errlen, "tc gemm: unsupported shape N=%d Kslab=%d", g.N, g.Kslab);
+    delete p;
+    return nullptr;
+  }
+  const int swz = p->BK * 2;
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(g.Kslab), static_cast<uint64_t>(g.L),
+                              static_cast<uint64_t>(planes_in)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(g.lda) * 2, static_cast<uint64_t>(g.L) * g.lda * 2};
+    const uint32_t box[3] = {static_cast<uint32_t>(p->BK), TG_BM, 1};
+    if (!make_tmap(&p->tmA, A, 3, dims, strides, box, swz, err, errlen)) { delete p; return nullptr; }
+  }
+  {
+    const uint64_t Ktot = static_cast<uint64_t>(g.Kslab) * g.nslab;
+    const uint64_t dims[2] = {Ktot, static_cast<uint64_t>(g.N)};
+    const uint64_t strides[1] = {Ktot * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(p->BK), static_cast<uint32_t>(p->BN)};
+    if (!make_tmap(&p->tmW, W, 2, dims, strides, box, swz, err, errlen)) { delete p; return nullptr; }
+  }
+  p->t_tiles = ceil_div(g.L, TG_BM);
+  p->n_tiles = g.N / p->BN;
+  p->num_tiles = p->t_tiles * g.planes_out * p->n_tiles;
+  p->grid = p->num_tiles < g_num_sms ? p->num_tiles : g_num_sms;
+  return p;
+}
+void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
+
+int launch_gemm_tc(const TcGemmPlan* p, const EpiParams& e, cudaStream_t st) {
+#define BT_TG_CASE(bn, bk) \
+  if (p->BN == bn && p->BK == bk) return gemm_tc_launch<bn, bk>(p, e, st);
+  BT_TG_CASE(256, 64) BT_TG_CASE(192, 64) BT_TG_CASE(128, 64) BT_TG_CASE(96, 64) BT_TG_CASE(64, 64)
+  BT_TG_CASE(32, 64) BT_TG_CASE(128, 32) BT_TG_CASE(96, 32) BT_TG_CASE(64, 32) BT_TG_CASE(32, 32)
+#undef BT_TG_CASE
+  return -2;
+}
+
+// ========================================================================== attention
+// One CTA per (sequence, head, 128-query tile).  Warps 0-3: softmax (one query row per
+// thread, the tcgen05.ld 32x32b lane mapping); warp 4 lane 0: TMA producer + MMA issuer.
+//   S = Q K^T      : A = Q  [128 x 32] (SW64), B = K tile [128 keys x 32] (SW64) -> TMEM cols [0,128)
+//   O_j = P_j V_j  : A = P  [128 x 128] bf16 written by the softmax threads in the SW128
+//                    K-major layout, B = V^T tile [32 x 128 keys] (SW128) -> TMEM cols 128+32*(j%2)
+// The running output lives in registers (o = o*alpha + O_j), so TMEM is never read-modify-
+// written.  q is pre-scaled by log2(e)/sqrt(32) in the QKV GEMM epilogue -> exp2 softmax.
+constexpr int AT_BQ = 128, AT_BKV = 128;
+constexpr int AT_THREADS = 160;
+constexpr int AT_SQ = 8192, AT_SK = 8192, AT_SV = 8192, AT_SP = 32768;
+constexpr int AT_SMEM = AT_SQ + 2 * AT_SK + 2 * AT_SV + 2 * AT_SP + 1024 + 128;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVt,
+               const float* __restrict__ gates, bf16* __restrict__ out, int L, int heads) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + AT_SQ;
+  uint8_t* sV = sK + 2 * AT_SK;
+  uint8_t* sP = sV + 2 * AT_SV;
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sP + 2 * AT_SP);
+  uint64_t* bar_kv = bar_q + 1;  // [2]
+  uint64_t* bar_s = bar_kv + 2;
+  uint64_t* bar_p = bar_s + 1;   // [2]
+  uint64_t* bar_o = bar_p + 2;   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_o + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_BQ;
+  const int h = blockIdx.y;
+  const int seq = blockIdx.z;
+  const int C = heads * 32;
+  const int nkv = ceil_div(L, AT_BKV);
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQK);
+    tma_prefetch_desc(&tmVt);
+    mbar_init(bar_q, 1);
+    mbar_init(&bar_kv[0], 1); mbar_init(&bar_kv[1], 1);
+    mbar_init(bar_s, 1);
+    mbar_init(&bar_p[0], 128); mbar_init(&bar_p[1], 128);
+    mbar_init(&bar_o[0], 1); mbar_init(&bar_o[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<256>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 32);
+      auto load_kv = [&](int j) {
+        const int st = j & 1;
+        mbar_expect_tx(&bar_kv[st], AT_SK + AT_SV);
+        tma_load_3d(sK + st * AT_SK, &tmQK, &bar_kv[st], C + h * 32, j * AT_BKV, seq);
+        tma_load_2d(sV + st * AT_SV, &tmVt, &bar_kv[st], j * AT_BKV, (seq * heads + h) * 32);
+        tma_load_2d(sV + st * AT_SV + 4096, &tmVt, &bar_kv[st], j * AT_BKV + 64, (seq * heads + h) * 32);
+      };
+      auto issue_s = [&](int j) {
+        const uint32_t a = smem_u32(sQ), b = smem_u32(sK + (j & 1) * AT_SK);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          umma_bf16(tmem_base, make_kmajor_desc<64>(a + k * 32), make_kmajor_desc<64>(b + k * 32), idesc_s,
+                    k != 0 ? 1u : 0u);
+        umma_commit(bar_s);
+      };
+      mbar_expect_tx(bar_q, AT_SQ);
+      tma_load_3d(sQ, &tmQK, bar_q, h * 32, q0, seq);
+      load_kv(0);
+      if (nkv > 1) load_kv(1);
+      mbar_wait(bar_q, 0);
+      mbar_wait(&bar_kv[0], 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&bar_p[st], ph);  // P_j written, S_j consumed
+        tc_fence_after();
+        if (j + 1 < nkv) {
+          mbar_wait(&bar_kv[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(j + 1);
+        }
+        const uint32_t pa = smem_u32(sP + st * AT_SP), vb = smem_u32(sV + st * AT_SV);
+        const uint32_t d_o = tmem_base + 128 + st * 32;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t aoff = (k >> 2) * 16384 + (k & 3) * 32;
+          const uint32_t boff = (k >> 2) * 4096 + (k & 3) * 32;
+          umma_bf16(d_o, make_kmajor_desc<128>(pa + aoff), make_kmajor_desc<128>(vb + boff), idesc_o,
+                    k != 0 ? 1u : 0u);
+        }
+        umma_commit(&bar_o[st]);
+        if (j + 2 < nkv) {
+          mbar_wait(&bar_o[st], ph);  // PV_j done -> K/V stage reusable
+          load_kv(j + 2);
+        }
+      }
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    float o[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) o[d] = 0.f;
+    float m_run = -INFINITY, m_ref = -INFINITY, l = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j & 1;
+      mbar_wait(bar_s, j & 1);
+      tc_fence_after();
+      float s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_base + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(r[i]);
+      }
+      if (j == nkv - 1) {
+        const int lim = L - j * AT_BKV;  // keys >= lim are padding
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= lim) s[i] = -INFINITY;
+      }
+      float mx = s[0];
+#pragma unroll
+      for (int i = 1; i < 128; ++i) mx = fmaxf(mx, s[i]);
+      const float m_prev = m_run;
+      const float m_new = fmaxf(m_run, mx);
+      float sum = 0.f;
+      uint8_t* prow = sP + st * AT_SP + row * 128;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 keys (16 bytes of bf16)
+        float p[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          p[i] = ex2_approx(s[c * 8 + i] - m_new);
+          sum += p[i];
+        }
+        uint4 u;
+        u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
+        u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
+        *reinterpret_cast<uint4*>(prow + (c >> 3) * 16384 + (((c & 7) ^ (row & 7)) << 4)) = u;
+      }
+      l = l * ex2_approx(m_prev - m_new) + sum;
+      m_run = m_new;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&bar_p[st]);
+      if (j >= 1) {  // deferred accumulate of tile j-1 (its P was relative to m_prev)
+        const int so = (j - 1) & 1;
+        mbar_wait(&bar_o[so], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_base + 128 + so * 32, r);
+        tmem_ld_wait();
+        const float a = ex2_approx(m_ref - m_prev);
+#pragma unroll
+        for (int d = 0; d < 32; ++d) o[d] = fmaf(o[d], a, __uint_as_float(r[d]));
+        m_ref = m_prev;
+      }
+    }
+    {
+      const int so = (nkv - 1) & 1;
+      mbar_wait(&bar_o[so], ((nkv - 1) >> 1) & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_base + 128 + so * 32, r);
+      tmem_ld_wait();
+      const float a = ex2_approx(m_ref - m_run);
+#pragma unroll
+      for (int d = 0; d < 32; ++d) o[d] = fmaf(o[d], a, __uint_as_float(r[d]));
+    }
+    const int q = q0 + row;
+    if (q < L) {
+      const int64_t m = static_cast<int64_t>(seq) * L + q;
+      const float gsc = gates[m * heads + h] / l;
+      float v[32];
+#pragma unroll
+      for (int d = 0; d < 32; ++d) v[d] = o[d] * gsc;
+      store_act<bf16, 32>(out + m * C + h * 32, v);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<256>(tmem_base);
+}
+
+struct TcAttnPlan {
+  CUtensorMap tmQK, tmVt;
+  int seqs, L, heads;
+};
+
+TcAttnPlan* tc_attn_plan_create(const void* qkv, const void* vt, int vt_ld, int seqs, int L, int heads,
+                                char* err, int errlen) {
+  TcAttnPlan* p = new TcAttnPlan();
+  p->seqs = seqs; p->L = L; p->heads = heads;
+  const int C = heads * 32;
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(3 * C), static_cast<uint64_t>(L), static_cast<uint64_t>(seqs)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(3 * C) * 2, static_cast<uint64_t>(L) * 3 * C * 2};
+    const uint32_t box[3] = {32, AT_BQ, 1};
+    if (!make_tmap(&p->tmQK, qkv, 3, dims, strides, box, 64, err, errlen)) { delete p; return nullptr; }
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(L), static_cast<uint64_t>(seqs) * heads * 32};
+    const uint64_t strides[1] = {static_cast<uint64_t>(vt_ld) * 2};
+    const uint32_t box[2] = {64, 32};
+    if (!make_tmap(&p->tmVt, vt, 2, dims, strides, box, 128, err, errlen)) { delete p; return nullptr; }
+  }
+  return p;
+}
+void tc_attn_plan_destroy(TcAttnPlan* p) { delete p; }
+
+int launch_attn_time_tc(const TcAttnPlan* p, const float* gates, void* out, cudaStream_t st) {
+  dim3 grid(ceil_div(p->L, AT_BQ), p->heads, p->seqs);
+  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(p->tmQK, p->tmVt, gates, reinterpret_cast<bf16*>(out), p->L,
+                                                    p->heads);
+  return 0;
+}
+
+int tc_init(char* err, int errlen) {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t r = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (r != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+      snprintf(err, errlen, "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(r));
+      return -1;
+    }
+    g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaError_t r = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+  if (r != cudaSuccess) {
+    snprintf(err, errlen, "cudaFuncSetAttribute(attn_tc_kernel) failed: %s", cudaGetErrorString(r));
+    return -1;
+  }
+  return 0;
+}
+
+}  // namespace bt

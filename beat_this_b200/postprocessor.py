@@ -1,0 +1,84 @@
+"""Postprocessor mirror (reference beat_this/model/postprocessor.py:9-197).
+
+``type="minimal"``: peak picking (max-pool 7 equality and logit > 0), adjacent-peak merging,
+downbeat snapping and ``np.unique`` all run in one device kernel (``bt_peakpick``); only the
+final timestamp arrays come back to the host.  ``type="dbn"``: the madmom DBN stays on the
+host exactly as in the reference (postprocessor.py:138-173) and needs ``madmom`` installed.
+"""
+from __future__ import annotations
+
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import torch
+
+
+class Postprocessor:
+    def __init__(self, type: str = "minimal", fps: int = 50, engine=None, device="cuda"):
+        assert type in ["minimal", "dbn"]
+        self.type = type
+        self.fps = fps
+        if fps != 50:
+            raise NotImplementedError("the device peak picker is built for the reference's 50 fps")
+        if type == "dbn":
+            from madmom.features.downbeats import DBNDownBeatTrackingProcessor
+
+            self.dbn = DBNDownBeatTrackingProcessor(
+                beats_per_bar=[3, 4], min_bpm=55.0, max_bpm=215.0, fps=self.fps, transition_lambda=100
+            )
+        if engine is None:
+            from .engine import Engine
+
+            engine = Engine.mel_only(device)  # a weight-less context is enough for bt_peakpick
+        self.engine = engine
+
+    def __call__(self, beat: torch.Tensor, downbeat: torch.Tensor, padding_mask: torch.Tensor | None = None):
+        """Works with batched ([B,T]) and unbatched ([T]) logits like the reference; returns
+        (beat_times, downbeat_times) or tuples of them for batched input."""
+        batched = beat.ndim != 1
+        if not batched:
+            beat, downbeat = beat.unsqueeze(0), downbeat.unsqueeze(0)
+            if padding_mask is not None:
+                padding_mask = padding_mask.unsqueeze(0)
+        dev = self.engine.device
+        beat = torch.as_tensor(beat, device=dev).float()
+        downbeat = torch.as_tensor(downbeat, device=dev).float()
+        if padding_mask is None:
+            lengths = [beat.shape[1]] * beat.shape[0]
+        else:
+            # the reference truncates each piece to its un-padded frames (postprocessor.py:116-117);
+            # padding is trailing by construction
+            lengths = [int(m.sum()) for m in padding_mask.to(torch.bool).cpu()]
+        fo = [0]
+        for n in lengths:
+            fo.append(fo[-1] + n)
+        bcat = torch.cat([beat[i, :n] for i, n in enumerate(lengths)]).contiguous()
+        dcat = torch.cat([downbeat[i, :n] for i, n in enumerate(lengths)]).contiguous()
+        res = self.batch_cat(bcat, dcat, fo)
+        if not batched:
+            return res[0]
+        return tuple(r[0] for r in res), tuple(r[1] for r in res)
+
+    def batch_cat(self, beat: torch.Tensor, downbeat: torch.Tensor, frame_offsets):
+        """Concatenated logits of many clips -> list of (beat_times, downbeat_times)."""
+        if self.type == "minimal":
+            return self.engine.peakpick_cat(beat, downbeat, frame_offsets)
+        return self._postp_dbn(beat, downbeat, frame_offsets)
+
+    def _postp_dbn(self, beat, downbeat, frame_offsets):
+        # reference postprocessor.py:138-173 (host, float64)
+        bp = beat.double().sigmoid().cpu().numpy()
+        dp = downbeat.double().sigmoid().cpu().numpy()
+        eps = 1e-5
+        bp = bp * (1 - eps) + eps / 2
+        dp = dp * (1 - eps) + eps / 2
+
+        def item(i):
+            b = bp[frame_offsets[i] : frame_offsets[i + 1]]
+            d = dp[frame_offsets[i] : frame_offsets[i + 1]]
+            act = np.vstack((np.maximum(b - d, eps / 2), d)).T
+            out = self.dbn(act)
+            return out[:, 0], out[out[:, 1] == 1][:, 0]
+
+        with ThreadPoolExecutor() as ex:
+            return list(ex.map(item, range(len(frame_offsets) - 1)))

@@ -1,0 +1,153 @@
+"""Audio loading and the log-mel frontend (mirror of reference beat_this/preprocessing.py).
+
+``LogMelSpect`` keeps the reference's constructor defaults and call signature
+(preprocessing.py:27-59) but runs the fused sm_100a kernel (frame -> Hann -> 1024-point FFT
+-> |.| -> 128-band slaney mel -> log1p(1000 x)) through ``bt_logmel``.
+``load_audio`` (preprocessing.py:6-24) reads PCM/float WAV files with the standard library /
+scipy (torchaudio's decoder backends, soundfile and madmom are not available offline).
+"""
+from __future__ import annotations
+
+import math
+import wave
+
+import numpy as np
+import torch
+
+SAMPLE_RATE = 22050
+N_FFT = 1024
+HOP = 441
+N_MELS = 128
+F_MIN = 30.0
+F_MAX = 11000.0
+
+
+def load_audio(path, dtype="float64"):
+    """Returns (waveform[time] or [time, channels], samplerate); float in [-1, 1) like
+    torchaudio/soundfile (reference preprocessing.py:6-24)."""
+    try:
+        try:
+            from scipy.io import wavfile
+
+            sr, data = wavfile.read(str(path))
+            if data.dtype == np.int16:
+                wav = data.astype(dtype) / 32768.0
+            elif data.dtype == np.int32:
+                wav = data.astype(dtype) / 2147483648.0
+            elif data.dtype == np.uint8:
+                wav = (data.astype(dtype) - 128.0) / 128.0
+            else:
+                wav = data.astype(dtype)
+            return wav, int(sr)
+        except Exception:
+            with wave.open(str(path), "rb") as w:
+                sr, nch, sw, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
+                raw = w.readframes(n)
+            if sw == 2:
+                wav = np.frombuffer(raw, dtype="<i2").astype(dtype) / 32768.0
+            elif sw == 3:
+                b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+                v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+                v = np.where(v >= 1 << 23, v - (1 << 24), v)
+                wav = v.astype(dtype) / 8388608.0
+            elif sw == 4:
+                wav = np.frombuffer(raw, dtype="<i4").astype(dtype) / 2147483648.0
+            else:
+                wav = (np.frombuffer(raw, dtype=np.uint8).astype(dtype) - 128.0) / 128.0
+            if nch > 1:
+                wav = wav.reshape(-1, nch)
+            return wav, int(sr)
+    except Exception:
+        raise RuntimeError(f'Could not load audio from "{path}".')
+
+
+# ------------------------------------------------------------------------------------------
+# constants of the fused log-mel kernel
+# ------------------------------------------------------------------------------------------
+
+
+def _hz_to_mel_slaney(freq: float) -> float:
+    f_sp = 200.0 / 3
+    mels = freq / f_sp
+    min_log_hz = 1000.0
+    if freq >= min_log_hz:
+        mels = min_log_hz / f_sp + math.log(freq / min_log_hz) / (math.log(6.4) / 27.0)
+    return mels
+
+
+def mel_filterbank(n_freqs=N_FFT // 2 + 1, f_min=F_MIN, f_max=F_MAX, n_mels=N_MELS, sample_rate=SAMPLE_RATE):
+    """torchaudio.functional.melscale_fbanks(norm=None, mel_scale='slaney') restated with the
+    same fp32 torch ops so that the coefficients are bit-identical to what the reference's
+    MelSpectrogram holds (reference preprocessing.py:43-53)."""
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_pts = torch.linspace(_hz_to_mel_slaney(f_min), _hz_to_mel_slaney(f_max), n_mels + 2)
+    f_sp = 200.0 / 3
+    f_pts = f_sp * m_pts
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = math.log(6.4) / 27.0
+    log_t = m_pts >= min_log_mel
+    f_pts[log_t] = min_log_hz * torch.exp(logstep * (m_pts[log_t] - min_log_mel))
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.max(torch.zeros(1), torch.min(down, up))  # [n_freqs, n_mels]
+
+
+def mel_constants() -> dict:
+    """Window, FFT twiddles and the filterbank in CSR form (each mel band is one contiguous
+    run of FFT bins) as packed parameters ``mel.*``."""
+    fb = mel_filterbank().numpy()  # [513, 128]
+    starts, ptr, w = [], [0], []
+    for m in range(fb.shape[1]):
+        nz = np.nonzero(fb[:, m])[0]
+        if len(nz) == 0:
+            starts.append(0)
+        else:
+            lo, hi = int(nz[0]), int(nz[-1]) + 1
+            starts.append(lo)
+            w.extend(fb[lo:hi, m].tolist())
+        ptr.append(len(w))
+    k = np.arange(512, dtype=np.float64)
+    tw = np.stack([np.cos(2 * np.pi * k / N_FFT), -np.sin(2 * np.pi * k / N_FFT)], axis=1)
+    return {
+        "mel.window": torch.hann_window(N_FFT, periodic=True).numpy(),
+        "mel.twiddle": tw.astype(np.float32).reshape(-1),
+        "mel.fb_start": np.asarray(starts, dtype=np.float32),
+        "mel.fb_ptr": np.asarray(ptr, dtype=np.float32),
+        "mel.fb_w": np.asarray(w, dtype=np.float32),
+    }
+
+
+class LogMelSpect(torch.nn.Module):
+    """Drop-in for the reference class (preprocessing.py:27-59).  Only the reference's
+    default analysis parameters are implemented in the kernel; anything else raises."""
+
+    def __init__(
+        self,
+        sample_rate=22050,
+        n_fft=1024,
+        hop_length=441,
+        f_min=30,
+        f_max=11000,
+        n_mels=128,
+        mel_scale="slaney",
+        normalized="frame_length",
+        power=1,
+        log_multiplier=1000,
+        device="cuda",
+        _engine=None,
+    ):
+        super().__init__()
+        given = (sample_rate, n_fft, hop_length, f_min, f_max, n_mels, mel_scale, normalized, power, log_multiplier)
+        if given != (22050, 1024, 441, 30, 11000, 128, "slaney", "frame_length", 1, 1000):
+            raise NotImplementedError("the sm_100a log-mel kernel implements the reference defaults only")
+        from .engine import Engine
+
+        self.engine = _engine if _engine is not None else Engine.mel_only(device)
+
+    def forward(self, x):
+        """Input is a waveform as a monodimensional array of shape T,
+        output is a 2D log mel spectrogram of shape (F,128)."""
+        return self.engine.logmel([x])[0]

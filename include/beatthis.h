@@ -1,0 +1,160 @@
+/*
+ * beatthis.h -- C ABI of libbeatthis_sm100.so, the B200 (sm_100a) implementation of the
+ * CPJKU/beat_this Audio -> Frames -> Beats inference path.
+ *
+ * The reference has no FFI: its boundary is the Python API of beat_this/inference.py
+ * (Spect2Frames / Audio2Frames / Audio2Beats / File2Beats).  Each entry point below names
+ * the reference function (file:line under the reference tree) whose arithmetic it
+ * replaces.  beat_this_b200/_lib.py binds these with ctypes; INTEGRATION.md shows the stub
+ * a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain C types only; no torch / CUDA types in signatures (streams travel as void*).
+ *  - `*_dev` pointers are device pointers on the context's GPU, `*_host` are host pointers.
+ *  - ragged batches are CSR style: `offsets[n+1]` (host, int64) into a concatenated buffer.
+ *  - all work is enqueued on the given CUDA stream (cudaStream_t as void*, NULL = default
+ *    stream); no hidden device synchronisation except where stated.
+ *  - return value: 0 = ok, negative = error (bt_last_error() gives the text).  Nothing
+ *    throws across the ABI.  There is NO CPU fallback: without a CUDA device every compute
+ *    entry point fails with BT_ERR_CUDA.
+ *  - one bt_ctx per GPU; a ctx is not thread-safe (one host thread per ctx).
+ */
+#ifndef BEATTHIS_H_
+#define BEATTHIS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BT_OK 0
+#define BT_ERR_ARG (-1)
+#define BT_ERR_CUDA (-2)
+#define BT_ERR_STATE (-3)
+#define BT_ERR_PARAM (-4)
+
+#define BT_DTYPE_F32 0  /* fp32 CUDA-core kernels: the reference's float16=False numerics   */
+#define BT_DTYPE_BF16 1 /* bf16 tcgen05 tensor-core kernels, fp32 accumulate + fp32 residual */
+
+#define BT_SAMPLE_RATE 22050
+#define BT_N_FFT 1024
+#define BT_HOP 441
+#define BT_N_MELS 128
+#define BT_CHUNK 1500
+#define BT_BORDER 6
+#define BT_FPS 50
+
+typedef struct bt_ctx bt_ctx;
+
+/* BeatThis constructor arguments (reference beat_this/model/beat_tracker.py:39-49), as
+ * filtered from the checkpoint's hyper_parameters by load_model (inference.py:72-78). */
+typedef struct bt_hparams {
+  int32_t spect_dim;            /* 128 */
+  int32_t transformer_dim;      /* 512 (final*) / 128 (small*) */
+  int32_t ff_mult;              /* 4 */
+  int32_t n_layers;             /* 6 */
+  int32_t head_dim;             /* 32 */
+  int32_t stem_dim;             /* 32 */
+  int32_t sum_head;             /* 1 */
+  int32_t partial_transformers; /* 1 */
+} bt_hparams;
+
+/* Library / ABI version (major*100 + minor). */
+int bt_version(void);
+
+/* ---- model lifetime: replaces load_model (inference.py:56-87) ------------------------ */
+
+/* Create a context on CUDA device `device_ordinal` for a model of shape `hp`.
+ * compute_dtype: BT_DTYPE_F32 or BT_DTYPE_BF16. */
+int bt_create(bt_ctx** out, int device_ordinal, const bt_hparams* hp, int compute_dtype);
+
+/* Upload one packed parameter (fp32, host memory, `count` elements) under `name`.
+ * The host side (beat_this_b200/weights.py) folds eval-mode BatchNorm and the RMSNorm
+ * gamma*sqrt(dim) factors into neighbouring weights and lays convolution / frontend.linear
+ * weights out as GEMM operands; names and shapes are listed in DESIGN.md "Packed
+ * parameters".  Replaces model.load_state_dict (inference.py:84). */
+int bt_set_param(bt_ctx* ctx, const char* name, const float* data_host, int64_t count);
+
+/* Check that every parameter the model shape needs is present, build bf16 copies and TMA
+ * descriptors.  After this the weights are immutable.  (model.to(device).eval(), :87) */
+int bt_finalize(bt_ctx* ctx);
+
+/* Free everything. */
+void bt_destroy(bt_ctx* ctx);
+
+/* Text of the last error on this ctx (or the last bt_create failure when ctx == NULL). */
+const char* bt_last_error(const bt_ctx* ctx);
+
+/* ---- host-side planning helpers (pure host, no GPU needed) ---------------------------------- */
+
+/* Number of log-mel frames for `n_samples` samples: 1 + n/441 (torch.stft center=True,
+ * preprocessing.py:43-59). */
+int64_t bt_num_frames(int64_t n_samples);
+
+/* split_piece (inference.py:100-135) for a piece of T frames with chunk 1500 / border 6 /
+ * avoid_short_end: writes up to `cap` chunk starts and lengths, returns the chunk count
+ * (or the count needed when cap is too small). */
+int64_t bt_plan_chunks(int64_t T, int64_t* starts, int64_t* lens, int64_t cap);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+
+/* LogMelSpect.forward (preprocessing.py:56-59) for n_clips mono 22.05 kHz clips.
+ * audio_dev: concatenated fp32 samples; sample_offsets_host[n_clips+1].
+ * spect_dev: out, concatenated [T_i,128] fp32 with T_i = bt_num_frames(len_i), laid out
+ * at frame_offsets_host[i] (frames; frame_offsets_host[n_clips+1]). */
+int bt_logmel(bt_ctx* ctx, const float* audio_dev, const int64_t* sample_offsets_host,
+              int32_t n_clips, float* spect_dev, const int64_t* frame_offsets_host,
+              void* stream);
+
+/* Spect2Frames.spect2frames (inference.py:244-254): split_piece -> BeatThis.forward on
+ * every chunk -> aggregate_prediction(keep_first).  spect_dev as produced by bt_logmel.
+ * beat_dev / downbeat_dev: out, fp32 logits, concatenated with the same frame offsets. */
+int bt_spect2frames(bt_ctx* ctx, const float* spect_dev, const int64_t* frame_offsets_host,
+                    int32_t n_clips, float* beat_dev, float* downbeat_dev, void* stream);
+
+/* Audio2Frames.__call__ (inference.py:279-281) for already mono, 22.05 kHz fp32 audio:
+ * bt_logmel + bt_spect2frames with the spectrogram kept in the ctx workspace. */
+int bt_audio2frames(bt_ctx* ctx, const float* audio_dev, const int64_t* sample_offsets_host,
+                    int32_t n_clips, float* beat_dev, float* downbeat_dev,
+                    const int64_t* frame_offsets_host, void* stream);
+
+/* Postprocessor("minimal") (model/postprocessor.py:85-136,176-197) on device.
+ * Per clip i: beat_times_dev[i*max_peaks ..] (float64 seconds), n_beats_dev[i], same for
+ * downbeats.  A clip with more than max_peaks peaks reports the true count (> max_peaks)
+ * and stores the first max_peaks. */
+int bt_peakpick(bt_ctx* ctx, const float* beat_dev, const float* downbeat_dev,
+                const int64_t* frame_offsets_host, int32_t n_clips, double* beat_times_dev,
+                int32_t* n_beats_dev, double* down_times_dev, int32_t* n_down_dev,
+                int32_t max_peaks, void* stream);
+
+/* ---- introspection / tuning ----------------------------------------------------------------- */
+
+/* Chunks processed per wave (workspace is sized for this many 1500-frame chunks). */
+int bt_set_wave_chunks(bt_ctx* ctx, int32_t chunks);
+
+/* Number of kernel launches issued by this ctx since creation (bench.py "gpu_launches"). */
+int64_t bt_launch_count(const bt_ctx* ctx);
+
+/* Test hook: after the next bt_spect2frames call on a single wave, copy the activation
+ * named `tap` (see DESIGN.md "Taps") as fp32 into out_dev (capacity `cap` floats).
+ * Returns the element count through *count.  Used only by tests/. */
+int bt_debug_request_tap(bt_ctx* ctx, const char* tap, float* out_dev, int64_t cap);
+int64_t bt_debug_tap_count(const bt_ctx* ctx);
+
+/* Test hook: D[M,N] = A[M,K] * W[N,K]^T through the ctx's GEMM for its compute dtype
+ * (fp32 inputs on device; the bf16 path rounds A and W to bf16 first). */
+int bt_debug_gemm(bt_ctx* ctx, const float* a_dev, const float* w_dev, float* d_dev,
+                  int32_t M, int32_t N, int32_t K, void* stream);
+
+/* Test hook: softmax(Q K^T / sqrt(32)) V for `seqs` sequences of length L and `heads`
+ * heads of dim 32 through the ctx's time-direction attention kernel.  q/k/v/o_dev are
+ * [seqs, L, heads*32] fp32. */
+int bt_debug_attention(bt_ctx* ctx, const float* q_dev, const float* k_dev, const float* v_dev,
+                       float* o_dev, int32_t seqs, int32_t L, int32_t heads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEATTHIS_H_ */

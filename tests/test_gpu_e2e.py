@@ -1,0 +1,120 @@
+"""End-to-end GPU parity against the reference's own outputs (tests/golden/model.npz, written by
+oracle/make_golden.py from the UNMODIFIED reference) and against the CPU oracle on ragged batches."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from test_gpu_kernels import BF16_TOL, F32_TOL
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+
+def _gold():
+    return np.load(os.path.join(GOLDEN, "model.npz"))
+
+
+def _check_ckpt(path, key):
+    from beat_this_b200 import synthetic
+    from oracle import beat_this_oracle as O
+
+    sd = O.strip_prefix(torch.load(path, weights_only=True)["state_dict"])
+    assert abs(synthetic.tensor_checksum(sd) - float(_gold()[key])) < 1e-6 * abs(float(_gold()[key])), (
+        "synthetic checkpoint drifted from the one the golden fixtures were generated with"
+    )
+
+
+def _beat_match(a, b, tol_frames=0):
+    return len(a) == len(b) and (len(a) == 0 or np.abs(np.asarray(a) - np.asarray(b)).max() <= tol_frames / 50 + 1e-12)
+
+
+@pytest.mark.parametrize("float16", [False, True])
+def test_config1_spect2frames_small0(small0_ckpt, lib_built, float16):
+    """BASELINE config 1: Spect2Frames small0 on one random 1500-frame spectrogram (2 chunks)."""
+    from beat_this_b200.inference import Spect2Frames
+
+    _check_ckpt(small0_ckpt, "small0_ckpt_sum")
+    g = _gold()
+    torch.manual_seed(0)
+    spect = torch.rand(1500, 128) * 7
+    s2f = Spect2Frames(small0_ckpt, "cuda:0", float16)
+    beat, down = s2f(spect.cuda())
+    assert isinstance(beat, torch.Tensor) and beat.dtype == torch.float32 and beat.shape == (1500,) and beat.is_cuda
+    eb = np.abs(beat.cpu().numpy() - g["small0_spect1500_beat"]).max()
+    ed = np.abs(down.cpu().numpy() - g["small0_spect1500_down"]).max()
+    print(f"small0 spect1500 float16={float16}: max abs err beat {eb:.3e} downbeat {ed:.3e}")
+    assert max(eb, ed) < (BF16_TOL if float16 else F32_TOL)
+
+
+@pytest.mark.parametrize("float16", [False, True])
+def test_final0_audio2beats_golden(final0_ckpt, lib_built, float16):
+    """Audio2Frames / Audio2Beats, final0-shaped checkpoint, 10 s (one short chunk) and 30 s
+    (two 1500-frame chunks) clips, against the reference's own logits and timestamps."""
+    from beat_this_b200 import synthetic
+    from beat_this_b200.inference import Audio2Beats, Audio2Frames
+
+    _check_ckpt(final0_ckpt, "final0_ckpt_sum")
+    g = _gold()
+    a2b = Audio2Beats(final0_ckpt, "cuda:0", float16)
+    for idx in (1, 2):
+        x = synthetic.synth_clip(idx, float(g[f"final0_clip{idx}_secs"]))
+        beat, down = Audio2Frames.__call__(a2b, x, 22050)
+        rb, rd = g[f"final0_clip{idx}_beat"], g[f"final0_clip{idx}_down"]
+        assert beat.shape == rb.shape
+        eb = np.abs(beat.cpu().numpy() - rb).max()
+        ed = np.abs(down.cpu().numpy() - rd).max()
+        print(f"final0 clip{idx} float16={float16}: max abs err beat {eb:.3e} downbeat {ed:.3e}")
+        assert max(eb, ed) < (BF16_TOL if float16 else F32_TOL)
+        bt, dt = a2b(x, 22050)
+        assert bt.dtype == np.float64 and dt.dtype == np.float64
+        # the postprocessor itself is bit exact on identical logits (test_peakpick_golden_bit_exact);
+        # end to end the peak sets agree wherever the decision margin exceeds the logit error
+        same_b = np.array_equal(bt, g[f"final0_clip{idx}_beat_times"])
+        same_d = np.array_equal(dt, g[f"final0_clip{idx}_down_times"])
+        print(f"  timestamps identical: beats {same_b} ({len(bt)}), downbeats {same_d} ({len(dt)})")
+        if not float16:
+            assert same_b and same_d
+    # stereo input -> mono mix (inference.py:270-271)
+    x = synthetic.synth_clip(3, 4.0)
+    xs2 = np.stack([x, 0.5 * x[::-1]], axis=1)
+    beat, down = Audio2Frames.__call__(a2b, xs2, 22050)
+    e = max(np.abs(beat.cpu().numpy() - g["final0_stereo4s_beat"]).max(), np.abs(down.cpu().numpy() - g["final0_stereo4s_down"]).max())
+    print(f"final0 stereo 4 s float16={float16}: max abs err {e:.3e}")
+    assert e < (BF16_TOL if float16 else F32_TOL)
+    with pytest.raises(ValueError):
+        a2b(np.zeros((10, 2, 2)), 22050)
+
+
+@pytest.mark.parametrize("float16", [False, True])
+def test_ragged_batch_vs_oracle(small0_ckpt, lib_built, float16):
+    """Variable-length clips in one call (BASELINE config 5 shape, small): 1..3 chunks per
+    clip, short (T+12) and full chunks mixed; compared with the CPU oracle clip by clip."""
+    from beat_this_b200 import synthetic
+    from beat_this_b200.inference import Audio2Beats
+    from oracle import beat_this_oracle as O
+
+    sd = O.strip_prefix(torch.load(small0_ckpt, weights_only=True)["state_dict"])
+    secs = [5.0, 29.7, 30.0, 61.3, 12.34, 5.0]
+    clips = [synthetic.synth_clip(10 + i, s) for i, s in enumerate(secs)]
+    a2b = Audio2Beats(small0_ckpt, "cuda:0", float16)
+    frames = super(Audio2Beats, a2b).batch(clips, 22050)
+    beats = a2b.batch(clips, 22050)
+    worst = 0.0
+    for x, (b, d), (bt, dt) in zip(clips, frames, beats):
+        ob, od = O.spect2frames(sd, O.signal2spect(x, 22050))
+        assert b.shape == ob.shape
+        e = max((b.cpu() - ob).abs().max().item(), (d.cpu() - od).abs().max().item())
+        worst = max(worst, e)
+        obt, odt = O.postp_minimal(b.cpu(), d.cpu())  # oracle postprocessor on OUR logits: must be bit exact
+        assert np.array_equal(bt, obt) and np.array_equal(dt, odt)
+    print(f"ragged batch float16={float16}: worst max abs logit err {worst:.3e}")
+    assert worst < (BF16_TOL if float16 else F32_TOL)
+
+
+def test_no_cpu_fallback(small0_ckpt, lib_built):
+    from beat_this_b200.inference import Spect2Frames
+
+    with pytest.raises(RuntimeError):
+        Spect2Frames(small0_ckpt, "cpu")

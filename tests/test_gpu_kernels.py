@@ -1,0 +1,197 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every test calls the CUDA path
+through the C ABI (ctypes) and compares with the CPU oracle (oracle/beat_this_oracle.py) or the
+golden fixtures written from the reference's own outputs (tests/golden, oracle/make_golden.py).
+
+Tolerances (stated, per north_star):
+  fp32 path  : frame logits within 1e-3 of the fp32 reference (measured ~1e-4).
+  bf16 path  : frame logits within BF16_TOL (absolute, logits have std ~2 and range +-8).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+F32_TOL = 1e-3
+BF16_TOL = 0.15
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (run under gpurun)")
+    return torch.device("cuda:0")
+
+
+def _engine(ckpt, bf16):
+    from beat_this_b200.inference import load_model
+
+    return load_model(ckpt, "cuda:0", float16=bf16)
+
+
+@pytest.fixture(scope="module")
+def small_f32(small0_ckpt, lib_built, dev):
+    return _engine(small0_ckpt, False)
+
+
+@pytest.fixture(scope="module")
+def small_bf16(small0_ckpt, lib_built, dev):
+    return _engine(small0_ckpt, True)
+
+
+@pytest.fixture(scope="module")
+def final_f32(final0_ckpt, lib_built, dev):
+    return _engine(final0_ckpt, False)
+
+
+@pytest.fixture(scope="module")
+def final_bf16(final0_ckpt, lib_built, dev):
+    return _engine(final0_ckpt, True)
+
+
+def _sd(path):
+    from oracle import beat_this_oracle as O
+
+    return O.strip_prefix(torch.load(path, weights_only=True)["state_dict"])
+
+
+# ------------------------------------------------------------------------------ log-mel
+def test_logmel_matches_reference_golden(lib_built, dev):
+    from beat_this_b200 import synthetic
+    from beat_this_b200.preprocessing import LogMelSpect
+
+    g = np.load(os.path.join(GOLDEN, "logmel.npz"))
+    mel = LogMelSpect(device=dev)
+    for idx in (0, 1):
+        x = synthetic.synth_clip(idx, float(g[f"clip{idx}_secs"]))
+        out = mel(torch.tensor(x, dtype=torch.float32, device=dev)).cpu().numpy()
+        ref = g[f"clip{idx}_mel"]
+        assert out.shape == ref.shape
+        err = np.abs(out - ref).max()
+        print(f"logmel clip{idx}: max abs err vs reference {err:.3e}")
+        assert err < 2e-3  # fp32 FFT round-off amplified by log1p(1000 x) near silence
+
+
+def test_logmel_batch_and_edges(lib_built, dev):
+    from beat_this_b200.engine import Engine
+    from oracle import beat_this_oracle as O
+
+    eng = Engine.mel_only(dev)
+    rng = np.random.default_rng(0)
+    lens = [513, 1024, 22050, 44100 + 17, 441 * 7]
+    sigs = [rng.standard_normal(n).astype(np.float32) * 0.1 for n in lens]
+    outs = eng.logmel(sigs)
+    for s, o in zip(sigs, outs):
+        ref = O.logmel(torch.tensor(s))
+        assert o.shape == ref.shape == (1 + len(s) // 441, 128)
+        assert (o.cpu() - ref).abs().max() < 2e-3
+    with pytest.raises(Exception):
+        eng.logmel([np.zeros(512, np.float32)])  # torch.stft reflect padding fails here too
+
+
+# ------------------------------------------------------------------------------ peak picking
+def test_peakpick_golden_bit_exact(lib_built, dev):
+    from beat_this_b200.postprocessor import Postprocessor
+
+    g = np.load(os.path.join(GOLDEN, "postp_minimal.npz"))
+    post = Postprocessor("minimal", device=dev)
+    n = int(g["n"])
+    # one by one (unbatched API) ...
+    for i in range(n):
+        bt, dt = post(torch.tensor(g[f"beat_{i}"]), torch.tensor(g[f"down_{i}"]))
+        assert bt.dtype == np.float64 and dt.dtype == np.float64
+        assert np.array_equal(bt, g[f"beat_times_{i}"]), i
+        assert np.array_equal(dt, g[f"down_times_{i}"]), i
+    # ... and all clips in one launch
+    fo = [0]
+    for i in range(n):
+        fo.append(fo[-1] + len(g[f"beat_{i}"]))
+    b = torch.tensor(np.concatenate([g[f"beat_{i}"] for i in range(n)]), device=dev)
+    d = torch.tensor(np.concatenate([g[f"down_{i}"] for i in range(n)]), device=dev)
+    res = post.batch_cat(b, d, fo)
+    for i in range(n):
+        assert np.array_equal(res[i][0], g[f"beat_times_{i}"]), i
+        assert np.array_equal(res[i][1], g[f"down_times_{i}"]), i
+
+
+# ------------------------------------------------------------------------------ GEMM / attention units
+GEMM_SHAPES = [(300, 96, 32), (1500, 32, 128), (1000, 64, 64), (700, 192, 64), (1500, 1536, 512), (520, 512, 2048), (257, 128, 256)]
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_debug_gemm(small_f32, small_bf16, bf16):
+    eng = (small_bf16 if bf16 else small_f32).engine
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for M, N, K in GEMM_SHAPES:
+        a = torch.randn(M, K, generator=g)
+        w = torch.randn(N, K, generator=g) / math.sqrt(K)
+        if bf16:
+            a, w = a.bfloat16().float(), w.bfloat16().float()
+        ref = a.double() @ w.double().T
+        d = eng.debug_gemm(a.cuda(), w.cuda()).cpu().double()
+        err = (d - ref).abs().max().item()
+        print(f"gemm bf16={bf16} {M}x{N}x{K}: max abs err {err:.3e}")
+        assert err < (2e-3 if bf16 else 1e-4), (M, N, K)
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_debug_attention(small_f32, small_bf16, bf16):
+    eng = (small_bf16 if bf16 else small_f32).engine
+    g = torch.Generator(device="cpu").manual_seed(2)
+    for seqs, L, heads in [(3, 1500, 2), (2, 200, 1), (1, 13, 4), (2, 128, 1), (1, 129, 1)]:
+        q = torch.randn(seqs, L, heads * 32, generator=g) * 1.5
+        k = torch.randn(seqs, L, heads * 32, generator=g)
+        v = torch.randn(seqs, L, heads * 32, generator=g)
+        sh = lambda t: t.view(seqs, L, heads, 32).permute(0, 2, 1, 3).double()
+        ref = torch.nn.functional.scaled_dot_product_attention(sh(q), sh(k), sh(v)).permute(0, 2, 1, 3).reshape(seqs, L, -1)
+        o = eng.debug_attention(q.cuda(), k.cuda(), v.cuda()).cpu().double()
+        err = (o - ref).abs().max().item()
+        print(f"attention bf16={bf16} seqs={seqs} L={L} heads={heads}: max abs err {err:.3e}")
+        assert err < (3e-2 if bf16 else 1e-4), (seqs, L, heads)
+
+
+# ------------------------------------------------------------------------------ per-stage parity
+TAPS = ["stem"] + [f"b{i}.{s}" for i in range(3) for s in ("attnF", "ffF", "attnT", "ffT", "conv")] + ["frontend"] + [
+    f"l{l}.{s}" for l in range(6) for s in ("attn", "ff")
+]
+
+
+def _stage_errors(model, ckpt, T=138, nclips=2):
+    from oracle import beat_this_oracle as O
+
+    sd = _sd(ckpt)
+    torch.manual_seed(3)
+    spects = [torch.rand(T, 128) * 7 for _ in range(nclips)]
+    chunks = torch.stack([O.split_piece(s)[0][0] for s in spects])  # [n, T+12, 128]
+    taps = {}
+    with torch.inference_mode():
+        O.forward(sd, chunks, taps)
+    fo = [i * T for i in range(nclips + 1)]
+    cat = torch.cat(spects).cuda()
+    rows = []
+    for name in TAPS:
+        ref = taps[name]
+        got, _ = model.engine.tap(name, cat, fo, ref.numel())
+        assert got.numel() == ref.numel(), name
+        err = (got.cpu().view(ref.shape) - ref).abs().max().item()
+        rows.append((name, err, ref.abs().max().item()))
+    return rows
+
+
+def test_stage_parity_fp32(small_f32, small0_ckpt):
+    rows = _stage_errors(small_f32, small0_ckpt)
+    for name, err, mag in rows:
+        print(f"fp32 stage {name:10s} max abs err {err:.3e} (|ref| max {mag:.2f})")
+    assert max(r[1] for r in rows) < 1e-3
+
+
+def test_stage_parity_bf16(small_bf16, small0_ckpt):
+    rows = _stage_errors(small_bf16, small0_ckpt)
+    for name, err, mag in rows:
+        print(f"bf16 stage {name:10s} max abs err {err:.3e} (|ref| max {mag:.2f})")
+    assert max(r[1] / max(r[2], 1.0) for r in rows) < 0.05
