@@ -56,6 +56,11 @@ PROTOTYPES = {
     ),
     "bt_set_wave_chunks": (c_int, [c_void_p, c_int32]),
     "bt_launch_count": (c_int64, [c_void_p]),
+    "bt_profile_enable": (c_int, [c_void_p, c_int]),
+    "bt_profile_collect": (c_int, [c_void_p]),
+    "bt_profile_reset": (c_int, [c_void_p]),
+    "bt_profile_count": (c_int, [c_void_p]),
+    "bt_profile_get": (c_int, [c_void_p, c_int, c_char_p, c_int, POINTER(c_double), POINTER(c_int64)]),
     "bt_debug_request_tap": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
     "bt_debug_tap_count": (c_int64, [c_void_p]),
     "bt_debug_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),

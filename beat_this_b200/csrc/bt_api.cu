@@ -76,6 +76,18 @@ struct bt_ctx {
 
   std::map<std::pair<int, int>, WavePlans*> plans;
 
+  // per-kernel-class device timing (bt_profile_*): one event after every launch; the
+  // duration of a launch is the gap to the previous event on the same stream
+  bool prof = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct ProfRec { int kind; int ev; int prev; };
+  std::vector<ProfRec> prof_recs;
+  int prof_prev = -1;
+  std::vector<std::string> prof_names;
+  std::vector<double> prof_ms;
+  std::vector<int64_t> prof_cnt;
+
   // debug tap
   std::string tap_name;
   float* tap_out = nullptr;
@@ -102,8 +114,39 @@ int fail(const bt_ctx* c, int code, const char* fmt, ...) {
                   __FILE__, __LINE__);                                                       \
   } while (0)
 
+int prof_event(bt_ctx* c, cudaStream_t st) {
+  if (c->ev_used == c->ev_pool.size()) {
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return -1;
+    c->ev_pool.push_back(ev);
+  }
+  const int idx = static_cast<int>(c->ev_used++);
+  cudaEventRecord(c->ev_pool[idx], st);
+  return idx;
+}
+
+void prof_mark(bt_ctx* c, cudaStream_t st) {  // start of an API call: reference point for the first kernel
+  if (c->prof) c->prof_prev = prof_event(c, st);
+}
+
+void prof_launch(bt_ctx* c, const char* what, cudaStream_t st) {
+  int kind = -1;
+  for (size_t i = 0; i < c->prof_names.size(); ++i)
+    if (c->prof_names[i] == what) { kind = static_cast<int>(i); break; }
+  if (kind < 0) {
+    kind = static_cast<int>(c->prof_names.size());
+    c->prof_names.push_back(what);
+    c->prof_ms.push_back(0.0);
+    c->prof_cnt.push_back(0);
+  }
+  const int ev = prof_event(c, st);
+  if (ev >= 0 && c->prof_prev >= 0) c->prof_recs.push_back({kind, ev, c->prof_prev});
+  c->prof_prev = ev;
+}
+
 int check_launch(bt_ctx* c, const char* what, cudaStream_t st) {
   c->launches++;
+  if (c->prof) prof_launch(c, what, st);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess && c->sync_debug) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return fail(c, BT_ERR_CUDA, "kernel %s failed: %s", what, cudaGetErrorString(e));
@@ -670,6 +713,7 @@ void bt_destroy(bt_ctx* c) {
   if (c->stage_host) cudaFreeHost(c->stage_host);
   if (c->stage_dev) cudaFree(c->stage_dev);
   if (c->stage_ev) cudaEventDestroy(c->stage_ev);
+  for (auto ev : c->ev_pool) cudaEventDestroy(ev);
   delete c;
 }
 
@@ -680,6 +724,48 @@ int bt_set_wave_chunks(bt_ctx* c, int32_t chunks) {
 }
 
 int64_t bt_launch_count(const bt_ctx* c) { return c ? c->launches : 0; }
+
+int bt_profile_enable(bt_ctx* c, int enable) {
+  if (!c) return BT_ERR_ARG;
+  c->prof = enable != 0;
+  c->prof_prev = -1;
+  return BT_OK;
+}
+
+int bt_profile_collect(bt_ctx* c) {
+  if (!c) return BT_ERR_ARG;
+  BT_CUDA(c, cudaSetDevice(c->device));
+  BT_CUDA(c, cudaDeviceSynchronize());
+  for (const auto& r : c->prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_pool[r.prev], c->ev_pool[r.ev]) == cudaSuccess) {
+      c->prof_ms[r.kind] += ms;
+      c->prof_cnt[r.kind] += 1;
+    }
+  }
+  c->prof_recs.clear();
+  c->ev_used = 0;
+  c->prof_prev = -1;
+  return BT_OK;
+}
+
+int bt_profile_reset(bt_ctx* c) {
+  if (!c) return BT_ERR_ARG;
+  int r = bt_profile_collect(c);
+  for (auto& v : c->prof_ms) v = 0.0;
+  for (auto& v : c->prof_cnt) v = 0;
+  return r;
+}
+
+int bt_profile_count(const bt_ctx* c) { return c ? static_cast<int>(c->prof_names.size()) : 0; }
+
+int bt_profile_get(const bt_ctx* c, int index, char* name, int name_cap, double* total_ms, int64_t* launches) {
+  if (!c || index < 0 || index >= static_cast<int>(c->prof_names.size())) return BT_ERR_ARG;
+  if (name && name_cap > 0) snprintf(name, name_cap, "%s", c->prof_names[index].c_str());
+  if (total_ms) *total_ms = c->prof_ms[index];
+  if (launches) *launches = c->prof_cnt[index];
+  return BT_OK;
+}
 
 int bt_debug_request_tap(bt_ctx* c, const char* tap, float* out_dev, int64_t cap) {
   if (!c) return BT_ERR_ARG;
@@ -701,6 +787,7 @@ int bt_logmel(bt_ctx* c, const float* audio_dev, const int64_t* sample_offsets_h
     return fail(c, BT_ERR_ARG, "bt_logmel: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BT_CUDA(c, cudaSetDevice(c->device));
+  prof_mark(c, st);
   for (int i = 0; i < n_clips; ++i) {
     const int64_t len = sample_offsets_host[i + 1] - sample_offsets_host[i];
     if (len <= BT_N_FFT / 2)
@@ -735,6 +822,7 @@ int bt_spect2frames(bt_ctx* c, const float* spect_dev, const int64_t* frame_offs
     return fail(c, BT_ERR_ARG, "bt_spect2frames: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BT_CUDA(c, cudaSetDevice(c->device));
+  prof_mark(c, st);
   int r = ensure_ws(c);
   if (r != BT_OK) return r;
   // plan: all chunks of all clips, grouped by chunk length (1500 except for pieces <= 1488 frames)
@@ -811,6 +899,7 @@ int bt_peakpick(bt_ctx* c, const float* beat_dev, const float* downbeat_dev, con
     return fail(c, BT_ERR_ARG, "bt_peakpick: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BT_CUDA(c, cudaSetDevice(c->device));
+  prof_mark(c, st);
   const size_t bytes = static_cast<size_t>(n_clips + 1) * 8;
   int r = ensure_stage(c, bytes);
   if (r != BT_OK) return r;

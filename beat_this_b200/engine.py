@@ -163,6 +163,24 @@ class Engine:
         dn_h = dn_t[:, :width].cpu().numpy()
         return [(bt_h[i, : cnt_h[0, i]].copy(), dn_h[i, : cnt_h[1, i]].copy()) for i in range(n)]
 
+    # ---- per-kernel-class timing (bench.py roofline) -------------------------------------------
+    def profile_enable(self, on: bool = True):
+        _lib.check(self.lib, self.ctx, self.lib.bt_profile_enable(self.ctx, int(on)))
+
+    def profile_reset(self):
+        _lib.check(self.lib, self.ctx, self.lib.bt_profile_reset(self.ctx))
+
+    def profile_results(self) -> dict:
+        """{kernel class: (total device ms, launches)} accumulated since the last reset."""
+        _lib.check(self.lib, self.ctx, self.lib.bt_profile_collect(self.ctx))
+        out = {}
+        for i in range(int(self.lib.bt_profile_count(self.ctx))):
+            name = ctypes.create_string_buffer(64)
+            ms, n = ctypes.c_double(), ctypes.c_int64()
+            self.lib.bt_profile_get(self.ctx, i, name, 64, ctypes.byref(ms), ctypes.byref(n))
+            out[name.value.decode()] = (ms.value, n.value)
+        return out
+
     # ---- test hooks --------------------------------------------------------------------------
     def tap(self, name: str, spect: torch.Tensor, frame_offsets, capacity: int):
         buf = torch.zeros(capacity, dtype=torch.float32, device=self.device)

@@ -137,6 +137,18 @@ int bt_set_wave_chunks(bt_ctx* ctx, int32_t chunks);
 /* Number of kernel launches issued by this ctx since creation (bench.py "gpu_launches"). */
 int64_t bt_launch_count(const bt_ctx* ctx);
 
+/* Per-kernel-class device timing for bench.py's roofline line.  While enabled, one CUDA event
+ * is recorded on the launch stream after every kernel launch; a launch's duration is the gap
+ * to the previous event.  bt_profile_collect synchronises the device and folds the recorded
+ * events into per-class totals; bt_profile_get(index) reads class `index` (name, total
+ * milliseconds, launches), bt_profile_count the number of classes seen so far. */
+int bt_profile_enable(bt_ctx* ctx, int enable);
+int bt_profile_collect(bt_ctx* ctx);
+int bt_profile_reset(bt_ctx* ctx);
+int bt_profile_count(const bt_ctx* ctx);
+int bt_profile_get(const bt_ctx* ctx, int index, char* name, int name_cap, double* total_ms,
+                   int64_t* launches);
+
 /* Test hook: after the next bt_spect2frames call on a single wave, copy the activation
  * named `tap` (see DESIGN.md "Taps") as fp32 into out_dev (capacity `cap` floats).
  * Returns the element count through *count.  Used only by tests/. */

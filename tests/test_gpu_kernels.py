@@ -18,7 +18,7 @@ from conftest import GOLDEN
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 F32_TOL = 1e-3
-BF16_TOL = 0.15
+BF16_TOL = 0.35
 
 
 @pytest.fixture(scope="module")
