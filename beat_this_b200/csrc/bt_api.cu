@@ -32,7 +32,7 @@ struct AttnW { const Param *wqkv, *wg, *bg, *wout; };
 struct FfW { const Param *w1, *b1, *w2, *b2; };
 
 // tensor-core plans for one (wave size, chunk length) geometry
-struct AttnPlans { TcGemmPlan *qkv = nullptr, *out = nullptr; TcAttnPlan* attn = nullptr; };
+struct AttnPlans { TcGemmPlan *qkv = nullptr, *out = nullptr, *gates = nullptr; TcAttnPlan* attn = nullptr; };
 struct FfPlans { TcGemmPlan *ff1 = nullptr, *ff2 = nullptr; };
 struct WavePlans {
   AttnPlans fa[3], ta[3];
@@ -56,6 +56,8 @@ struct bt_ctx {
   mutable char err[1024] = "";
   int64_t launches = 0;
   bool sync_debug = false;
+  bool v_mn = true;  // tensor-core attention reads V in its natural [key, d] layout (MN-major B operand);
+                     // BT_V_TRANSPOSED=1 selects the K-major variant with a transposed copy of V
 
   // workspace (sized for `wave` chunks of BT_CHUNK frames)
   int wave = 8;
@@ -231,6 +233,7 @@ void free_plans(bt_ctx* c) {
     auto fa = [](AttnPlans& a) {
       if (a.qkv) tc_gemm_plan_destroy(a.qkv);
       if (a.out) tc_gemm_plan_destroy(a.out);
+      if (a.gates) tc_gemm_plan_destroy(a.gates);
       if (a.attn) tc_attn_plan_destroy(a.attn);
     };
     auto ff = [](FfPlans& f) {
@@ -338,8 +341,18 @@ int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool f
   const bool tc = c->dtype == BT_DTYPE_BF16;
   const int heads = C / kHeadDim;
   const int64_t M = static_cast<int64_t>(planes) * L;
-  launch_norm_gates(X, c->XN, c->GATES, w.wg->f32, w.bg->f32, M, C, heads, tc, st);
-  BT_LAUNCHED(c, "norm_gates", st);
+  launch_norm(X, c->XN, M, C, tc, st);
+  BT_LAUNCHED(c, "norm", st);
+  {  // gates = sigmoid(to_gates(x_normed)): a [heads -> 32 padded] x C GEMM on the same normalised rows
+    GemmShape gg = plain_shape(planes, L, 32, C, C);
+    EpiParams eg{};
+    eg.kind = 2;
+    eg.bias = w.bg->f32;
+    eg.heads = heads;
+    eg.out_f32 = c->GATES;
+    int rg = run_gemm(c, c->XN, w.wg, tp ? tp->gates : nullptr, gg, eg, "gemm_gates", st);
+    if (rg != BT_OK) return rg;
+  }
   const float inv_sqrt_d = 0.17677669529663687f;  // 1/sqrt(32): SDPA default scale (roformer.py:78-80)
   EpiParams e{};
   e.kind = 1;
@@ -350,7 +363,7 @@ int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool f
   const bool tc_time = tc && !freq;
   e.qscale = tc_time ? inv_sqrt_d * 1.4426950408889634f : 1.0f;
   const int lpad = (L + 7) / 8 * 8;
-  if (tc_time) { e.vt = c->VT; e.vt_ld = lpad; }
+  if (tc_time && !c->v_mn) { e.vt = c->VT; e.vt_ld = lpad; }
   GemmShape g = plain_shape(planes, L, 3 * C, C, C);
   int r = run_gemm(c, c->XN, w.wqkv, tp ? tp->qkv : nullptr, g, e, "gemm_qkv", st);
   if (r != BT_OK) return r;
@@ -375,7 +388,7 @@ int ff_block(bt_ctx* c, float* X, int planes, int L, int C, int mult, const FfW&
              cudaStream_t st) {
   const bool tc = c->dtype == BT_DTYPE_BF16;
   const int64_t M = static_cast<int64_t>(planes) * L;
-  launch_norm_gates(X, c->XN, nullptr, nullptr, nullptr, M, C, 0, tc, st);
+  launch_norm(X, c->XN, M, C, tc, st);
   BT_LAUNCHED(c, "norm", st);
   GemmShape g1 = plain_shape(planes, L, mult * C, C, C);
   EpiParams e1 = epi_generic(w.b1, 1, nullptr, 0, nullptr, 0, c->H, mult * C);
@@ -427,9 +440,10 @@ int build_plans(bt_ctx* c, int nb, int L, WavePlans** out) {
   auto mk_attn = [&](AttnPlans& a, const AttnW& aw, int planes, int C, bool freq) -> bool {
     a.qkv = mk(c->XN, aw.wqkv, plain_shape(planes, L, 3 * C, C, C), planes);
     a.out = mk(c->O, aw.wout, plain_shape(planes, L, C, C, C), planes);
-    if (!a.qkv || !a.out) return false;
+    a.gates = mk(c->XN, aw.wg, plain_shape(planes, L, 32, C, C), planes);
+    if (!a.qkv || !a.out || !a.gates) return false;
     if (!freq) {
-      a.attn = tc_attn_plan_create(c->QKV, c->VT, lpad, planes, L, C / 32, err, sizeof(err));
+      a.attn = tc_attn_plan_create(c->QKV, c->v_mn ? nullptr : c->VT, lpad, planes, L, C / 32, err, sizeof(err));
       if (!a.attn) return false;
     }
     return true;
@@ -557,7 +571,7 @@ std::vector<std::string> required_params(const bt_hparams& hp) {
 
 bool is_gemm_weight(const std::string& n) {
   auto ends = [&](const char* s) { size_t k = strlen(s); return n.size() >= k && n.compare(n.size() - k, k, s) == 0; };
-  return ends(".wqkv") || ends(".wout") || ends(".w1") || ends(".w2") || ends(".conv.w") || n == "lin.w";
+  return ends(".wqkv") || ends(".wout") || ends(".wg") || ends(".w1") || ends(".w2") || ends(".conv.w") || n == "lin.w";
 }
 
 }  // namespace
@@ -606,6 +620,8 @@ int bt_create(bt_ctx** out, int device_ordinal, const bt_hparams* hp, int comput
   c->dtype = compute_dtype;
   const char* dbg = getenv("BT_SYNC_DEBUG");
   c->sync_debug = dbg && dbg[0] == '1';
+  const char* vtr = getenv("BT_V_TRANSPOSED");
+  c->v_mn = !(vtr && vtr[0] == '1');
   if (cudaEventCreateWithFlags(&c->stage_ev, cudaEventDisableTiming) != cudaSuccess) {
     delete c;
     return fail(nullptr, BT_ERR_CUDA, "cudaEventCreate failed");
@@ -660,7 +676,7 @@ int bt_finalize(bt_ctx* c) {
     return true;
   };
   auto chk_attn = [&](const std::string& p, int64_t C) {
-    return expect(p + ".wqkv", 3 * C * C) && expect(p + ".wg", C / 32 * C) && expect(p + ".bg", C / 32) &&
+    return expect(p + ".wqkv", 3 * C * C) && expect(p + ".wg", 32 * C) && expect(p + ".bg", 32) &&
            expect(p + ".wout", C * C);
   };
   auto chk_ff = [&](const std::string& p, int64_t C, int64_t mult) {
@@ -960,9 +976,11 @@ int bt_debug_attention(bt_ctx* c, const float* q_dev, const float* k_dev, const 
   BT_CUDA(c, cudaMemcpyAsync(gates, ones.data(), M * heads * 4, cudaMemcpyHostToDevice, st));
   int rc = BT_OK;
   if (tc) {
-    const int64_t vte = static_cast<int64_t>(seqs) * C * lpad;
-    BT_CUDA(c, cudaMalloc(&vt, vte * 2));
-    BT_CUDA(c, cudaMemsetAsync(vt, 0, vte * 2, st));
+    if (!c->v_mn) {
+      const int64_t vte = static_cast<int64_t>(seqs) * C * lpad;
+      BT_CUDA(c, cudaMalloc(&vt, vte * 2));
+      BT_CUDA(c, cudaMemsetAsync(vt, 0, vte * 2, st));
+    }
     launch_pack_qkv_test(q_dev, k_dev, v_dev, qkv, vt, lpad, seqs, L, heads,
                          0.17677669529663687f * 1.4426950408889634f, 1, st);
     char err[512] = "";

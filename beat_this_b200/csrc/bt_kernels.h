@@ -27,7 +27,8 @@ struct GemmShape {
 
 // Epilogue description (shared by the fp32 CUDA-core GEMM and the bf16 tcgen05 GEMM).
 struct EpiParams {
-  int kind;            // 0 generic, 1 qkv (RoPE + scaling + optional V transpose)
+  int kind;            // 0 generic, 1 qkv (RoPE + scaling + optional V transpose), 2 attention gates:
+                       //   out_f32[m*heads + n] = sigmoid(acc + bias[n]) for n < heads (N padded to 32)
   const float* bias;   // [N] or null
   int gelu;            // exact-erf GELU after bias
   const float* resid;  // fp32 [M, ldr] added after activation (may alias out_f32) or null
@@ -59,9 +60,8 @@ void launch_attn_time_simt(const float* qkv, const float* gates, float* out, int
 // frequency-direction attention: tokens m = (b*F + f)*L + t, sequences over f.
 void launch_attn_freq(const void* qkv, const float* gates, void* out, int B, int F, int L,
                       int heads, float scale, int act_bf16, cudaStream_t st);
-// RMSNorm without gamma (folded into the next weight) + optional sigmoid gates.
-void launch_norm_gates(const float* x, void* xn, float* gates, const float* wg, const float* bg,
-                       int64_t M, int C, int heads, int act_bf16, cudaStream_t st);
+// RMSNorm without gamma (folded into the next weight).
+void launch_norm(const float* x, void* xn, int64_t M, int C, int act_bf16, cudaStream_t st);
 // per-chunk source description for the stem (chunk gather from per-clip spectrograms)
 struct ChunkSrc {
   int64_t frame_base;  // first frame of the clip inside the concatenated spectrogram

@@ -39,11 +39,34 @@ __device__ __forceinline__ void store_act<bf16, 32>(bf16* p, const float (&v)[32
   }
 }
 
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7) on the MUFU/FMA pipes: the tensor-core
+// epilogue evaluates GELU for every FFN hidden element and erff()'s ~35 instructions made it
+// issue-bound.  gelu(x) = 0.5 x (1 + erf(x / sqrt 2)).
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float erf_abs = fmaf(-p, e, 1.0f);            // erf(|x|/sqrt2)
+  return 0.5f * x + 0.5f * fabsf(x) * erf_abs;         // 0.5x(1 + sign(x) erf_abs)
+}
+template <typename TAct>
+__device__ __forceinline__ float gelu_for(float x) {
+  if constexpr (sizeof(TAct) == 2) return gelu_fast(x);
+  else return gelu_erf(x);
+}
+
 // CNT in {4, 32}; n0 % CNT == 0; for kind 1 a head (32 columns) is never split across a
 // q/k/v boundary because C % 32 == 0.
 template <typename TAct, int CNT>
 __device__ __forceinline__ void epilogue_apply(const EpiParams& e, int L, int64_t m, int n0,
-                                               float (&v)[CNT]) {
+                                               float (&v)[CNT], const float* rpre = nullptr) {
   if (e.kind == 0) {
     if (e.bias) {
 #pragma unroll
@@ -51,9 +74,12 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& e, int L, int64_
     }
     if (e.gelu) {
 #pragma unroll
-      for (int i = 0; i < CNT; ++i) v[i] = gelu_erf(v[i]);
+      for (int i = 0; i < CNT; ++i) v[i] = gelu_for<TAct>(v[i]);
     }
-    if (e.resid) {
+    if (rpre) {  // residual prefetched by the caller before it waited for the accumulator
+#pragma unroll
+      for (int i = 0; i < CNT; ++i) v[i] += rpre[i];
+    } else if (e.resid) {
       const float4* r = reinterpret_cast<const float4*>(e.resid + m * e.ldr + n0);
 #pragma unroll
       for (int i = 0; i < CNT / 4; ++i) {
@@ -66,6 +92,11 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& e, int L, int64_
     }
     if (e.out_f32) store_act<float, CNT>(e.out_f32 + m * e.ldo_f32 + n0, v);
     if (e.out_act) store_act<TAct, CNT>(reinterpret_cast<TAct*>(e.out_act) + m * e.ldo_act + n0, v);
+  } else if (e.kind == 2) {
+    // attention gates (reference roformer.py:127-128): sigmoid(to_gates(x_normed)), N padded to 32
+#pragma unroll
+    for (int i = 0; i < CNT; ++i)
+      if (n0 + i < e.heads) e.out_f32[m * e.heads + n0 + i] = sigmoidf_(v[i] + __ldg(e.bias + n0 + i));
   } else {
     // qkv: RoPE on interleaved pairs (rotary_embedding_torch semantics, reference
     // roformer.py:121-123): out[2i] = x[2i] cos - x[2i+1] sin ; out[2i+1] = x[2i+1] cos + x[2i] sin

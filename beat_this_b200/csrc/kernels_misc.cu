@@ -165,138 +165,214 @@ void launch_stem(const float* spect, const ChunkSrc* chunks, int nchunks, int L,
 
 // ------------------------------------------------------------------------------------------
 // RMSNorm (reference roformer.py:22-32: x / max(||x||, 1e-12) * sqrt(dim) * gamma; the
-// sqrt(dim)*gamma factor is folded into the consuming weights) and the attention gates
-// sigmoid(to_gates(x_normed)) (roformer.py:127-128).  One warp per token.
+// sqrt(dim)*gamma factor is folded into the consuming weights).  Pure HBM streaming:
+// 4 B read + sizeof(TAct) B written per element.  A row is handled by C/4 (<= 32) lanes with
+// float4 loads; several rows share a warp when C < 128.
 // ------------------------------------------------------------------------------------------
 template <typename TAct, int C>
 __global__ void __launch_bounds__(256)
-norm_gates_kernel(const float* __restrict__ x, TAct* __restrict__ xn, float* __restrict__ gates,
-                  const float* __restrict__ wg, const float* __restrict__ bg, int64_t M, int heads) {
-  constexpr int PER = C / 32;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+norm_kernel(const float* __restrict__ x, TAct* __restrict__ xn, int64_t M) {
+  constexpr int LPR = C / 4 < 32 ? C / 4 : 32;  // lanes per row
+  constexpr int RPW = 32 / LPR;                 // rows per warp
+  constexpr int VPL = C / 4 / LPR;              // float4 per lane
   const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  const float* xr = x + row * C;
-  float v[PER];
+  const int64_t warp = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int64_t row = warp * RPW + lane / LPR;
+  const int li = lane % LPR;
+  const bool ok = row < M;
+  const float4* xr = reinterpret_cast<const float4*>(x + (ok ? row : 0) * C);
+  float4 v[VPL];
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    v[i] = xr[lane + 32 * i];
-    ss = fmaf(v[i], v[i], ss);
+  for (int i = 0; i < VPL; ++i) {
+    v[i] = xr[li + LPR * i];
+    ss = fmaf(v[i].x, v[i].x, ss); ss = fmaf(v[i].y, v[i].y, ss);
+    ss = fmaf(v[i].z, v[i].z, ss); ss = fmaf(v[i].w, v[i].w, ss);
   }
-  ss = warp_sum(ss);
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  if (!ok) return;
 #pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    v[i] *= inv;
-    xn[row * C + lane + 32 * i] = to_out<TAct>(v[i]);
-  }
-  if (gates) {
-    for (int h = 0; h < heads; ++h) {
-      float a = 0.f;
-#pragma unroll
-      for (int i = 0; i < PER; ++i) a = fmaf(v[i], __ldg(wg + h * C + lane + 32 * i), a);
-      a = warp_sum(a);
-      if (lane == 0) gates[row * heads + h] = sigmoidf_(a + bg[h]);
+  for (int i = 0; i < VPL; ++i) {
+    const float o4[4] = {v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv};
+    TAct* dst = xn + row * C + 4 * (li + LPR * i);
+    if constexpr (sizeof(TAct) == 4) {
+      *reinterpret_cast<float4*>(dst) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    } else {
+      uint2 u;
+      u.x = pack_bf16x2(o4[0], o4[1]);
+      u.y = pack_bf16x2(o4[2], o4[3]);
+      *reinterpret_cast<uint2*>(dst) = u;
     }
   }
 }
 
 template <typename TAct>
-static void norm_gates_dispatch(const float* x, void* xn, float* gates, const float* wg,
-                                const float* bg, int64_t M, int C, int heads, cudaStream_t st) {
-  const unsigned grid = static_cast<unsigned>(ceil_div64(M, 8));
+static void norm_dispatch(const float* x, void* xn, int64_t M, int C, cudaStream_t st) {
   TAct* o = reinterpret_cast<TAct*>(xn);
+#define BT_NORM_CASE(c)                                                                         \
+  case c: {                                                                                     \
+    constexpr int rpw = (c / 4 < 32) ? 32 / (c / 4) : 1;                                        \
+    norm_kernel<TAct, c><<<static_cast<unsigned>(ceil_div64(M, 8 * rpw)), 256, 0, st>>>(x, o, M); \
+  } break;
   switch (C) {
-    case 32: norm_gates_kernel<TAct, 32><<<grid, 256, 0, st>>>(x, o, gates, wg, bg, M, heads); break;
-    case 64: norm_gates_kernel<TAct, 64><<<grid, 256, 0, st>>>(x, o, gates, wg, bg, M, heads); break;
-    case 128: norm_gates_kernel<TAct, 128><<<grid, 256, 0, st>>>(x, o, gates, wg, bg, M, heads); break;
-    case 256: norm_gates_kernel<TAct, 256><<<grid, 256, 0, st>>>(x, o, gates, wg, bg, M, heads); break;
-    case 512: norm_gates_kernel<TAct, 512><<<grid, 256, 0, st>>>(x, o, gates, wg, bg, M, heads); break;
-    case 1024: norm_gates_kernel<TAct, 1024><<<grid, 256, 0, st>>>(x, o, gates, wg, bg, M, heads); break;
+    BT_NORM_CASE(32) BT_NORM_CASE(64) BT_NORM_CASE(128) BT_NORM_CASE(256) BT_NORM_CASE(512) BT_NORM_CASE(1024)
     default: break;  // validated in bt_create
   }
+#undef BT_NORM_CASE
 }
 
-void launch_norm_gates(const float* x, void* xn, float* gates, const float* wg, const float* bg,
-                       int64_t M, int C, int heads, int act_bf16, cudaStream_t st) {
-  if (act_bf16) norm_gates_dispatch<bf16>(x, xn, gates, wg, bg, M, C, heads, st);
-  else norm_gates_dispatch<float>(x, xn, gates, wg, bg, M, C, heads, st);
+void launch_norm(const float* x, void* xn, int64_t M, int C, int act_bf16, cudaStream_t st) {
+  if (act_bf16) norm_dispatch<bf16>(x, xn, M, C, st);
+  else norm_dispatch<float>(x, xn, M, C, st);
 }
 
 // ------------------------------------------------------------------------------------------
 // frequency-direction attention (PartialFTTransformer attnF, reference
-// beat_tracker.py:292-294): sequences of F <= 32 tokens over the frequency axis for every
-// (chunk, frame, head).  Token m = (b*F + f)*L + t.  One warp per (b, t, h); lane = f.
+// beat_tracker.py:292-294): sequences of F in {32,16,8} tokens over the frequency axis for
+// every (chunk, frame, head).  Token m = (b*F + f)*L + t.  A warp handles 32/F groups
+// (b,t,h) at once: lane -> (group g = lane / F, token f = lane % F).  Each lane loads its own
+// q/k/v rows with 16-byte loads, K/V are shared through padded shared memory (float4
+// broadcast reads).  HBM bytes: 3C in + C out per token (activation dtype).
 // ------------------------------------------------------------------------------------------
 template <typename TAct>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void load_row32(const TAct* p, float (&v)[32]);
+template <>
+__device__ __forceinline__ void load_row32<float>(const float* p, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 q = reinterpret_cast<const float4*>(p)[i];
+    v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+  }
+}
+template <>
+__device__ __forceinline__ void load_row32<bf16>(const bf16* p, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 q = reinterpret_cast<const uint4*>(p)[i];
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[8 * i + 2 * j] = __uint_as_float(w[j] << 16);
+      v[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    }
+  }
+}
+
+template <typename TAct, int F>
+__global__ void __launch_bounds__(128, 4)
 attn_freq_kernel(const TAct* __restrict__ qkv, const float* __restrict__ gates, TAct* __restrict__ out,
-                 int B, int F, int L, int heads, float scale) {
-  __shared__ float Ks[4][32][33];
-  __shared__ float Vs[4][32][33];
+                 int B, int L, int heads, float scale) {
+  constexpr int GPW = 32 / F;
+  constexpr int RS = 36;               // padded row stride (floats)
+  constexpr int GS = F * RS + 4;       // group stride: skews groups onto different banks
+  __shared__ __align__(16) float Ks[4][GPW * GS];
+  __shared__ __align__(16) float Vs[4][GPW * GS];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t grp = static_cast<int64_t>(blockIdx.x) * 4 + wib;
+  const int g = lane / F, f = lane % F;
   const int64_t ngrp = static_cast<int64_t>(B) * L * heads;
-  if (grp >= ngrp) return;  // warp-uniform
-  const int h = static_cast<int>(grp % heads);
-  const int64_t bt_ = grp / heads;
+  const int64_t grp0 = (static_cast<int64_t>(blockIdx.x) * 4 + wib) * GPW;
+  if (grp0 >= ngrp) return;  // warp-uniform
+  const int64_t grp = grp0 + g;
+  const bool act = grp < ngrp;
+  const int64_t gg = act ? grp : grp0;
+  const int h = static_cast<int>(gg % heads);
+  const int64_t bt_ = gg / heads;
   const int t = static_cast<int>(bt_ % L);
   const int b = static_cast<int>(bt_ / L);
   const int C = heads * 32;
-  const bool act = lane < F;
-  const int64_t m = (static_cast<int64_t>(b) * F + (act ? lane : 0)) * L + t;
+  const int64_t m = (static_cast<int64_t>(b) * F + f) * L + t;
   const TAct* rp = qkv + m * 3 * C + h * 32;
   float q[32];
+  {
+    float kv[32];
+    load_row32<TAct>(rp + C, kv);
+    float* kd = &Ks[wib][g * GS + f * RS];
 #pragma unroll
-  for (int d = 0; d < 32; ++d) {
-    q[d] = to_f32(rp[d]) * scale;
-    Ks[wib][lane][d] = act ? to_f32(rp[C + d]) : 0.f;
-    Vs[wib][lane][d] = act ? to_f32(rp[2 * C + d]) : 0.f;
+    for (int i = 0; i < 8; ++i)
+      reinterpret_cast<float4*>(kd)[i] = make_float4(kv[4 * i], kv[4 * i + 1], kv[4 * i + 2], kv[4 * i + 3]);
+    load_row32<TAct>(rp + 2 * C, kv);
+    float* vd = &Vs[wib][g * GS + f * RS];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      reinterpret_cast<float4*>(vd)[i] = make_float4(kv[4 * i], kv[4 * i + 1], kv[4 * i + 2], kv[4 * i + 3]);
+    load_row32<TAct>(rp, q);
+#pragma unroll
+    for (int d = 0; d < 32; ++d) q[d] *= scale;
   }
   __syncwarp();
-  float s[32];
+  const float* kb = &Ks[wib][g * GS];
+  const float* vb = &Vs[wib][g * GS];
+  float s[F];
   float mx = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < F; ++j) {
     float a = 0.f;
 #pragma unroll
-    for (int d = 0; d < 32; ++d) a = fmaf(q[d], Ks[wib][j][d], a);
-    s[j] = j < F ? a : -INFINITY;
-    mx = fmaxf(mx, s[j]);
+    for (int i = 0; i < 8; ++i) {
+      const float4 k4 = reinterpret_cast<const float4*>(kb + j * RS)[i];
+      a = fmaf(q[4 * i], k4.x, a); a = fmaf(q[4 * i + 1], k4.y, a);
+      a = fmaf(q[4 * i + 2], k4.z, a); a = fmaf(q[4 * i + 3], k4.w, a);
+    }
+    s[j] = a;
+    mx = fmaxf(mx, a);
+    asm volatile("" ::: "memory");  // keep ptxas from hoisting every K row into registers (spills)
   }
   float l = 0.f;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    s[j] = expf(s[j] - mx);
+  for (int j = 0; j < F; ++j) {
+    s[j] = __expf(s[j] - mx);
     l += s[j];
   }
   float o[32];
 #pragma unroll
   for (int d = 0; d < 32; ++d) o[d] = 0.f;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < F; ++j) {
 #pragma unroll
-    for (int d = 0; d < 32; ++d) o[d] = fmaf(s[j], Vs[wib][j][d], o[d]);
+    for (int i = 0; i < 8; ++i) {
+      const float4 v4 = reinterpret_cast<const float4*>(vb + j * RS)[i];
+      o[4 * i] = fmaf(s[j], v4.x, o[4 * i]); o[4 * i + 1] = fmaf(s[j], v4.y, o[4 * i + 1]);
+      o[4 * i + 2] = fmaf(s[j], v4.z, o[4 * i + 2]); o[4 * i + 3] = fmaf(s[j], v4.w, o[4 * i + 3]);
+    }
+    asm volatile("" ::: "memory");
   }
   if (act) {
-    const float g = gates[m * heads + h] / l;
+    const float gsc = gates[m * heads + h] / l;
     TAct* op = out + m * C + h * 32;
+    if constexpr (sizeof(TAct) == 4) {
 #pragma unroll
-    for (int d = 0; d < 32; ++d) op[d] = to_out<TAct>(o[d] * g);
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(op)[i] = make_float4(o[4 * i] * gsc, o[4 * i + 1] * gsc, o[4 * i + 2] * gsc, o[4 * i + 3] * gsc);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16x2(o[8 * i] * gsc, o[8 * i + 1] * gsc); u.y = pack_bf16x2(o[8 * i + 2] * gsc, o[8 * i + 3] * gsc);
+        u.z = pack_bf16x2(o[8 * i + 4] * gsc, o[8 * i + 5] * gsc); u.w = pack_bf16x2(o[8 * i + 6] * gsc, o[8 * i + 7] * gsc);
+        reinterpret_cast<uint4*>(op)[i] = u;
+      }
+    }
   }
+}
+
+template <typename TAct>
+static void attn_freq_dispatch(const void* qkv, const float* gates, void* out, int B, int F, int L, int heads,
+                               float scale, cudaStream_t st) {
+  const int64_t ngrp = static_cast<int64_t>(B) * L * heads;
+  const TAct* q = reinterpret_cast<const TAct*>(qkv);
+  TAct* o = reinterpret_cast<TAct*>(out);
+  const unsigned grid = static_cast<unsigned>(ceil_div64(ngrp, 4 * (32 / F)));
+  if (F == 32) attn_freq_kernel<TAct, 32><<<grid, 128, 0, st>>>(q, gates, o, B, L, heads, scale);
+  else if (F == 16) attn_freq_kernel<TAct, 16><<<grid, 128, 0, st>>>(q, gates, o, B, L, heads, scale);
+  else attn_freq_kernel<TAct, 8><<<grid, 128, 0, st>>>(q, gates, o, B, L, heads, scale);
 }
 
 void launch_attn_freq(const void* qkv, const float* gates, void* out, int B, int F, int L, int heads,
                       float scale, int act_bf16, cudaStream_t st) {
-  const int64_t ngrp = static_cast<int64_t>(B) * L * heads;
-  const unsigned grid = static_cast<unsigned>(ceil_div64(ngrp, 4));
-  if (act_bf16)
-    attn_freq_kernel<bf16><<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), gates,
-                                                   reinterpret_cast<bf16*>(out), B, F, L, heads, scale);
-  else
-    attn_freq_kernel<float><<<grid, 128, 0, st>>>(reinterpret_cast<const float*>(qkv), gates,
-                                                    reinterpret_cast<float*>(out), B, F, L, heads, scale);
+  if (act_bf16) attn_freq_dispatch<bf16>(qkv, gates, out, B, F, L, heads, scale, st);
+  else attn_freq_dispatch<float>(qkv, gates, out, B, F, L, heads, scale, st);
 }
 
 // ------------------------------------------------------------------------------------------

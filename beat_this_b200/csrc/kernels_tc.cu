@@ -88,7 +88,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TG_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], BN <= 64 ? TG_EPI_WARPS / 2 : TG_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TCOLS>(tmem_ptr);
@@ -150,22 +150,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
+    // Epilogue warps.  A warp may only touch TMEM lanes [32*(warp%4), +32).  Two schedules:
+    //  BN >= 96: the 8 warps split the columns of every tile (2 warps per lane quarter);
+    //  BN <= 64: warps 2-5 take the even tiles of this CTA and warps 6-9 the odd ones, so two
+    //            tiles are in their (memory-latency-bound) epilogue at the same time.
     const int ew = warp - 2;
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;
     const int half = ew >> 2;
     constexpr int NCH = BN / 32;
+    constexpr bool TILE_SPLIT = NCH <= 2;
     constexpr int SPLIT = (NCH + 1) / 2;
-    const int c_begin = half == 0 ? 0 : SPLIT;
-    const int c_end = half == 0 ? SPLIT : NCH;
+    const int c_begin = TILE_SPLIT ? 0 : (half == 0 ? 0 : SPLIT);
+    const int c_end = TILE_SPLIT ? NCH : (half == 0 ? SPLIT : NCH);
     const int row = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      if (TILE_SPLIT && (iter & 1) != half) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int p_out = mt / t_tiles;
       const int t = (mt - p_out * t_tiles) * TG_BM + row;
       const bool valid = t < g.L;
       const int64_t m = static_cast<int64_t>(p_out) * g.L + t;
+      float rv[32];
+      const bool pre = e.kind == 0 && e.resid != nullptr && valid;
+      if (pre) {  // issue the residual loads before blocking on the accumulator
+        const float4* r4 = reinterpret_cast<const float4*>(e.resid + m * e.ldr + nt * BN + c_begin * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 q = r4[i];
+          rv[4 * i] = q.x; rv[4 * i + 1] = q.y; rv[4 * i + 2] = q.z; rv[4 * i + 3] = q.w;
+        }
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       for (int c = c_begin; c < c_end; ++c) {
@@ -176,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          epilogue_apply<bf16, 32>(e, g.L, m, nt * BN + c * 32, v);
+          epilogue_apply<bf16, 32>(e, g.L, m, nt * BN + c * 32, v, (pre && c == c_begin) ? rv : nullptr);
         }
       }
       tc_fence_before();
@@ -283,6 +304,14 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// B operand in MN-major form (N = head dim contiguous): V tile [128 keys][32 d] exactly as the
+// QKV GEMM stores it -- rows of 64 B, SWIZZLE_64B, 8-row groups 512 B apart (SBO).
+__device__ __forceinline__ uint64_t make_mnmajor_desc_sw64(uint32_t smem_addr) {
+  return static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (static_cast<uint64_t>(512 >> 4) << 32) |
+         (1ull << 46) | (4ull << 61);
+}
+
+template <bool V_MN>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVt,
                const float* __restrict__ gates, bf16* __restrict__ out, int L, int heads) {
@@ -325,13 +354,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
   if (warp == 4) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 32);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 32) | (V_MN ? (1u << 16) : 0u);  // bit 16: B is MN-major
       auto load_kv = [&](int j) {
         const int st = j & 1;
         mbar_expect_tx(&bar_kv[st], AT_SK + AT_SV);
         tma_load_3d(sK + st * AT_SK, &tmQK, &bar_kv[st], C + h * 32, j * AT_BKV, seq);
-        tma_load_2d(sV + st * AT_SV, &tmVt, &bar_kv[st], j * AT_BKV, (seq * heads + h) * 32);
-        tma_load_2d(sV + st * AT_SV + 4096, &tmVt, &bar_kv[st], j * AT_BKV + 64, (seq * heads + h) * 32);
+        if constexpr (V_MN) {
+          tma_load_3d(sV + st * AT_SV, &tmQK, &bar_kv[st], 2 * C + h * 32, j * AT_BKV, seq);
+        } else {
+          tma_load_2d(sV + st * AT_SV, &tmVt, &bar_kv[st], j * AT_BKV, (seq * heads + h) * 32);
+          tma_load_2d(sV + st * AT_SV + 4096, &tmVt, &bar_kv[st], j * AT_BKV + 64, (seq * heads + h) * 32);
+        }
       };
       auto issue_s = [&](int j) {
         const uint32_t a = smem_u32(sQ), b = smem_u32(sK + (j & 1) * AT_SK);
@@ -364,9 +397,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t aoff = (k >> 2) * 16384 + (k & 3) * 32;
-          const uint32_t boff = (k >> 2) * 4096 + (k & 3) * 32;
-          umma_bf16(d_o, make_kmajor_desc<128>(pa + aoff), make_kmajor_desc<128>(vb + boff), idesc_o,
-                    k != 0 ? 1u : 0u);
+          const uint64_t bdesc = V_MN ? make_mnmajor_desc_sw64(vb + k * 1024)
+                                      : make_kmajor_desc<128>(vb + (k >> 2) * 4096 + (k & 3) * 32);
+          umma_bf16(d_o, make_kmajor_desc<128>(pa + aoff), bdesc, idesc_o, k != 0 ? 1u : 0u);
         }
         umma_commit(&bar_o[st]);
         if (j + 2 < nkv) {
@@ -468,12 +501,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
 struct TcAttnPlan {
   CUtensorMap tmQK, tmVt;
   int seqs, L, heads;
+  bool v_mn;
 };
 
 TcAttnPlan* tc_attn_plan_create(const void* qkv, const void* vt, int vt_ld, int seqs, int L, int heads,
                                 char* err, int errlen) {
   TcAttnPlan* p = new TcAttnPlan();
   p->seqs = seqs; p->L = L; p->heads = heads;
+  p->v_mn = vt == nullptr;
   const int C = heads * 32;
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(3 * C), static_cast<uint64_t>(L), static_cast<uint64_t>(seqs)};
@@ -481,7 +516,9 @@ TcAttnPlan* tc_attn_plan_create(const void* qkv, const void* vt, int vt_ld, int 
     const uint32_t box[3] = {32, AT_BQ, 1};
     if (!make_tmap(&p->tmQK, qkv, 3, dims, strides, box, 64, err, errlen)) { delete p; return nullptr; }
   }
-  {
+  if (p->v_mn) {
+    p->tmVt = p->tmQK;
+  } else {
     const uint64_t dims[2] = {static_cast<uint64_t>(L), static_cast<uint64_t>(seqs) * heads * 32};
     const uint64_t strides[1] = {static_cast<uint64_t>(vt_ld) * 2};
     const uint32_t box[2] = {64, 32};
@@ -493,8 +530,10 @@ void tc_attn_plan_destroy(TcAttnPlan* p) { delete p; }
 
 int launch_attn_time_tc(const TcAttnPlan* p, const float* gates, void* out, cudaStream_t st) {
   dim3 grid(ceil_div(p->L, AT_BQ), p->heads, p->seqs);
-  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(p->tmQK, p->tmVt, gates, reinterpret_cast<bf16*>(out), p->L,
-                                                    p->heads);
+  if (p->v_mn)
+    attn_tc_kernel<true><<<grid, AT_THREADS, AT_SMEM, st>>>(p->tmQK, p->tmVt, gates, reinterpret_cast<bf16*>(out), p->L, p->heads);
+  else
+    attn_tc_kernel<false><<<grid, AT_THREADS, AT_SMEM, st>>>(p->tmQK, p->tmVt, gates, reinterpret_cast<bf16*>(out), p->L, p->heads);
   return 0;
 }
 
@@ -512,7 +551,8 @@ int tc_init(char* err, int errlen) {
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaError_t r = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+  cudaError_t r = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
   if (r != cudaSuccess) {
     snprintf(err, errlen, "cudaFuncSetAttribute(attn_tc_kernel) failed: %s", cudaGetErrorString(r));
     return -1;

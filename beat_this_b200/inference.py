@@ -67,6 +67,9 @@ def load_model(checkpoint_path: str | dict | None = "final0", device: str | torc
     """Load a BeatThis model from a checkpoint (reference inference.py:56-87).  Accepts the
     reference ``.ckpt`` layout unchanged (``hyper_parameters`` + ``state_dict`` with the
     ``model.`` prefix).  ``checkpoint_path`` may also be an already loaded checkpoint dict."""
+    from .engine import _cuda_device
+
+    _cuda_device(device)  # fail before touching the checkpoint: there is no CPU path
     if checkpoint_path is None:
         raise ValueError("beat_this_b200 needs a checkpoint (the reference's random-init BeatThis() has no use here)")
     checkpoint = checkpoint_path if isinstance(checkpoint_path, dict) else load_checkpoint(checkpoint_path, "cpu")

@@ -17,7 +17,6 @@ beat_this/inference.py:56-87 strips the ``model.`` prefix).  Output is a dict
 """
 from __future__ import annotations
 
-import inspect
 import math
 
 import numpy as np
@@ -68,8 +67,13 @@ def _bn_fold(sd, prefix):
 def _attention(out, sd, src, dst, dim):
     g = _f64(sd[src + ".norm.gamma"]) * math.sqrt(dim)
     out[dst + ".wqkv"] = _f64(sd[src + ".to_qkv.weight"]) * g[None, :]
-    out[dst + ".wg"] = _f64(sd[src + ".to_gates.weight"]) * g[None, :]
-    out[dst + ".bg"] = _f64(sd[src + ".to_gates.bias"])
+    # gates run as a GEMM with N padded to 32 (heads <= 32): zero rows / zero bias beyond `heads`
+    heads = dim // 32
+    wg = torch.zeros(32, dim, dtype=torch.float64)
+    wg[:heads] = _f64(sd[src + ".to_gates.weight"]) * g[None, :]
+    bg = torch.zeros(32, dtype=torch.float64)
+    bg[:heads] = _f64(sd[src + ".to_gates.bias"])
+    out[dst + ".wg"], out[dst + ".bg"] = wg, bg
     out[dst + ".wout"] = _f64(sd[src + ".to_out.0.weight"])
 
 

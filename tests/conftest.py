@@ -12,6 +12,10 @@ CACHE = os.environ.get("BT_TEST_CACHE", "/tmp/beat_this_b200_cache")
 
 
 def pytest_configure(config):
+    # torch CPU ops crawl when they spawn one thread per hardware thread of a 100+ core box
+    import torch
+
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
     config.addinivalue_line("markers", "gpu: needs a CUDA (sm_100a) device; run with -m gpu on the B200 box")
 
 

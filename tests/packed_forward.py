@@ -28,7 +28,7 @@ def _attention(x, packed, p, C, cos, sin, freq_mode):
     heads = C // 32
     xn = _norm(x)
     qkv = xn @ _p(packed, p + ".wqkv", 3 * C, C).T
-    gates = torch.sigmoid(xn @ _p(packed, p + ".wg", heads, C).T + _p(packed, p + ".bg", heads))
+    gates = torch.sigmoid(xn @ _p(packed, p + ".wg", 32, C)[:heads].T + _p(packed, p + ".bg", 32)[:heads])
     B, Fq, L, _ = x.shape
     q, k, v = qkv.split(C, dim=-1)
     sh = lambda t: t.view(B, Fq, L, heads, 32)

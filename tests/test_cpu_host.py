@@ -1,0 +1,193 @@
+"""CPU tests (no GPU) of the host logic: packed-parameter folds, the native chunk planner,
+the C-ABI surface, the API mirror, TSV writer, multi-process (gloo) sharding + broadcast."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+from beat_this_b200 import synthetic, weights
+
+
+def test_abi_exports_every_declared_symbol(lib_built):
+    hdr = open(os.path.join(ROOT, "include", "beatthis.h")).read()
+    declared = set(re.findall(r"\b(bt_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"bt_ctx", "bt_hparams"}
+    from beat_this_b200 import _lib
+
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    for name in declared:
+        assert hasattr(lib_built, name), name
+    assert lib_built.bt_version() >= 100
+
+
+def test_native_chunk_planner_matches_reference_table(lib_built):
+    g = np.load(os.path.join(GOLDEN, "chunking.npz"))
+    from beat_this_b200.inference import split_piece
+
+    st = (ctypes.c_int64 * 64)()
+    ln = (ctypes.c_int64 * 64)()
+    for T in list(g["Ts"]) + [2, 13, 1487, 2975, 2976, 100000]:
+        T = int(T)
+        n = lib_built.bt_plan_chunks(T, st, ln, 64)
+        chunks, starts = split_piece(torch.zeros(T, 1), 1500, 6, True)  # host mirror of the reference function
+        if n <= 64:
+            assert list(st[:n]) == list(starts), T
+            assert list(ln[:n]) == [len(c) for c in chunks], T
+        assert n == len(starts)
+        if f"starts_{T}" in g:
+            assert list(st[:n]) == list(g[f"starts_{T}"])
+    assert lib_built.bt_plan_chunks(0, None, None, 0) == 0
+    assert lib_built.bt_num_frames(661500) == 1501 and lib_built.bt_num_frames(440) == 1
+
+
+def test_no_gpu_fails_loudly(lib_built):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from beat_this_b200 import _lib
+    from beat_this_b200.inference import Spect2Frames
+
+    hp = _lib.bt_hparams(128, 128, 4, 6, 32, 32, 1, 1)
+    ctx = ctypes.c_void_p()
+    code = lib_built.bt_create(ctypes.byref(ctx), 0, ctypes.byref(hp), 0)
+    assert code != 0 and b"no CPU fallback" in lib_built.bt_last_error(None)
+    with pytest.raises(RuntimeError):
+        Spect2Frames("whatever.ckpt", "cpu")
+
+
+@pytest.mark.parametrize("name", ["small0"])
+def test_packed_parameters_reproduce_the_oracle(name):
+    """Fold/layout logic of weights.py: the kernel schedule emulated in torch with the packed
+    parameters (tests/packed_forward.py) must equal the oracle forward, stage by stage."""
+    import packed_forward as PF
+    from oracle import beat_this_oracle as O
+
+    hp = synthetic.model_hparams(name)
+    sd = synthetic.make_state_dict(hp, 0)
+    packed = weights.pack_parameters(sd, hp)
+    torch.manual_seed(1)
+    x = torch.rand(2, 90, 128) * 7
+    t1, t2 = {}, {}
+    with torch.inference_mode():
+        b, d = O.forward(sd, x, t1)
+        b2, d2 = PF.forward(packed, weights.filter_hparams(hp), x, t2)
+    for k in t1:
+        assert (t1[k] - t2[k]).abs().max() < 1e-4, k
+    assert (b - b2).abs().max() < 1e-4 and (d - d2).abs().max() < 1e-4
+    blob, names, sizes = weights.blob_from_packed(packed)
+    back = weights.packed_from_blob(blob, names, sizes)
+    assert all(np.array_equal(back[k], packed[k]) for k in packed)
+
+
+def test_checkpoint_layout_roundtrip(small0_ckpt):
+    from beat_this_b200.inference import load_checkpoint
+
+    ck = load_checkpoint(small0_ckpt)
+    assert set(ck) >= {"state_dict", "hyper_parameters"}
+    assert all(k.startswith("model.") for k in ck["state_dict"])
+    assert len(ck["state_dict"]) == 166
+    assert sum(v.numel() for v in ck["state_dict"].values()) == 2101357
+    with pytest.raises(ValueError):
+        load_checkpoint("/nonexistent/dir/nothing-here")  # falls through to the URL path, no network -> ValueError
+
+
+def test_api_surface_matches_reference_names():
+    import beat_this_b200.inference as I
+
+    for name in ["load_checkpoint", "load_model", "zeropad", "split_piece", "aggregate_prediction", "Spect2Frames",
+                 "Audio2Frames", "Audio2Beats", "File2Beats", "File2File", "CHECKPOINT_URL"]:
+        assert hasattr(I, name), name
+    assert issubclass(I.File2File, I.File2Beats) and issubclass(I.File2Beats, I.Audio2Beats)
+    assert issubclass(I.Audio2Beats, I.Audio2Frames) and issubclass(I.Audio2Frames, I.Spect2Frames)
+    # aggregate_prediction mirror: keep_first
+    chunks, starts = I.split_piece(torch.arange(3001.0)[:, None].repeat(1, 2), 1500, 6, True)
+    preds = [{"beat": c[:, 0] + 10000 * i, "downbeat": c[:, 1]} for i, c in enumerate(chunks)]
+    b, d = I.aggregate_prediction(preds, starts, 3001, 1500, 6, "keep_first", "cpu")
+    assert torch.equal(d, torch.arange(3001.0))
+    assert b[1487] == 1487 and b[1488] == 1488 + 10000 and b[2976] == 2976 + 20000 and b[2975] == 2975 + 10000
+
+
+def test_save_beat_tsv_and_beat_numbers(tmp_path):
+    from beat_this_b200.utils import infer_beat_numbers, save_beat_tsv
+
+    beats = np.array([0.5, 1.0, 1.5, 2.0, 2.5, 3.0, 3.5])
+    downs = np.array([1.0, 3.0])
+    assert list(infer_beat_numbers(beats, downs)) == [4, 1, 2, 3, 4, 1, 2]
+    with pytest.raises(ValueError):
+        infer_beat_numbers(beats, np.array([0.75]))
+    out = tmp_path / "sub" / "x.beats"
+    save_beat_tsv(beats, downs, str(out))
+    assert out.read_text().splitlines()[:2] == ["0.5\t4", "1.0\t1"]
+
+
+def test_load_audio_wav(tmp_path):
+    from scipy.io import wavfile
+
+    from beat_this_b200.preprocessing import load_audio
+
+    x = (np.sin(np.arange(2000) / 10) * 20000).astype(np.int16)
+    wavfile.write(tmp_path / "a.wav", 22050, np.stack([x, x // 2], 1))
+    wav, sr = load_audio(tmp_path / "a.wav")
+    assert sr == 22050 and wav.shape == (2000, 2) and wav.dtype == np.float64
+    assert np.allclose(wav[:, 0], x / 32768.0)
+    with pytest.raises(RuntimeError):
+        load_audio(tmp_path / "missing.wav")
+
+
+def test_mel_constants_match_oracle_filterbank():
+    from beat_this_b200.preprocessing import mel_constants, mel_filterbank
+    from oracle import beat_this_oracle as O
+
+    assert torch.equal(mel_filterbank(), O.mel_filterbank())
+    c = mel_constants()
+    ptr = c["mel.fb_ptr"].astype(int)
+    assert ptr[-1] == 1004 and len(c["mel.fb_w"]) == 1004
+    fb = O.mel_filterbank().numpy()
+    for m in (0, 5, 64, 127):
+        s = int(c["mel.fb_start"][m])
+        w = c["mel.fb_w"][ptr[m]:ptr[m + 1]]
+        assert np.array_equal(fb[s:s + len(w), m], w) and fb[:, m].sum() == pytest.approx(w.sum())
+
+
+GLOO_WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from beat_this_b200 import synthetic, weights
+from beat_this_b200.distributed import init_from_env, broadcast_packed, shard_indices, shard_by_cost, gather_results
+rank, world, local = init_from_env("gloo")
+packed = hp = None
+if rank == 0:
+    hp = weights.filter_hparams(synthetic.model_hparams("small0"))
+    packed = weights.pack_parameters(synthetic.make_state_dict(synthetic.model_hparams("small0"), 0), hp)
+packed, hp = broadcast_packed(packed, hp, "cpu")
+chk = float(sum(float(np.abs(v).sum()) for v in packed.values()))
+mine = shard_indices(10, rank, world)
+res = gather_results({i: (i * i, rank) for i in mine}, world)
+assert sorted(res) == list(range(10)) and all(res[i][0] == i * i for i in res)
+parts = shard_by_cost([11, 1, 1, 1, 5, 5, 2], world)
+assert sorted(sum(parts, [])) == list(range(7))
+t = torch.tensor([chk], dtype=torch.float64)
+lst = [torch.zeros_like(t) for _ in range(world)]
+dist.all_gather(lst, t)
+assert all(abs(float(x) - chk) < 1e-9 for x in lst), "ranks hold different weights"
+if rank == 0:
+    print("GLOO_OK", hp["transformer_dim"], len(packed))
+dist.destroy_process_group()
+"""
+
+
+def test_world_size_2_gloo_broadcast_and_sharding(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(script), ROOT]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "GLOO_OK 128" in res.stdout
