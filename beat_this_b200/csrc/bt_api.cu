@@ -56,15 +56,12 @@ struct bt_ctx {
   mutable char err[1024] = "";
   int64_t launches = 0;
   bool sync_debug = false;
-  bool v_mn = true;  // tensor-core attention reads V in its natural [key, d] layout (MN-major B operand);
-                     // BT_V_TRANSPOSED=1 selects the K-major variant with a transposed copy of V
 
   // workspace (sized for `wave` chunks of BT_CHUNK frames)
   int wave = 8;
   int ws_wave = 0;
   float *X0 = nullptr, *X1 = nullptr, *GATES = nullptr;
-  void *XB = nullptr, *XN = nullptr, *QKV = nullptr, *VT = nullptr, *O = nullptr, *H = nullptr;
-  int64_t vt_elems = 0;
+  void *XB = nullptr, *XN = nullptr, *QKV = nullptr, *O = nullptr, *H = nullptr;
   // spectrogram scratch for bt_audio2frames
   float* spect_ws = nullptr;
   int64_t spect_cap = 0;
@@ -219,7 +216,7 @@ int upload_stage(bt_ctx* c, size_t bytes, cudaStream_t st) {
 
 void free_ws(bt_ctx* c) {
   void** ptrs[] = {reinterpret_cast<void**>(&c->X0), reinterpret_cast<void**>(&c->X1),
-                   reinterpret_cast<void**>(&c->GATES), &c->XB, &c->XN, &c->QKV, &c->VT, &c->O, &c->H};
+                   reinterpret_cast<void**>(&c->GATES), &c->XB, &c->XN, &c->QKV, &c->O, &c->H};
   for (auto p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -276,11 +273,6 @@ int ensure_ws(bt_ctx* c) {
   BT_CUDA(c, cudaMalloc(&c->H, G * 4 * xe * act));
   if (c->dtype == BT_DTYPE_BF16) {
     BT_CUDA(c, cudaMalloc(&c->XB, G * xe * 2));
-    // transposed V: rows (seq,head,d) x padded length; rows = tokens*C/L
-    const int64_t lpad = (BT_CHUNK + 7) / 8 * 8;
-    c->vt_elems = G * (xe / BT_CHUNK) * lpad + 64;
-    BT_CUDA(c, cudaMalloc(&c->VT, c->vt_elems * 2));
-    BT_CUDA(c, cudaMemset(c->VT, 0, c->vt_elems * 2));
   }
   c->ws_wave = c->wave;
   return BT_OK;
@@ -362,8 +354,6 @@ int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool f
   e.C = C; e.heads = heads; e.posmode = freq ? 1 : 0; e.F = F;
   const bool tc_time = tc && !freq;
   e.qscale = tc_time ? inv_sqrt_d * 1.4426950408889634f : 1.0f;
-  const int lpad = (L + 7) / 8 * 8;
-  if (tc_time && !c->v_mn) { e.vt = c->VT; e.vt_ld = lpad; }
   GemmShape g = plain_shape(planes, L, 3 * C, C, C);
   int r = run_gemm(c, c->XN, w.wqkv, tp ? tp->qkv : nullptr, g, e, "gemm_qkv", st);
   if (r != BT_OK) return r;
@@ -433,7 +423,6 @@ int build_plans(bt_ctx* c, int nb, int L, WavePlans** out) {
   WavePlans* w = new WavePlans();
   c->plans[key] = w;
   char err[512] = "";
-  const int lpad = (L + 7) / 8 * 8;
   auto mk = [&](const void* A, const Param* W, const GemmShape& g, int planes_in) -> TcGemmPlan* {
     return tc_gemm_plan_create(A, W->b16, g, planes_in, err, sizeof(err));
   };
@@ -443,7 +432,7 @@ int build_plans(bt_ctx* c, int nb, int L, WavePlans** out) {
     a.gates = mk(c->XN, aw.wg, plain_shape(planes, L, 32, C, C), planes);
     if (!a.qkv || !a.out || !a.gates) return false;
     if (!freq) {
-      a.attn = tc_attn_plan_create(c->QKV, c->v_mn ? nullptr : c->VT, lpad, planes, L, C / 32, err, sizeof(err));
+      a.attn = tc_attn_plan_create(c->QKV, planes, L, C / 32, err, sizeof(err));
       if (!a.attn) return false;
     }
     return true;
@@ -620,8 +609,7 @@ int bt_create(bt_ctx** out, int device_ordinal, const bt_hparams* hp, int comput
   c->dtype = compute_dtype;
   const char* dbg = getenv("BT_SYNC_DEBUG");
   c->sync_debug = dbg && dbg[0] == '1';
-  const char* vtr = getenv("BT_V_TRANSPOSED");
-  c->v_mn = !(vtr && vtr[0] == '1');
+
   if (cudaEventCreateWithFlags(&c->stage_ev, cudaEventDisableTiming) != cudaSuccess) {
     delete c;
     return fail(nullptr, BT_ERR_CUDA, "cudaEventCreate failed");
@@ -966,8 +954,7 @@ int bt_debug_attention(bt_ctx* c, const float* q_dev, const float* k_dev, const 
   const int64_t M = static_cast<int64_t>(seqs) * L;
   const bool tc = c->dtype == BT_DTYPE_BF16;
   const size_t act = tc ? 2 : 4;
-  const int lpad = (L + 7) / 8 * 8;
-  void *qkv = nullptr, *vt = nullptr, *o = nullptr;
+  void *qkv = nullptr, *o = nullptr;
   float* gates = nullptr;
   BT_CUDA(c, cudaMalloc(&qkv, M * 3 * C * act));
   BT_CUDA(c, cudaMalloc(&o, M * C * act));
@@ -976,15 +963,9 @@ int bt_debug_attention(bt_ctx* c, const float* q_dev, const float* k_dev, const 
   BT_CUDA(c, cudaMemcpyAsync(gates, ones.data(), M * heads * 4, cudaMemcpyHostToDevice, st));
   int rc = BT_OK;
   if (tc) {
-    if (!c->v_mn) {
-      const int64_t vte = static_cast<int64_t>(seqs) * C * lpad;
-      BT_CUDA(c, cudaMalloc(&vt, vte * 2));
-      BT_CUDA(c, cudaMemsetAsync(vt, 0, vte * 2, st));
-    }
-    launch_pack_qkv_test(q_dev, k_dev, v_dev, qkv, vt, lpad, seqs, L, heads,
-                         0.17677669529663687f * 1.4426950408889634f, 1, st);
+    launch_pack_qkv_test(q_dev, k_dev, v_dev, qkv, seqs, L, heads, 0.17677669529663687f * 1.4426950408889634f, 1, st);
     char err[512] = "";
-    TcAttnPlan* p = tc_attn_plan_create(qkv, vt, lpad, seqs, L, heads, err, sizeof(err));
+    TcAttnPlan* p = tc_attn_plan_create(qkv, seqs, L, heads, err, sizeof(err));
     if (!p) rc = fail(c, BT_ERR_CUDA, "%s", err);
     else {
       launch_attn_time_tc(p, gates, o, st);
@@ -994,14 +975,13 @@ int bt_debug_attention(bt_ctx* c, const float* q_dev, const float* k_dev, const 
     if (rc == BT_OK && se != cudaSuccess) rc = fail(c, BT_ERR_CUDA, "tc attention: %s", cudaGetErrorString(se));
     if (p) tc_attn_plan_destroy(p);
   } else {
-    launch_pack_qkv_test(q_dev, k_dev, v_dev, qkv, nullptr, 0, seqs, L, heads, 1.0f, 0, st);
+    launch_pack_qkv_test(q_dev, k_dev, v_dev, qkv, seqs, L, heads, 1.0f, 0, st);
     launch_attn_time_simt(static_cast<const float*>(qkv), gates, o_dev, seqs, L, heads, st);
     cudaError_t se = cudaStreamSynchronize(st);
     if (se != cudaSuccess) rc = fail(c, BT_ERR_CUDA, "simt attention: %s", cudaGetErrorString(se));
   }
   c->launches += 2;
   cudaFree(qkv); cudaFree(o); cudaFree(gates);
-  if (vt) cudaFree(vt);
   return rc;
 }
 

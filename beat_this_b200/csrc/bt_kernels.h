@@ -27,7 +27,7 @@ struct GemmShape {
 
 // Epilogue description (shared by the fp32 CUDA-core GEMM and the bf16 tcgen05 GEMM).
 struct EpiParams {
-  int kind;            // 0 generic, 1 qkv (RoPE + scaling + optional V transpose), 2 attention gates:
+  int kind;            // 0 generic, 1 qkv (RoPE + q scaling; V as fp16 in the tensor-core path), 2 attention gates:
                        //   out_f32[m*heads + n] = sigmoid(acc + bias[n]) for n < heads (N padded to 32)
   const float* bias;   // [N] or null
   int gelu;            // exact-erf GELU after bias
@@ -45,8 +45,6 @@ struct EpiParams {
   int posmode;  // 0: position = m % L (time attention)   1: position = (m / L) % F (freq attention)
   int F;
   float qscale;  // multiplied into q after RoPE
-  void* vt;      // when non-null V is written transposed: vt[((seq*heads + h)*32 + d) * vt_ld + t],
-  int vt_ld;     //   seq = m / L, t = m % L  (time attention, tensor-core path)
 };
 
 // ---- fp32 CUDA-core path -------------------------------------------------------------------
@@ -85,11 +83,10 @@ void launch_peakpick(const float* beat, const float* down, const int64_t* frame_
                      int max_peaks, cudaStream_t st);
 void launch_f32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t st);
 void launch_bf16_to_f32(const void* in, float* out, int64_t n, cudaStream_t st);
-// [seqs, L, heads*32] fp32 q,k,v -> packed qkv buffer [seqs*L, 3C] of the activation dtype,
-// bf16 path: V transposed into vt.  (test hook for bt_debug_attention)
-void launch_pack_qkv_test(const float* q, const float* k, const float* v, void* qkv, void* vt,
-                          int vt_ld, int seqs, int L, int heads, float qscale, int act_bf16,
-                          cudaStream_t st);
+// [seqs, L, heads*32] fp32 q,k,v -> packed qkv buffer [seqs*L, 3C] of the activation dtype
+// (bf16 path: q,k bf16, v fp16).  (test hook for bt_debug_attention)
+void launch_pack_qkv_test(const float* q, const float* k, const float* v, void* qkv, int seqs, int L,
+                          int heads, float qscale, int act_bf16, cudaStream_t st);
 
 // ---- bf16 tcgen05 path ------------------------------------------------------------------------
 struct TcGemmPlan;  // cached tensor maps + launch geometry
@@ -99,8 +96,7 @@ void tc_gemm_plan_destroy(TcGemmPlan*);
 int launch_gemm_tc(const TcGemmPlan* plan, const EpiParams& e, cudaStream_t st);
 
 struct TcAttnPlan;
-TcAttnPlan* tc_attn_plan_create(const void* qkv_bf16, const void* vt_bf16, int vt_ld, int seqs, int L,
-                                int heads, char* err, int errlen);
+TcAttnPlan* tc_attn_plan_create(const void* qkv_bf16, int seqs, int L, int heads, char* err, int errlen);
 void tc_attn_plan_destroy(TcAttnPlan*);
 int launch_attn_time_tc(const TcAttnPlan* plan, const float* gates, void* out_bf16, cudaStream_t st);
 

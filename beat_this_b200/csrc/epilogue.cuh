@@ -2,6 +2,8 @@
 // A thread hands over CNT consecutive accumulator columns [n0, n0+CNT) of output row m.
 #pragma once
 #include "bt_kernels.h"
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace bt {
@@ -39,6 +41,27 @@ __device__ __forceinline__ void store_act<bf16, 32>(bf16* p, const float (&v)[32
   }
 }
 
+// In the tensor-core path V (and the softmax probabilities P) are IEEE fp16, not bf16: the
+// attention kernel exponentiates two scores per MUFU op with ex2.approx.f16x2, so P is born
+// as fp16 and the P*V MMA takes fp16 x fp16 operands (same tensor rate, 3 more mantissa bits).
+template <typename TAct>
+__device__ __forceinline__ void store_v32(TAct* p, const float (&v)[32]);
+template <>
+__device__ __forceinline__ void store_v32<float>(float* p, const float (&v)[32]) { store_act<float, 32>(p, v); }
+template <>
+__device__ __forceinline__ void store_v32<bf16>(bf16* p, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    __half2 h;
+    h = __floats2half2_rn(v[8 * i + 0], v[8 * i + 1]); u.x = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]); u.y = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]); u.z = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]); u.w = *reinterpret_cast<uint32_t*>(&h);
+    reinterpret_cast<uint4*>(p)[i] = u;
+  }
+}
+
 // erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7) on the MUFU/FMA pipes: the tensor-core
 // epilogue evaluates GELU for every FFN hidden element and erff()'s ~35 instructions made it
 // issue-bound.  gelu(x) = 0.5 x (1 + erf(x / sqrt 2)).
@@ -69,8 +92,12 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& e, int L, int64_
                                                float (&v)[CNT], const float* rpre = nullptr) {
   if (e.kind == 0) {
     if (e.bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
 #pragma unroll
-      for (int i = 0; i < CNT; ++i) v[i] += __ldg(e.bias + n0 + i);
+      for (int i = 0; i < CNT / 4; ++i) {
+        const float4 q = __ldg(b4 + i);
+        v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+      }
     }
     if (e.gelu) {
 #pragma unroll
@@ -101,33 +128,34 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& e, int L, int64_
     // qkv: RoPE on interleaved pairs (rotary_embedding_torch semantics, reference
     // roformer.py:121-123): out[2i] = x[2i] cos - x[2i+1] sin ; out[2i+1] = x[2i+1] cos + x[2i] sin
     const int which = n0 / e.C;          // 0 q, 1 k, 2 v
-    const int c = n0 - which * e.C;      // column inside q/k/v
-    const int t = static_cast<int>(m % L);
+    TAct* dst = reinterpret_cast<TAct*>(e.out_act) + m * e.ldo_act + n0;
     if (which < 2) {
-      const int pos = e.posmode == 0 ? t : static_cast<int>((m / L) % e.F);
-      const int d0 = c & 31;             // first head-dim index handled here (even)
-      const float* cs = e.rope_cos + pos * 16 + (d0 >> 1);
-      const float* sn = e.rope_sin + pos * 16 + (d0 >> 1);
       const float sc = which == 0 ? e.qscale : 1.0f;
+      if (rpre) {  // cos[16] | sin[16] of this row's position, preloaded by the caller (CNT == 32)
 #pragma unroll
-      for (int i = 0; i < CNT / 2; ++i) {
-        const float co = __ldg(cs + i), si = __ldg(sn + i);
-        const float x0 = v[2 * i], x1 = v[2 * i + 1];
-        v[2 * i] = (x0 * co - x1 * si) * sc;
-        v[2 * i + 1] = (x1 * co + x0 * si) * sc;
+        for (int i = 0; i < CNT / 2; ++i) {
+          const float co = rpre[i], si = rpre[16 + i];
+          const float x0 = v[2 * i], x1 = v[2 * i + 1];
+          v[2 * i] = (x0 * co - x1 * si) * sc;
+          v[2 * i + 1] = (x1 * co + x0 * si) * sc;
+        }
+      } else {
+        const int c = n0 - which * e.C;
+        const int pos = e.posmode == 0 ? static_cast<int>(m % L) : static_cast<int>((m / L) % e.F);
+        const float* cs = e.rope_cos + pos * 16 + ((c & 31) >> 1);
+        const float* sn = e.rope_sin + pos * 16 + ((c & 31) >> 1);
+#pragma unroll
+        for (int i = 0; i < CNT / 2; ++i) {
+          const float co = __ldg(cs + i), si = __ldg(sn + i);
+          const float x0 = v[2 * i], x1 = v[2 * i + 1];
+          v[2 * i] = (x0 * co - x1 * si) * sc;
+          v[2 * i + 1] = (x1 * co + x0 * si) * sc;
+        }
       }
-    }
-    if (which == 2 && e.vt) {
-      // transposed V for the tensor-core attention: consecutive lanes (= consecutive t) write
-      // consecutive addresses for a fixed d.
-      const int64_t seq = m / L;
-      const int h = c >> 5;
-      TAct* base = reinterpret_cast<TAct*>(e.vt) +
-                   ((seq * e.heads + h) * 32 + (c & 31)) * static_cast<int64_t>(e.vt_ld) + t;
-#pragma unroll
-      for (int i = 0; i < CNT; ++i) base[static_cast<int64_t>(i) * e.vt_ld] = to_out<TAct>(v[i]);
+      store_act<TAct, CNT>(dst, v);
     } else {
-      store_act<TAct, CNT>(reinterpret_cast<TAct*>(e.out_act) + m * e.ldo_act + n0, v);
+      if constexpr (CNT == 32) store_v32<TAct>(dst, v);
+      else store_act<TAct, CNT>(dst, v);
     }
   }
 }

@@ -1,5 +1,7 @@
 // HBM-bound kernels of the path: log-mel frontend, stem conv, RMSNorm(+gates),
 // frequency-direction attention, head + aggregation scatter, peak picking.
+#include <cuda_fp16.h>
+
 #include "bt_kernels.h"
 #include "common.cuh"
 
@@ -260,6 +262,25 @@ __device__ __forceinline__ void load_row32<bf16>(const bf16* p, float (&v)[32]) 
   }
 }
 
+template <typename TAct>
+__device__ __forceinline__ void load_vrow32(const TAct* p, float (&v)[32]) {
+  if constexpr (sizeof(TAct) == 4) {
+    load_row32<TAct>(p, v);
+  } else {  // V is fp16 in the tensor-core path (epilogue.cuh store_v32)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 q = reinterpret_cast<const uint4*>(p)[i];
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+        v[8 * i + 2 * j] = f.x;
+        v[8 * i + 2 * j + 1] = f.y;
+      }
+    }
+  }
+}
+
 template <typename TAct, int F>
 __global__ void __launch_bounds__(128, 4)
 attn_freq_kernel(const TAct* __restrict__ qkv, const float* __restrict__ gates, TAct* __restrict__ out,
@@ -292,7 +313,7 @@ attn_freq_kernel(const TAct* __restrict__ qkv, const float* __restrict__ gates, 
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       reinterpret_cast<float4*>(kd)[i] = make_float4(kv[4 * i], kv[4 * i + 1], kv[4 * i + 2], kv[4 * i + 3]);
-    load_row32<TAct>(rp + 2 * C, kv);
+    load_vrow32<TAct>(rp + 2 * C, kv);
     float* vd = &Vs[wib][g * GS + f * RS];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -562,8 +583,8 @@ void launch_bf16_to_f32(const void* in, float* out, int64_t n, cudaStream_t st) 
 
 template <typename TAct>
 __global__ void pack_qkv_test_kernel(const float* __restrict__ q, const float* __restrict__ k,
-                                     const float* __restrict__ v, TAct* __restrict__ qkv, TAct* __restrict__ vt,
-                                     int vt_ld, int seqs, int L, int heads, float qscale) {
+                                     const float* __restrict__ v, TAct* __restrict__ qkv, int seqs, int L,
+                                     int heads, float qscale) {
   const int C = heads * 32;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t n = static_cast<int64_t>(seqs) * L * C;
@@ -572,24 +593,17 @@ __global__ void pack_qkv_test_kernel(const float* __restrict__ q, const float* _
   const int64_t m = i / C;
   qkv[m * 3 * C + c] = to_out<TAct>(q[i] * qscale);
   qkv[m * 3 * C + C + c] = to_out<TAct>(k[i]);
-  if (vt) {
-    const int64_t seq = m / L;
-    const int t = static_cast<int>(m % L);
-    vt[((seq * heads + (c >> 5)) * 32 + (c & 31)) * vt_ld + t] = to_out<TAct>(v[i]);
-  } else {
-    qkv[m * 3 * C + 2 * C + c] = to_out<TAct>(v[i]);
-  }
+  if constexpr (sizeof(TAct) == 2) reinterpret_cast<__half*>(qkv)[m * 3 * C + 2 * C + c] = __float2half_rn(v[i]);
+  else qkv[m * 3 * C + 2 * C + c] = v[i];
 }
-void launch_pack_qkv_test(const float* q, const float* k, const float* v, void* qkv, void* vt, int vt_ld,
-                          int seqs, int L, int heads, float qscale, int act_bf16, cudaStream_t st) {
+void launch_pack_qkv_test(const float* q, const float* k, const float* v, void* qkv, int seqs, int L, int heads,
+                          float qscale, int act_bf16, cudaStream_t st) {
   const int64_t n = static_cast<int64_t>(seqs) * L * heads * 32;
   const unsigned grid = static_cast<unsigned>(ceil_div64(n, 256));
   if (act_bf16)
-    pack_qkv_test_kernel<bf16><<<grid, 256, 0, st>>>(q, k, v, reinterpret_cast<bf16*>(qkv),
-                                                       reinterpret_cast<bf16*>(vt), vt_ld, seqs, L, heads, qscale);
+    pack_qkv_test_kernel<bf16><<<grid, 256, 0, st>>>(q, k, v, reinterpret_cast<bf16*>(qkv), seqs, L, heads, qscale);
   else
-    pack_qkv_test_kernel<float><<<grid, 256, 0, st>>>(q, k, v, reinterpret_cast<float*>(qkv),
-                                                        reinterpret_cast<float*>(vt), vt_ld, seqs, L, heads, qscale);
+    pack_qkv_test_kernel<float><<<grid, 256, 0, st>>>(q, k, v, reinterpret_cast<float*>(qkv), seqs, L, heads, qscale);
 }
 
 }  // namespace bt

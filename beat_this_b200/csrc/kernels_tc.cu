@@ -7,6 +7,7 @@
 //   attn_tc_kernel  -- flash attention for head_dim 32 over sequences of up to 1500 frames
 //                      (time-direction attention of the frontend and the 6 main layers).
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstdio>
 #include <cstring>
@@ -178,6 +179,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool valid = t < g.L;
       const int64_t m = static_cast<int64_t>(p_out) * g.L + t;
       float rv[32];
+      const bool pre_rope = e.kind == 1 && valid;
+      if (pre_rope) {  // cos[16] | sin[16] of this row's position, reused by every q/k head of the row
+        const int pos = e.posmode == 0 ? t : static_cast<int>((m / g.L) % e.F);
+        const float4* c4 = reinterpret_cast<const float4*>(e.rope_cos + pos * 16);
+        const float4* s4 = reinterpret_cast<const float4*>(e.rope_sin + pos * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 a = __ldg(c4 + i), b = __ldg(s4 + i);
+          rv[4 * i] = a.x; rv[4 * i + 1] = a.y; rv[4 * i + 2] = a.z; rv[4 * i + 3] = a.w;
+          rv[16 + 4 * i] = b.x; rv[16 + 4 * i + 1] = b.y; rv[16 + 4 * i + 2] = b.z; rv[16 + 4 * i + 3] = b.w;
+        }
+      }
       const bool pre = e.kind == 0 && e.resid != nullptr && valid;
       if (pre) {  // issue the residual loads before blocking on the accumulator
         const float4* r4 = reinterpret_cast<const float4*>(e.resid + m * e.ldr + nt * BN + c_begin * 32);
@@ -197,7 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          epilogue_apply<bf16, 32>(e, g.L, m, nt * BN + c * 32, v, (pre && c == c_begin) ? rv : nullptr);
+          epilogue_apply<bf16, 32>(e, g.L, m, nt * BN + c * 32, v, (pre_rope || (pre && c == c_begin)) ? rv : nullptr);
         }
       }
       tc_fence_before();
@@ -288,11 +301,15 @@ int launch_gemm_tc(const TcGemmPlan* p, const EpiParams& e, cudaStream_t st) {
 // ========================================================================== attention
 // One CTA per (sequence, head, 128-query tile).  Warps 0-3: softmax (one query row per
 // thread, the tcgen05.ld 32x32b lane mapping); warp 4 lane 0: TMA producer + MMA issuer.
-//   S = Q K^T      : A = Q  [128 x 32] (SW64), B = K tile [128 keys x 32] (SW64) -> TMEM cols [0,128)
-//   O_j = P_j V_j  : A = P  [128 x 128] bf16 written by the softmax threads in the SW128
-//                    K-major layout, B = V^T tile [32 x 128 keys] (SW128) -> TMEM cols 128+32*(j%2)
+//   S = Q K^T      : A = Q  [128 x 32] bf16 (K-major, SW64), B = K tile [128 keys x 32] bf16 (K-major,
+//                    SW64) -> TMEM cols [0,128)
+//   O_j = P_j V_j  : A = P  [128 x 128] fp16 written by the softmax threads in the SW128 K-major
+//                    layout, B = V tile [128 keys x 32] fp16 exactly as the QKV GEMM stored it
+//                    (MN-major operand, SW64) -> TMEM cols 128 + 32*(j%2)
 // The running output lives in registers (o = o*alpha + O_j), so TMEM is never read-modify-
 // written.  q is pre-scaled by log2(e)/sqrt(32) in the QKV GEMM epilogue -> exp2 softmax.
+// exp2 is evaluated two scores at a time with ex2.approx.f16x2 (the MUFU pipe is the
+// bottleneck of head_dim-32 attention: 128 tensor FLOPs per exponential).
 constexpr int AT_BQ = 128, AT_BKV = 128;
 constexpr int AT_THREADS = 160;
 constexpr int AT_SQ = 8192, AT_SK = 8192, AT_SV = 8192, AT_SP = 32768;
@@ -303,18 +320,32 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-
-// B operand in MN-major form (N = head dim contiguous): V tile [128 keys][32 d] exactly as the
-// QKV GEMM stores it -- rows of 64 B, SWIZZLE_64B, 8-row groups 512 B apart (SBO).
+// 2^x for two fp32 inputs -> packed fp16x2 (lo = 2^x0, hi = 2^x1) with ONE MUFU op
+__device__ __forceinline__ uint32_t ex2_f16x2(float x0, float x1) {
+  uint32_t h, y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(h));
+  return y;
+}
+__device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+// B operand in MN-major form (N = head dim contiguous): V tile [128 keys][32 d] -- rows of
+// 64 B, SWIZZLE_64B, 8-row groups 512 B apart (SBO).
 __device__ __forceinline__ uint64_t make_mnmajor_desc_sw64(uint32_t smem_addr) {
   return static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (static_cast<uint64_t>(512 >> 4) << 32) |
          (1ull << 46) | (4ull << 61);
 }
+// kind::f16 instruction descriptor with fp16 A/B (format 0), fp32 accumulate, B MN-major
+__host__ __device__ constexpr uint32_t make_idesc_f16_bmn(int M, int N) {
+  return (1u << 4) | (1u << 16) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
 
-template <bool V_MN>
 __global__ void __launch_bounds__(AT_THREADS, 2)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVt,
-               const float* __restrict__ gates, bf16* __restrict__ out, int L, int heads) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict__ gates, bf16* __restrict__ out,
+               int L, int heads) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -337,7 +368,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmQK);
-    tma_prefetch_desc(&tmVt);
     mbar_init(bar_q, 1);
     mbar_init(&bar_kv[0], 1); mbar_init(&bar_kv[1], 1);
     mbar_init(bar_s, 1);
@@ -354,17 +384,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
   if (warp == 4) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 32) | (V_MN ? (1u << 16) : 0u);  // bit 16: B is MN-major
+      constexpr uint32_t idesc_o = make_idesc_f16_bmn(128, 32);
       auto load_kv = [&](int j) {
         const int st = j & 1;
         mbar_expect_tx(&bar_kv[st], AT_SK + AT_SV);
         tma_load_3d(sK + st * AT_SK, &tmQK, &bar_kv[st], C + h * 32, j * AT_BKV, seq);
-        if constexpr (V_MN) {
-          tma_load_3d(sV + st * AT_SV, &tmQK, &bar_kv[st], 2 * C + h * 32, j * AT_BKV, seq);
-        } else {
-          tma_load_2d(sV + st * AT_SV, &tmVt, &bar_kv[st], j * AT_BKV, (seq * heads + h) * 32);
-          tma_load_2d(sV + st * AT_SV + 4096, &tmVt, &bar_kv[st], j * AT_BKV + 64, (seq * heads + h) * 32);
-        }
+        tma_load_3d(sV + st * AT_SV, &tmQK, &bar_kv[st], 2 * C + h * 32, j * AT_BKV, seq);
       };
       auto issue_s = [&](int j) {
         const uint32_t a = smem_u32(sQ), b = smem_u32(sK + (j & 1) * AT_SK);
@@ -397,9 +422,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t aoff = (k >> 2) * 16384 + (k & 3) * 32;
-          const uint64_t bdesc = V_MN ? make_mnmajor_desc_sw64(vb + k * 1024)
-                                      : make_kmajor_desc<128>(vb + (k >> 2) * 4096 + (k & 3) * 32);
-          umma_bf16(d_o, make_kmajor_desc<128>(pa + aoff), bdesc, idesc_o, k != 0 ? 1u : 0u);
+          umma_bf16(d_o, make_kmajor_desc<128>(pa + aoff), make_mnmajor_desc_sw64(vb + k * 1024), idesc_o,
+                    k != 0 ? 1u : 0u);
         }
         umma_commit(&bar_o[st]);
         if (j + 2 < nkv) {
@@ -442,16 +466,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
       float sum = 0.f;
       uint8_t* prow = sP + st * AT_SP + row * 128;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 keys (16 bytes of bf16)
-        float p[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          p[i] = ex2_approx(s[c * 8 + i] - m_new);
-          sum += p[i];
-        }
+      for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 keys (16 bytes of fp16)
         uint4 u;
-        u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
-        u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
+        u.x = ex2_f16x2(s[c * 8 + 0] - m_new, s[c * 8 + 1] - m_new);
+        u.y = ex2_f16x2(s[c * 8 + 2] - m_new, s[c * 8 + 3] - m_new);
+        u.z = ex2_f16x2(s[c * 8 + 4] - m_new, s[c * 8 + 5] - m_new);
+        u.w = ex2_f16x2(s[c * 8 + 6] - m_new, s[c * 8 + 7] - m_new);
+        const uint32_t hs = hadd2_u32(hadd2_u32(u.x, u.y), hadd2_u32(u.z, u.w));
+        const float2 fs = __half22float2(*reinterpret_cast<const __half2*>(&hs));
+        sum += fs.x + fs.y;
         *reinterpret_cast<uint4*>(prow + (c >> 3) * 16384 + (((c & 7) ^ (row & 7)) << 4)) = u;
       }
       l = l * ex2_approx(m_prev - m_new) + sum;
@@ -499,41 +522,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
 }
 
 struct TcAttnPlan {
-  CUtensorMap tmQK, tmVt;
+  CUtensorMap tmQK;
   int seqs, L, heads;
-  bool v_mn;
 };
 
-TcAttnPlan* tc_attn_plan_create(const void* qkv, const void* vt, int vt_ld, int seqs, int L, int heads,
-                                char* err, int errlen) {
+TcAttnPlan* tc_attn_plan_create(const void* qkv, int seqs, int L, int heads, char* err, int errlen) {
   TcAttnPlan* p = new TcAttnPlan();
   p->seqs = seqs; p->L = L; p->heads = heads;
-  p->v_mn = vt == nullptr;
   const int C = heads * 32;
-  {
-    const uint64_t dims[3] = {static_cast<uint64_t>(3 * C), static_cast<uint64_t>(L), static_cast<uint64_t>(seqs)};
-    const uint64_t strides[2] = {static_cast<uint64_t>(3 * C) * 2, static_cast<uint64_t>(L) * 3 * C * 2};
-    const uint32_t box[3] = {32, AT_BQ, 1};
-    if (!make_tmap(&p->tmQK, qkv, 3, dims, strides, box, 64, err, errlen)) { delete p; return nullptr; }
-  }
-  if (p->v_mn) {
-    p->tmVt = p->tmQK;
-  } else {
-    const uint64_t dims[2] = {static_cast<uint64_t>(L), static_cast<uint64_t>(seqs) * heads * 32};
-    const uint64_t strides[1] = {static_cast<uint64_t>(vt_ld) * 2};
-    const uint32_t box[2] = {64, 32};
-    if (!make_tmap(&p->tmVt, vt, 2, dims, strides, box, 128, err, errlen)) { delete p; return nullptr; }
-  }
+  const uint64_t dims[3] = {static_cast<uint64_t>(3 * C), static_cast<uint64_t>(L), static_cast<uint64_t>(seqs)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(3 * C) * 2, static_cast<uint64_t>(L) * 3 * C * 2};
+  const uint32_t box[3] = {32, AT_BQ, 1};
+  if (!make_tmap(&p->tmQK, qkv, 3, dims, strides, box, 64, err, errlen)) { delete p; return nullptr; }
   return p;
 }
 void tc_attn_plan_destroy(TcAttnPlan* p) { delete p; }
 
 int launch_attn_time_tc(const TcAttnPlan* p, const float* gates, void* out, cudaStream_t st) {
   dim3 grid(ceil_div(p->L, AT_BQ), p->heads, p->seqs);
-  if (p->v_mn)
-    attn_tc_kernel<true><<<grid, AT_THREADS, AT_SMEM, st>>>(p->tmQK, p->tmVt, gates, reinterpret_cast<bf16*>(out), p->L, p->heads);
-  else
-    attn_tc_kernel<false><<<grid, AT_THREADS, AT_SMEM, st>>>(p->tmQK, p->tmVt, gates, reinterpret_cast<bf16*>(out), p->L, p->heads);
+  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(p->tmQK, gates, reinterpret_cast<bf16*>(out), p->L, p->heads);
   return 0;
 }
 
@@ -551,8 +558,7 @@ int tc_init(char* err, int errlen) {
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaError_t r = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-  if (r == cudaSuccess) r = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+  cudaError_t r = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
   if (r != cudaSuccess) {
     snprintf(err, errlen, "cudaFuncSetAttribute(attn_tc_kernel) failed: %s", cudaGetErrorString(r));
     return -1;
