@@ -27,7 +27,7 @@ struct GemmShape {
 
 // Epilogue description (shared by the fp32 CUDA-core GEMM and the bf16 tcgen05 GEMM).
 struct EpiParams {
-  int kind;            // 0 generic, 1 qkv (RoPE + q scaling; V as fp16 in the tensor-core path), 2 attention gates:
+  int kind;            // 0 generic, 1 qkv (RoPE + q scaling), 2 attention gates:
                        //   out_f32[m*heads + n] = sigmoid(acc + bias[n]) for n < heads (N padded to 32)
   const float* bias;   // [N] or null
   int gelu;            // exact-erf GELU after bias
@@ -84,7 +84,7 @@ void launch_peakpick(const float* beat, const float* down, const int64_t* frame_
 void launch_f32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t st);
 void launch_bf16_to_f32(const void* in, float* out, int64_t n, cudaStream_t st);
 // [seqs, L, heads*32] fp32 q,k,v -> packed qkv buffer [seqs*L, 3C] of the activation dtype
-// (bf16 path: q,k bf16, v fp16).  (test hook for bt_debug_attention)
+// (test hook for bt_debug_attention)
 void launch_pack_qkv_test(const float* q, const float* k, const float* v, void* qkv, int seqs, int L,
                           int heads, float qscale, int act_bf16, cudaStream_t st);
 

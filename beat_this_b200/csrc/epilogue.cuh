@@ -41,27 +41,6 @@ __device__ __forceinline__ void store_act<bf16, 32>(bf16* p, const float (&v)[32
   }
 }
 
-// In the tensor-core path V (and the softmax probabilities P) are IEEE fp16, not bf16: the
-// attention kernel exponentiates two scores per MUFU op with ex2.approx.f16x2, so P is born
-// as fp16 and the P*V MMA takes fp16 x fp16 operands (same tensor rate, 3 more mantissa bits).
-template <typename TAct>
-__device__ __forceinline__ void store_v32(TAct* p, const float (&v)[32]);
-template <>
-__device__ __forceinline__ void store_v32<float>(float* p, const float (&v)[32]) { store_act<float, 32>(p, v); }
-template <>
-__device__ __forceinline__ void store_v32<bf16>(bf16* p, const float (&v)[32]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 u;
-    __half2 h;
-    h = __floats2half2_rn(v[8 * i + 0], v[8 * i + 1]); u.x = *reinterpret_cast<uint32_t*>(&h);
-    h = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]); u.y = *reinterpret_cast<uint32_t*>(&h);
-    h = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]); u.z = *reinterpret_cast<uint32_t*>(&h);
-    h = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]); u.w = *reinterpret_cast<uint32_t*>(&h);
-    reinterpret_cast<uint4*>(p)[i] = u;
-  }
-}
-
 // erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7) on the MUFU/FMA pipes: the tensor-core
 // epilogue evaluates GELU for every FFN hidden element and erff()'s ~35 instructions made it
 // issue-bound.  gelu(x) = 0.5 x (1 + erf(x / sqrt 2)).
@@ -154,8 +133,7 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& e, int L, int64_
       }
       store_act<TAct, CNT>(dst, v);
     } else {
-      if constexpr (CNT == 32) store_v32<TAct>(dst, v);
-      else store_act<TAct, CNT>(dst, v);
+      store_act<TAct, CNT>(dst, v);
     }
   }
 }

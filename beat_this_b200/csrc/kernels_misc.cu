@@ -262,25 +262,6 @@ __device__ __forceinline__ void load_row32<bf16>(const bf16* p, float (&v)[32]) 
   }
 }
 
-template <typename TAct>
-__device__ __forceinline__ void load_vrow32(const TAct* p, float (&v)[32]) {
-  if constexpr (sizeof(TAct) == 4) {
-    load_row32<TAct>(p, v);
-  } else {  // V is fp16 in the tensor-core path (epilogue.cuh store_v32)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint4 q = reinterpret_cast<const uint4*>(p)[i];
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-        v[8 * i + 2 * j] = f.x;
-        v[8 * i + 2 * j + 1] = f.y;
-      }
-    }
-  }
-}
-
 template <typename TAct, int F>
 __global__ void __launch_bounds__(128, 4)
 attn_freq_kernel(const TAct* __restrict__ qkv, const float* __restrict__ gates, TAct* __restrict__ out,
@@ -313,7 +294,7 @@ attn_freq_kernel(const TAct* __restrict__ qkv, const float* __restrict__ gates, 
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       reinterpret_cast<float4*>(kd)[i] = make_float4(kv[4 * i], kv[4 * i + 1], kv[4 * i + 2], kv[4 * i + 3]);
-    load_vrow32<TAct>(rp + 2 * C, kv);
+    load_row32<TAct>(rp + 2 * C, kv);
     float* vd = &Vs[wib][g * GS + f * RS];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -593,8 +574,7 @@ __global__ void pack_qkv_test_kernel(const float* __restrict__ q, const float* _
   const int64_t m = i / C;
   qkv[m * 3 * C + c] = to_out<TAct>(q[i] * qscale);
   qkv[m * 3 * C + C + c] = to_out<TAct>(k[i]);
-  if constexpr (sizeof(TAct) == 2) reinterpret_cast<__half*>(qkv)[m * 3 * C + 2 * C + c] = __float2half_rn(v[i]);
-  else qkv[m * 3 * C + 2 * C + c] = v[i];
+  qkv[m * 3 * C + 2 * C + c] = to_out<TAct>(v[i]);
 }
 void launch_pack_qkv_test(const float* q, const float* k, const float* v, void* qkv, int seqs, int L, int heads,
                           float qscale, int act_bf16, cudaStream_t st) {

@@ -303,44 +303,47 @@ int launch_gemm_tc(const TcGemmPlan* p, const EpiParams& e, cudaStream_t st) {
 // thread, the tcgen05.ld 32x32b lane mapping); warp 4 lane 0: TMA producer + MMA issuer.
 //   S = Q K^T      : A = Q  [128 x 32] bf16 (K-major, SW64), B = K tile [128 keys x 32] bf16 (K-major,
 //                    SW64) -> TMEM cols [0,128)
-//   O_j = P_j V_j  : A = P  [128 x 128] fp16 written by the softmax threads in the SW128 K-major
-//                    layout, B = V tile [128 keys x 32] fp16 exactly as the QKV GEMM stored it
+//   O_j = P_j V_j  : A = P  [128 x 128] bf16 written by the softmax threads in the SW128 K-major
+//                    layout, B = V tile [128 keys x 32] bf16 exactly as the QKV GEMM stored it
 //                    (MN-major operand, SW64) -> TMEM cols 128 + 32*(j%2)
 // The running output lives in registers (o = o*alpha + O_j), so TMEM is never read-modify-
 // written.  q is pre-scaled by log2(e)/sqrt(32) in the QKV GEMM epilogue -> exp2 softmax.
-// exp2 is evaluated two scores at a time with ex2.approx.f16x2 (the MUFU pipe is the
-// bottleneck of head_dim-32 attention: 128 tensor FLOPs per exponential).
+// (ex2.approx.f16x2 -- two exponentials per MUFU op -- was measured: 28% SLOWER than fp32
+// ex2 + bf16 pack on B200, profiles/r1_notes.md.)
 constexpr int AT_BQ = 128, AT_BKV = 128;
 constexpr int AT_THREADS = 160;
-constexpr int AT_SQ = 8192, AT_SK = 8192, AT_SV = 8192, AT_SP = 32768;
-constexpr int AT_SMEM = AT_SQ + 2 * AT_SK + 2 * AT_SV + 2 * AT_SP + 1024 + 128;
+constexpr int AT_SQ = 8192, AT_SK = 8192, AT_SV = 8192, AT_SONES = 8192, AT_SP = 32768;
+constexpr int AT_SMEM = AT_SQ + 2 * AT_SK + 2 * AT_SV + AT_SONES + AT_SP + 1024 + 128;
+constexpr int AT_POLY_MOD = 4;  // every AT_POLY_MOD-th exponential runs on the FMA pipe instead of MUFU
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x for two fp32 inputs -> packed fp16x2 (lo = 2^x0, hi = 2^x1) with ONE MUFU op
-__device__ __forceinline__ uint32_t ex2_f16x2(float x0, float x1) {
-  uint32_t h, y;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(h));
-  return y;
+// 2^x for x <= 0 on the FMA/ALU pipes (Cody-Waite split + degree-3 polynomial, rel. error
+// 8e-5, far below the bf16 rounding of P).  The MUFU pipe (16 ex2/clk/SM) is the bottleneck
+// of head_dim-32 attention -- 128 tensor FLOPs per exponential -- so a fixed fraction of the
+// exponentials is moved to the otherwise idle FMA pipe (the FlashAttention-4 trick).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -120.0f);
+  const float t = x + 12582912.0f;        // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float r = x - (t - 12582912.0f);  // [-0.5, 0.5]
+  float p = fmaf(0.05508868f, r, 0.24260405f);
+  p = fmaf(p, r, 0.69327623f);
+  p = fmaf(p, r, 0.99992895f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
-__device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
+__device__ __forceinline__ uint32_t tmem_ld_32x32b_x1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
 }
-// B operand in MN-major form (N = head dim contiguous): V tile [128 keys][32 d] -- rows of
-// 64 B, SWIZZLE_64B, 8-row groups 512 B apart (SBO).
-__device__ __forceinline__ uint64_t make_mnmajor_desc_sw64(uint32_t smem_addr) {
-  return static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (static_cast<uint64_t>(512 >> 4) << 32) |
-         (1ull << 46) | (4ull << 61);
-}
-// kind::f16 instruction descriptor with fp16 A/B (format 0), fp32 accumulate, B MN-major
-__host__ __device__ constexpr uint32_t make_idesc_f16_bmn(int M, int N) {
-  return (1u << 4) | (1u << 16) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+// B operand in MN-major form (N contiguous): rows of 64 B (32 bf16), SWIZZLE_64B, 8-row groups
+// 512 B apart (SBO); a second 32-column block of N lives `lbo_bytes` after the first (LBO).
+__device__ __forceinline__ uint64_t make_mnmajor_desc_sw64(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4) | (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         (static_cast<uint64_t>(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
@@ -351,12 +354,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + AT_SQ;
   uint8_t* sV = sK + 2 * AT_SK;
-  uint8_t* sP = sV + 2 * AT_SV;
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sP + 2 * AT_SP);
+  uint8_t* sOnes = sV + 2 * AT_SV;  // [128 keys][32 cols] bf16, col 0 = 1: second N block of the PV MMA -> row sums of P
+  uint8_t* sP = sOnes + AT_SONES;
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sP + AT_SP);
   uint64_t* bar_kv = bar_q + 1;  // [2]
   uint64_t* bar_s = bar_kv + 2;
-  uint64_t* bar_p = bar_s + 1;   // [2]
-  uint64_t* bar_o = bar_p + 2;   // [2]
+  uint64_t* bar_p = bar_s + 1;
+  uint64_t* bar_o = bar_p + 1;   // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_o + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -371,7 +375,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
     mbar_init(bar_q, 1);
     mbar_init(&bar_kv[0], 1); mbar_init(&bar_kv[1], 1);
     mbar_init(bar_s, 1);
-    mbar_init(&bar_p[0], 128); mbar_init(&bar_p[1], 128);
+    mbar_init(bar_p, 128);
     mbar_init(&bar_o[0], 1); mbar_init(&bar_o[1], 1);
     fence_barrier_init();
   }
@@ -384,7 +388,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
   if (warp == 4) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
-      constexpr uint32_t idesc_o = make_idesc_f16_bmn(128, 32);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64) | (1u << 16);  // bit 16: B is MN-major
       auto load_kv = [&](int j) {
         const int st = j & 1;
         mbar_expect_tx(&bar_kv[st], AT_SK + AT_SV);
@@ -407,27 +411,28 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
       mbar_wait(&bar_kv[0], 0);
       tc_fence_after();
       issue_s(0);
+      const uint32_t pa = smem_u32(sP);
       for (int j = 0; j < nkv; ++j) {
         const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&bar_p[st], ph);  // P_j written, S_j consumed
+        mbar_wait(bar_p, j & 1);  // P_j written, S_j consumed
         tc_fence_after();
         if (j + 1 < nkv) {
           mbar_wait(&bar_kv[(j + 1) & 1], ((j + 1) >> 1) & 1);
           tc_fence_after();
           issue_s(j + 1);
         }
-        const uint32_t pa = smem_u32(sP + st * AT_SP), vb = smem_u32(sV + st * AT_SV);
-        const uint32_t d_o = tmem_base + 128 + st * 32;
+        const uint32_t vb = smem_u32(sV + st * AT_SV);
+        const uint32_t lbo = smem_u32(sOnes) - vb;
+        const uint32_t d_o = tmem_base + 128 + st * 64;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t aoff = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_bf16(d_o, make_kmajor_desc<128>(pa + aoff), make_mnmajor_desc_sw64(vb + k * 1024), idesc_o,
+          umma_bf16(d_o, make_kmajor_desc<128>(pa + aoff), make_mnmajor_desc_sw64(vb + k * 1024, lbo), idesc_o,
                     k != 0 ? 1u : 0u);
         }
         umma_commit(&bar_o[st]);
         if (j + 2 < nkv) {
-          mbar_wait(&bar_o[st], ph);  // PV_j done -> K/V stage reusable
+          mbar_wait(&bar_o[st], (j >> 1) & 1);  // PV_j done -> K/V stage reusable
           load_kv(j + 2);
         }
       }
@@ -435,12 +440,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
   } else {
     const int row = warp * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    {  // ones block: logical column 0 of key row `row` is 1.0 (bf16 0x3F80), the rest 0; SW64 swizzle
+      uint4* orow = reinterpret_cast<uint4*>(sOnes + row * 64);
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) orow[i] = z;
+      *reinterpret_cast<uint16_t*>(sOnes + row * 64 + (((row >> 1) & 3) << 4)) = 0x3F80;
+    }
     float o[32];
 #pragma unroll
     for (int d = 0; d < 32; ++d) o[d] = 0.f;
     float m_run = -INFINITY, m_ref = -INFINITY, l = 0.f;
     for (int j = 0; j < nkv; ++j) {
-      const int st = j & 1;
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
       float s[128];
@@ -463,35 +474,38 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
       for (int i = 1; i < 128; ++i) mx = fmaxf(mx, s[i]);
       const float m_prev = m_run;
       const float m_new = fmaxf(m_run, mx);
-      float sum = 0.f;
-      uint8_t* prow = sP + st * AT_SP + row * 128;
+      m_run = m_new;
+      if (j >= 1) {  // PV_{j-1} complete: the P buffer is free again and O_{j-1} (+ its row sums) is ready
+        mbar_wait(&bar_o[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+      }
+      uint8_t* prow = sP + row * 128;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 keys (16 bytes of fp16)
+      for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 keys (16 bytes of bf16)
+        float p[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x = s[c * 8 + i] - m_new;
+          p[i] = (i % AT_POLY_MOD == AT_POLY_MOD - 1) ? ex2_poly(x) : ex2_approx(x);
+        }
         uint4 u;
-        u.x = ex2_f16x2(s[c * 8 + 0] - m_new, s[c * 8 + 1] - m_new);
-        u.y = ex2_f16x2(s[c * 8 + 2] - m_new, s[c * 8 + 3] - m_new);
-        u.z = ex2_f16x2(s[c * 8 + 4] - m_new, s[c * 8 + 5] - m_new);
-        u.w = ex2_f16x2(s[c * 8 + 6] - m_new, s[c * 8 + 7] - m_new);
-        const uint32_t hs = hadd2_u32(hadd2_u32(u.x, u.y), hadd2_u32(u.z, u.w));
-        const float2 fs = __half22float2(*reinterpret_cast<const __half2*>(&hs));
-        sum += fs.x + fs.y;
+        u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
+        u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
         *reinterpret_cast<uint4*>(prow + (c >> 3) * 16384 + (((c & 7) ^ (row & 7)) << 4)) = u;
       }
-      l = l * ex2_approx(m_prev - m_new) + sum;
-      m_run = m_new;
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&bar_p[st]);
+      mbar_arrive(bar_p);
       if (j >= 1) {  // deferred accumulate of tile j-1 (its P was relative to m_prev)
         const int so = (j - 1) & 1;
-        mbar_wait(&bar_o[so], ((j - 1) >> 1) & 1);
-        tc_fence_after();
         uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_base + 128 + so * 32, r);
+        tmem_ld_32x32b_x32(tmem_base + lane_base + 128 + so * 64, r);
+        const uint32_t rs = tmem_ld_32x32b_x1(tmem_base + lane_base + 128 + so * 64 + 32);
         tmem_ld_wait();
         const float a = ex2_approx(m_ref - m_prev);
 #pragma unroll
         for (int d = 0; d < 32; ++d) o[d] = fmaf(o[d], a, __uint_as_float(r[d]));
+        l = fmaf(l, a, __uint_as_float(rs));
         m_ref = m_prev;
       }
     }
@@ -500,11 +514,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
       mbar_wait(&bar_o[so], ((nkv - 1) >> 1) & 1);
       tc_fence_after();
       uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_base + 128 + so * 32, r);
+      tmem_ld_32x32b_x32(tmem_base + lane_base + 128 + so * 64, r);
+      const uint32_t rs = tmem_ld_32x32b_x1(tmem_base + lane_base + 128 + so * 64 + 32);
       tmem_ld_wait();
       const float a = ex2_approx(m_ref - m_run);
 #pragma unroll
       for (int d = 0; d < 32; ++d) o[d] = fmaf(o[d], a, __uint_as_float(r[d]));
+      l = fmaf(l, a, __uint_as_float(rs));
     }
     const int q = q0 + row;
     if (q < L) {
