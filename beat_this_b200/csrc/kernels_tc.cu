@@ -58,9 +58,10 @@ struct TgCfg {
   static constexpr int A_BYTES = TG_BM * BK * 2;
   static constexpr int W_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
-  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+  static constexpr int EPI_STAGING = TG_EPI_WARPS * 4096;  // 32x32 fp32 transpose tile per epilogue warp
+  static constexpr int STAGES = ((229376 - EPI_STAGING) / STAGE_BYTES) > 8 ? 8 : ((229376 - EPI_STAGING) / STAGE_BYTES);
   static constexpr int TCOLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_STAGING + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int SWZ = BK * 2;  // 128 or 64 byte rows
 };
 
@@ -74,7 +75,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sW = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sEpi + Cfg::EPI_STAGING);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -163,7 +165,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int SPLIT = (NCH + 1) / 2;
     const int c_begin = TILE_SPLIT ? 0 : (half == 0 ? 0 : SPLIT);
     const int c_end = TILE_SPLIT ? NCH : (half == 0 ? SPLIT : NCH);
-    const int row = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
     int iter = 0;
@@ -175,42 +176,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int p_out = mt / t_tiles;
-      const int t = (mt - p_out * t_tiles) * TG_BM + row;
-      const bool valid = t < g.L;
-      const int64_t m = static_cast<int64_t>(p_out) * g.L + t;
-      float rv[32];
-      const bool pre_rope = e.kind == 1 && valid;
-      if (pre_rope) {  // cos[16] | sin[16] of this row's position, reused by every q/k head of the row
-        const int pos = e.posmode == 0 ? t : static_cast<int>((m / g.L) % e.F);
-        const float4* c4 = reinterpret_cast<const float4*>(e.rope_cos + pos * 16);
-        const float4* s4 = reinterpret_cast<const float4*>(e.rope_sin + pos * 16);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 a = __ldg(c4 + i), b = __ldg(s4 + i);
-          rv[4 * i] = a.x; rv[4 * i + 1] = a.y; rv[4 * i + 2] = a.z; rv[4 * i + 3] = a.w;
-          rv[16 + 4 * i] = b.x; rv[16 + 4 * i + 1] = b.y; rv[16 + 4 * i + 2] = b.z; rv[16 + 4 * i + 3] = b.w;
-        }
-      }
-      const bool pre = e.kind == 0 && e.resid != nullptr && valid;
-      if (pre) {  // issue the residual loads before blocking on the accumulator
-        const float4* r4 = reinterpret_cast<const float4*>(e.resid + m * e.ldr + nt * BN + c_begin * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 q = r4[i];
-          rv[4 * i] = q.x; rv[4 * i + 1] = q.y; rv[4 * i + 2] = q.z; rv[4 * i + 3] = q.w;
-        }
-      }
+      const int t_base = (mt - p_out * t_tiles) * TG_BM + quarter * 32;  // first row of this warp
+      const int64_t m_base = static_cast<int64_t>(p_out) * g.L + t_base;
+      uint8_t* stg = sEpi + ew * 4096;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       for (int c = c_begin; c < c_end; ++c) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, r);
         tmem_ld_wait();
-        if (valid) {
-          float v[32];
+        // Transpose through shared memory: TMEM hands every lane one ROW (32 columns); written
+        // straight to global that is 32 partial lines per store instruction.  After the swizzled
+        // round trip 8 consecutive lanes hold one 128-byte row segment, so side inputs (bias,
+        // residual, RoPE tables) and outputs are accessed as whole lines.
+        __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          epilogue_apply<bf16, 32>(e, g.L, m, nt * BN + c * 32, v, (pre_rope || (pre && c == c_begin)) ? rv : nullptr);
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+              make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+        __syncwarp();
+        const int cc = lane & 7;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rl = 4 * it + (lane >> 3);
+          const float4 q = *reinterpret_cast<const float4*>(stg + rl * 128 + ((cc ^ (rl & 7)) << 4));
+          if (t_base + rl < g.L) {
+            float v[4] = {q.x, q.y, q.z, q.w};
+            epilogue_apply<bf16, 4>(e, g.L, m_base + rl, nt * BN + c * 32 + cc * 4, v);
+          }
         }
       }
       tc_fence_before();
@@ -359,7 +352,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(sP + AT_SP);
   uint64_t* bar_kv = bar_q + 1;  // [2]
   uint64_t* bar_s = bar_kv + 2;
-  uint64_t* bar_p = bar_s + 1;
+  uint64_t* bar_sfree = bar_s + 1;  // S_j has been copied to registers: S_{j+1} may overwrite it
+  uint64_t* bar_p = bar_sfree + 1;
   uint64_t* bar_o = bar_p + 1;   // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_o + 2);
 
@@ -375,6 +369,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
     mbar_init(bar_q, 1);
     mbar_init(&bar_kv[0], 1); mbar_init(&bar_kv[1], 1);
     mbar_init(bar_s, 1);
+    mbar_init(bar_sfree, 128);
     mbar_init(bar_p, 128);
     mbar_init(&bar_o[0], 1); mbar_init(&bar_o[1], 1);
     fence_barrier_init();
@@ -414,13 +409,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
       const uint32_t pa = smem_u32(sP);
       for (int j = 0; j < nkv; ++j) {
         const int st = j & 1;
-        mbar_wait(bar_p, j & 1);  // P_j written, S_j consumed
-        tc_fence_after();
-        if (j + 1 < nkv) {
+        if (j + 1 < nkv) {  // S_{j+1} is computed while the softmax warps work on S_j
+          mbar_wait(bar_sfree, j & 1);
           mbar_wait(&bar_kv[(j + 1) & 1], ((j + 1) >> 1) & 1);
           tc_fence_after();
           issue_s(j + 1);
         }
+        mbar_wait(bar_p, j & 1);  // P_j written
+        tc_fence_after();
         const uint32_t vb = smem_u32(sV + st * AT_SV);
         const uint32_t lbo = smem_u32(sOnes) - vb;
         const uint32_t d_o = tmem_base + 128 + st * 64;
@@ -455,13 +451,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
       float s[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_base + c * 32, r);
+      {
+        uint32_t r0[32], r1[32], r2[32], r3[32];  // all four TMEM loads in flight, one wait
+        tmem_ld_32x32b_x32(tmem_base + lane_base + 0, r0);
+        tmem_ld_32x32b_x32(tmem_base + lane_base + 32, r1);
+        tmem_ld_32x32b_x32(tmem_base + lane_base + 64, r2);
+        tmem_ld_32x32b_x32(tmem_base + lane_base + 96, r3);
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(bar_sfree);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(r[i]);
+        for (int i = 0; i < 32; ++i) {
+          s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]);
+          s[64 + i] = __uint_as_float(r2[i]); s[96 + i] = __uint_as_float(r3[i]);
+        }
       }
       if (j == nkv - 1) {
         const int lim = L - j * AT_BKV;  // keys >= lim are padding
@@ -469,9 +472,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
         for (int i = 0; i < 128; ++i)
           if (i >= lim) s[i] = -INFINITY;
       }
-      float mx = s[0];
+      float mxs[8];  // 8 independent max chains (a single 127-deep dependent chain stalls the warp)
 #pragma unroll
-      for (int i = 1; i < 128; ++i) mx = fmaxf(mx, s[i]);
+      for (int k = 0; k < 8; ++k) mxs[k] = fmaxf(s[k], s[8 + k]);
+#pragma unroll
+      for (int i = 16; i < 128; i += 16) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mxs[k] = fmaxf(mxs[k], fmaxf(s[i + k], s[i + 8 + k]));
+      }
+      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                             fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
       const float m_prev = m_run;
       const float m_new = fmaxf(m_run, mx);
       m_run = m_new;
