@@ -58,9 +58,20 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float erf_abs = fmaf(-p, e, 1.0f);            // erf(|x|/sqrt2)
   return 0.5f * x + 0.5f * fabsf(x) * erf_abs;         // 0.5x(1 + sign(x) erf_abs)
 }
+// tanh-form GELU on one MUFU op: 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))).  Differs from
+// the exact erf form by <= 5e-4 absolute (and tanh.approx adds ~5e-4): a quarter of a bf16 ulp
+// of the values it produces.  Used only by the bf16 tensor-core path, whose FFN epilogues were
+// issue/MUFU-bound on the 16-instruction + 2-MUFU erf evaluation above.
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
 template <typename TAct>
 __device__ __forceinline__ float gelu_for(float x) {
-  if constexpr (sizeof(TAct) == 2) return gelu_fast(x);
+  if constexpr (sizeof(TAct) == 2) return gelu_tanh_fast(x);
   else return gelu_erf(x);
 }
 
@@ -68,7 +79,7 @@ __device__ __forceinline__ float gelu_for(float x) {
 // q/k/v boundary because C % 32 == 0.
 template <typename TAct, int CNT>
 __device__ __forceinline__ void epilogue_apply(const EpiParams& e, int L, int64_t m, int n0,
-                                               float (&v)[CNT], const float* rpre = nullptr) {
+                                               float (&v)[CNT], const float (&pre)[CNT], bool use_pre) {
   if (e.kind == 0) {
     if (e.bias) {
       const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
@@ -82,9 +93,9 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& e, int L, int64_
 #pragma unroll
       for (int i = 0; i < CNT; ++i) v[i] = gelu_for<TAct>(v[i]);
     }
-    if (rpre) {  // residual prefetched by the caller before it waited for the accumulator
+    if (use_pre) {  // residual prefetched by the caller (pipelined with the previous chunk)
 #pragma unroll
-      for (int i = 0; i < CNT; ++i) v[i] += rpre[i];
+      for (int i = 0; i < CNT; ++i) v[i] += pre[i];
     } else if (e.resid) {
       const float4* r = reinterpret_cast<const float4*>(e.resid + m * e.ldr + n0);
 #pragma unroll
@@ -110,10 +121,10 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& e, int L, int64_
     TAct* dst = reinterpret_cast<TAct*>(e.out_act) + m * e.ldo_act + n0;
     if (which < 2) {
       const float sc = which == 0 ? e.qscale : 1.0f;
-      if (rpre) {  // cos[16] | sin[16] of this row's position, preloaded by the caller (CNT == 32)
+      if (use_pre && CNT == 32) {  // cos[16] | sin[16] of this row's position, preloaded by the caller
 #pragma unroll
         for (int i = 0; i < CNT / 2; ++i) {
-          const float co = rpre[i], si = rpre[16 + i];
+          const float co = pre[i % CNT], si = pre[(16 + i) % CNT];
           const float x0 = v[2 * i], x1 = v[2 * i + 1];
           v[2 * i] = (x0 * co - x1 * si) * sc;
           v[2 * i + 1] = (x1 * co + x0 * si) * sc;

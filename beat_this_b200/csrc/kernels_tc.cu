@@ -58,10 +58,9 @@ struct TgCfg {
   static constexpr int A_BYTES = TG_BM * BK * 2;
   static constexpr int W_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
-  static constexpr int EPI_STAGING = TG_EPI_WARPS * 4096;  // 32x32 fp32 transpose tile per epilogue warp
-  static constexpr int STAGES = ((229376 - EPI_STAGING) / STAGE_BYTES) > 8 ? 8 : ((229376 - EPI_STAGING) / STAGE_BYTES);
+  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int TCOLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_STAGING + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int SWZ = BK * 2;  // 128 or 64 byte rows
 };
 
@@ -75,8 +74,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sW = smem + STAGES * Cfg::A_BYTES;
-  uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sEpi + Cfg::EPI_STAGING);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -153,18 +151,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // Epilogue warps.  A warp may only touch TMEM lanes [32*(warp%4), +32).  Two schedules:
+    // Epilogue warps.  A warp may only touch TMEM lanes [32*(warp%4), +32); thread = one output row.
     //  BN >= 96: the 8 warps split the columns of every tile (2 warps per lane quarter);
-    //  BN <= 64: warps 2-5 take the even tiles of this CTA and warps 6-9 the odd ones, so two
-    //            tiles are in their (memory-latency-bound) epilogue at the same time.
+    //  BN <= 64: warps 2-5 take the even tiles of this CTA and warps 6-9 the odd ones.
+    // The residual rows of the NEXT 32-column chunk are requested before the current chunk is
+    // processed (software pipelining: the epilogue is latency-bound on those loads otherwise,
+    // ncu long_scoreboard 64% -- profiles/r1_notes.md).
     const int ew = warp - 2;
     const int quarter = warp & 3;
     const int half = ew >> 2;
     constexpr int NCH = BN / 32;
     constexpr bool TILE_SPLIT = NCH <= 2;
     constexpr int SPLIT = (NCH + 1) / 2;
+    constexpr int MAXC = TILE_SPLIT ? NCH : SPLIT;
     const int c_begin = TILE_SPLIT ? 0 : (half == 0 ? 0 : SPLIT);
-    const int c_end = TILE_SPLIT ? NCH : (half == 0 ? SPLIT : NCH);
+    const int nch = TILE_SPLIT ? NCH : (half == 0 ? SPLIT : NCH - SPLIT);
+    const int row = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
     int iter = 0;
@@ -176,33 +178,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int p_out = mt / t_tiles;
-      const int t_base = (mt - p_out * t_tiles) * TG_BM + quarter * 32;  // first row of this warp
-      const int64_t m_base = static_cast<int64_t>(p_out) * g.L + t_base;
-      uint8_t* stg = sEpi + ew * 4096;
+      const int t = (mt - p_out * t_tiles) * TG_BM + row;
+      const bool valid = t < g.L;
+      const int64_t m = static_cast<int64_t>(p_out) * g.L + t;
+      float ra[32], rb[32];
+      const bool has_resid = e.kind == 0 && e.resid != nullptr && valid;
+      const bool has_rope = e.kind == 1 && valid;
+      auto load_resid = [&](int c, float (&dst)[32]) {
+        const float4* r4 = reinterpret_cast<const float4*>(e.resid + m * e.ldr + nt * BN + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 q = r4[i];
+          dst[4 * i] = q.x; dst[4 * i + 1] = q.y; dst[4 * i + 2] = q.z; dst[4 * i + 3] = q.w;
+        }
+      };
+      if (has_rope) {  // cos[16] | sin[16] of this row's position, reused by every q/k head of the row
+        const int pos = e.posmode == 0 ? t : static_cast<int>((m / g.L) % e.F);
+        const float4* c4 = reinterpret_cast<const float4*>(e.rope_cos + pos * 16);
+        const float4* s4 = reinterpret_cast<const float4*>(e.rope_sin + pos * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 a = __ldg(c4 + i), b = __ldg(s4 + i);
+          ra[4 * i] = a.x; ra[4 * i + 1] = a.y; ra[4 * i + 2] = a.z; ra[4 * i + 3] = a.w;
+          ra[16 + 4 * i] = b.x; ra[16 + 4 * i + 1] = b.y; ra[16 + 4 * i + 2] = b.z; ra[16 + 4 * i + 3] = b.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rb[i] = ra[i];  // either buffer may be handed to the epilogue
+      }
+      if (has_resid) load_resid(c_begin, ra);  // in flight while we wait for the accumulator
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      for (int c = c_begin; c < c_end; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, r);
-        tmem_ld_wait();
-        // Transpose through shared memory: TMEM hands every lane one ROW (32 columns); written
-        // straight to global that is 32 partial lines per store instruction.  After the swizzled
-        // round trip 8 consecutive lanes hold one 128-byte row segment, so side inputs (bias,
-        // residual, RoPE tables) and outputs are accessed as whole lines.
-        __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((i ^ (lane & 7)) << 4)) =
-              make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
-        __syncwarp();
-        const int cc = lane & 7;
+      for (int k = 0; k < MAXC; ++k) {
+        if (k < nch) {
+          const int c = c_begin + k;
+          float (&cur)[32] = (k & 1) ? rb : ra;
+          float (&nxt)[32] = (k & 1) ? ra : rb;
+          if (has_resid && k + 1 < nch) load_resid(c + 1, nxt);
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, r);
+          tmem_ld_wait();
+          if (valid) {
+            float v[32];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rl = 4 * it + (lane >> 3);
-          const float4 q = *reinterpret_cast<const float4*>(stg + rl * 128 + ((cc ^ (rl & 7)) << 4));
-          if (t_base + rl < g.L) {
-            float v[4] = {q.x, q.y, q.z, q.w};
-            epilogue_apply<bf16, 4>(e, g.L, m_base + rl, nt * BN + c * 32 + cc * 4, v);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            epilogue_apply<bf16, 32>(e, g.L, m, nt * BN + c * 32, v, cur, has_rope || has_resid);
           }
         }
       }
