@@ -57,8 +57,8 @@ struct bt_ctx {
   int64_t launches = 0;
   bool sync_debug = false;
 
-  // workspace (sized for `wave` chunks of BT_CHUNK frames)
-  int wave = 8;
+  // workspace: sized for ws_wave chunks of BT_CHUNK frames; grows on demand up to `wave`
+  int wave = 128;
   int ws_wave = 0;
   float *X0 = nullptr, *X1 = nullptr, *GATES = nullptr;
   void *XB = nullptr, *XN = nullptr, *QKV = nullptr, *O = nullptr, *H = nullptr;
@@ -254,11 +254,13 @@ int64_t front_elems(const bt_ctx* c) {
   return static_cast<int64_t>(c->hp.spect_dim / 4) * BT_CHUNK * c->hp.stem_dim;
 }
 
-int ensure_ws(bt_ctx* c) {
-  if (c->ws_wave == c->wave) return BT_OK;
+int ensure_ws(bt_ctx* c, int need_chunks) {
+  int want = std::min(c->wave, std::max(need_chunks, 1));
+  if (want <= c->ws_wave) return BT_OK;
+  if (want < c->wave) want = std::min(c->wave, std::max(want, 2 * c->ws_wave));  // amortise growth
   free_ws(c);
   free_plans(c);
-  const int64_t G = c->wave;
+  const int64_t G = want;
   const int64_t fe = front_elems(c);                                     // 1.536M
   const int64_t D = c->hp.transformer_dim;
   const int64_t me = static_cast<int64_t>(BT_CHUNK) * D;                 // main tokens * dim
@@ -274,7 +276,7 @@ int ensure_ws(bt_ctx* c) {
   if (c->dtype == BT_DTYPE_BF16) {
     BT_CUDA(c, cudaMalloc(&c->XB, G * xe * 2));
   }
-  c->ws_wave = c->wave;
+  c->ws_wave = want;
   return BT_OK;
 }
 
@@ -724,6 +726,12 @@ void bt_destroy(bt_ctx* c) {
 int bt_set_wave_chunks(bt_ctx* c, int32_t chunks) {
   if (!c || chunks < 1 || chunks > 256) return fail(c, BT_ERR_ARG, "bt_set_wave_chunks: 1..256");
   c->wave = chunks;
+  if (c->ws_wave > chunks) {  // shrink: drop the workspace, it is re-created on the next call
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_ws(c);
+    free_plans(c);
+  }
   return BT_OK;
 }
 
@@ -827,8 +835,7 @@ int bt_spect2frames(bt_ctx* c, const float* spect_dev, const int64_t* frame_offs
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BT_CUDA(c, cudaSetDevice(c->device));
   prof_mark(c, st);
-  int r = ensure_ws(c);
-  if (r != BT_OK) return r;
+  int r = BT_OK;
   // plan: all chunks of all clips, grouped by chunk length (1500 except for pieces <= 1488 frames)
   struct HostChunk { ChunkSrc s; int len; };
   std::vector<HostChunk> all;
@@ -857,6 +864,7 @@ int bt_spect2frames(bt_ctx* c, const float* spect_dev, const int64_t* frame_offs
     }
   }
   if (all.empty()) return BT_OK;
+  if ((r = ensure_ws(c, static_cast<int>(all.size()))) != BT_OK) return r;
   std::stable_sort(all.begin(), all.end(), [](const HostChunk& a, const HostChunk& b) { return a.len > b.len; });
   const size_t bytes = all.size() * sizeof(ChunkSrc);
   if ((r = ensure_stage(c, bytes)) != BT_OK) return r;
@@ -867,7 +875,7 @@ int bt_spect2frames(bt_ctx* c, const float* spect_dev, const int64_t* frame_offs
   size_t i = 0;
   while (i < all.size()) {
     size_t j = i;
-    while (j < all.size() && all[j].len == all[i].len && j - i < static_cast<size_t>(c->wave)) ++j;
+    while (j < all.size() && all[j].len == all[i].len && j - i < static_cast<size_t>(c->ws_wave)) ++j;
     Wave wv{ds + i, static_cast<int>(j - i), all[i].len};
     if ((r = run_wave(c, spect_dev, wv, beat_dev, downbeat_dev, st)) != BT_OK) return r;
     i = j;

@@ -24,6 +24,23 @@ def _cuda_device(device) -> torch.device:
     return dev
 
 
+class _PeakHandle:
+    def __init__(self, slot, n):
+        self.slot, self.n = slot, n
+
+    def result(self):
+        self.slot["event"].synchronize()
+        cnt = self.slot["cnt_h"].numpy()
+        times = self.slot["times_h"].numpy()
+        out = [(times[0, i, : cnt[0, i]].copy(), times[1, i, : cnt[1, i]].copy()) for i in range(self.n)]
+        self.slot["keep"] = None
+        return out
+
+    @property
+    def d2h_bytes(self):
+        return self.slot["times_h"].numel() * 8 + self.slot["cnt_h"].numel() * 4
+
+
 class Engine:
     def __init__(self, packed: dict | None, hparams: dict | None, device="cuda", bf16: bool = False, wave_chunks: int | None = None):
         self.lib = _lib.load()
@@ -162,6 +179,32 @@ class Engine:
         bt_h = bt_t[:, :width].cpu().numpy()
         dn_h = dn_t[:, :width].cpu().numpy()
         return [(bt_h[i, : cnt_h[0, i]].copy(), dn_h[i, : cnt_h[1, i]].copy()) for i in range(n)]
+
+    def peakpick_async(self, beat: torch.Tensor, down: torch.Tensor, frame_offsets, slot: dict | None = None):
+        """Like peakpick_cat but without a host synchronisation: the timestamp arrays are copied to
+        pinned host memory asynchronously on the current stream; call ``.result()`` on the returned
+        handle (it waits on a CUDA event) to get the per-clip numpy arrays."""
+        n = len(frame_offsets) - 1
+        max_peaks = max(1, max(int(frame_offsets[i + 1]) - int(frame_offsets[i]) for i in range(n)))
+        slot = slot if slot is not None else {}
+        key = (n, max_peaks)
+        if slot.get("key") != key:
+            slot["key"] = key
+            slot["times"] = torch.empty((2, n, max_peaks), dtype=torch.float64, device=self.device)
+            slot["cnt"] = torch.zeros((2, n), dtype=torch.int32, device=self.device)
+            slot["times_h"] = torch.empty((2, n, max_peaks), dtype=torch.float64).pin_memory()
+            slot["cnt_h"] = torch.empty((2, n), dtype=torch.int32).pin_memory()
+            slot["event"] = torch.cuda.Event()
+        t, cnt = slot["times"], slot["cnt"]
+        code = self.lib.bt_peakpick(self.ctx, c_void_p(beat.data_ptr()), c_void_p(down.data_ptr()), i64_array(frame_offsets), n,
+                                    c_void_p(t[0].data_ptr()), c_void_p(cnt[0].data_ptr()), c_void_p(t[1].data_ptr()),
+                                    c_void_p(cnt[1].data_ptr()), max_peaks, self._stream())
+        _lib.check(self.lib, self.ctx, code)
+        slot["times_h"].copy_(t, non_blocking=True)
+        slot["cnt_h"].copy_(cnt, non_blocking=True)
+        slot["event"].record(torch.cuda.current_stream(self.device))
+        slot["keep"] = (beat, down)  # keep the logits alive until the kernels have run
+        return _PeakHandle(slot, n)
 
     # ---- per-kernel-class timing (bench.py roofline) -------------------------------------------
     def profile_enable(self, on: bool = True):

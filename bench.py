@@ -237,9 +237,6 @@ def run_ours(args, rank, world, local):
         beat, down, f = eng.audio2frames_cat(audio_dev, so)
         return eng.peakpick_cat(beat, down, f)
 
-    def step_e2e():
-        return a2b.batch_from_pinned(host, so)
-
     # ---- device-resident timing -----------------------------------------------------------------
     for _ in range(args.warmup):
         step_device()
@@ -260,16 +257,30 @@ def run_ours(args, rank, world, local):
     eng.profile_enable(False)
     prof = eng.profile_results()
     clocks = sampler.stop()
-    # ---- end-to-end timing ----------------------------------------------------------------------
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
+    # ---- end-to-end timing: pinned host audio in, numpy timestamps out, every step ------------
+    # BeatPipeline double-buffers: the H2D copy of step i+1 overlaps the kernels of step i.
+    from beat_this_b200.pipeline import BeatPipeline
+
+    pipe = BeatPipeline(a2b, depth=2)
+    hosts = [host, host.clone().pin_memory()]
+    for i in range(max(2, args.warmup // 2)):
+        pipe.submit(hosts[i % 2], so)
+        if len(pipe.inflight) == 2:
+            pipe.collect()
+    while pipe.inflight:
+        pipe.collect()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = step_e2e()
+    d2h = 0
+    for i in range(args.steps):
+        if not pipe.free:
+            res = pipe.collect()
+        h = pipe.submit(hosts[i % 2], so)
+        d2h = h.d2h_bytes
+    while pipe.inflight:
+        res = pipe.collect()
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    d2h = sum(b.nbytes + d.nbytes for b, d in res) + 2 * 4 * len(res)
     if world > 1:
         t = torch.tensor([ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -311,7 +322,7 @@ def run_ours(args, rank, world, local):
                    "profile": "per-kernel CUDA events recorded inside the timed region (bt_profile_*)"},
         "roofline": roof, "kernel_time_shares": shares,
         "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": so[-1] * 4, "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1000.0 * e2e_s / args.steps, "api": "Audio2Beats.batch_from_pinned (pinned host fp32 audio in, numpy timestamps out)"},
+                "ms_per_step": 1000.0 * e2e_s / args.steps, "api": "beat_this_b200.pipeline.BeatPipeline over Audio2Beats (pinned host fp32 audio in, numpy timestamps out; H2D of step i+1 overlaps the kernels of step i)"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -327,7 +338,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--seconds", type=float, default=30.0)
-    ap.add_argument("--wave", type=int, default=16, help="chunks per wave")
+    ap.add_argument("--wave", type=int, default=128, help="chunks per wave (one wave = one launch of every kernel)")
     ap.add_argument("--float32", action="store_true", help="fp32 CUDA-core path instead of bf16 tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-clips-per-step", type=int, default=2)

@@ -131,7 +131,9 @@ int bt_peakpick(bt_ctx* ctx, const float* beat_dev, const float* downbeat_dev,
 
 /* ---- introspection / tuning ----------------------------------------------------------------- */
 
-/* Chunks processed per wave (workspace is sized for this many 1500-frame chunks). */
+/* Upper bound on the chunks processed per wave (default 128; one wave = one launch of every
+ * kernel of the forward pass).  The workspace (~46 MB per 1500-frame chunk in bf16) grows on
+ * demand up to this many chunks. */
 int bt_set_wave_chunks(bt_ctx* ctx, int32_t chunks);
 
 /* Number of kernel launches issued by this ctx since creation (bench.py "gpu_launches"). */

@@ -118,3 +118,24 @@ def test_no_cpu_fallback(small0_ckpt, lib_built):
 
     with pytest.raises(RuntimeError):
         Spect2Frames(small0_ckpt, "cpu")
+
+
+def test_pipeline_matches_batch(small0_ckpt, lib_built):
+    """BeatPipeline (double-buffered H2D / compute / D2H) returns exactly what Audio2Beats.batch does."""
+    from beat_this_b200 import synthetic
+    from beat_this_b200.inference import Audio2Beats
+    from beat_this_b200.pipeline import BeatPipeline
+
+    a2b = Audio2Beats(small0_ckpt, "cuda:0", True)
+    clips = [synthetic.synth_clip(30 + i, 8.0 + i).astype(np.float32) for i in range(3)]
+    ref = a2b.batch(clips, 22050)
+    so = [0]
+    for c in clips:
+        so.append(so[-1] + len(c))
+    host = torch.from_numpy(np.concatenate(clips)).pin_memory()
+    pipe = BeatPipeline(a2b, depth=2)
+    outs = list(pipe.run([(host, so)] * 4))
+    assert len(outs) == 4
+    for out in outs:
+        for (b, d), (rb, rd) in zip(out, ref):
+            assert np.array_equal(b, rb) and np.array_equal(d, rd)
