@@ -27,6 +27,10 @@ import tempfile
 import threading
 import time
 
+# keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
