@@ -324,9 +324,10 @@ int launch_gemm_tc(const TcGemmPlan* p, const EpiParams& e, cudaStream_t st) {
 // (ex2.approx.f16x2 -- two exponentials per MUFU op -- was measured: 28% SLOWER than fp32
 // ex2 + bf16 pack on B200, profiles/r1_notes.md.)
 constexpr int AT_BQ = 128, AT_BKV = 128;
-constexpr int AT_THREADS = 160;
-constexpr int AT_SQ = 8192, AT_SK = 8192, AT_SV = 8192, AT_SONES = 8192, AT_SP = 32768;
-constexpr int AT_SMEM = AT_SQ + 2 * AT_SK + 2 * AT_SV + AT_SONES + AT_SP + 1024 + 128;
+constexpr int AT_SOFTMAX_WARPS = 8;                      // two threads per query row (64 keys each)
+constexpr int AT_THREADS = 32 * (AT_SOFTMAX_WARPS + 1);  // + 1 TMA/MMA warp
+constexpr int AT_SQ = 8192, AT_SK = 8192, AT_SV = 8192, AT_SONES = 8192, AT_SP = 32768, AT_SMAX = 2048;
+constexpr int AT_SMEM = AT_SQ + 2 * AT_SK + 2 * AT_SV + AT_SONES + AT_SP + AT_SMAX + 1024 + 128;
 constexpr int AT_POLY_MOD = 4;  // every AT_POLY_MOD-th exponential runs on the FMA pipe instead of MUFU
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -352,6 +353,18 @@ __device__ __forceinline__ uint32_t tmem_ld_32x32b_x1(uint32_t taddr) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
   return r;
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // B operand in MN-major form (N contiguous): rows of 64 B (32 bf16), SWIZZLE_64B, 8-row groups
 // 512 B apart (SBO); a second 32-column block of N lives `lbo_bytes` after the first (LBO).
 __device__ __forceinline__ uint64_t make_mnmajor_desc_sw64(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -369,7 +382,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
   uint8_t* sV = sK + 2 * AT_SK;
   uint8_t* sOnes = sV + 2 * AT_SV;  // [128 keys][32 cols] bf16, col 0 = 1: second N block of the PV MMA -> row sums of P
   uint8_t* sP = sOnes + AT_SONES;
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sP + AT_SP);
+  float* sMax = reinterpret_cast<float*>(sP + AT_SP);  // [2 parity][2 halves][128 rows] partial row maxima
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sP + AT_SP + AT_SMAX);
   uint64_t* bar_kv = bar_q + 1;  // [2]
   uint64_t* bar_s = bar_kv + 2;
   uint64_t* bar_sfree = bar_s + 1;  // S_j has been copied to registers: S_{j+1} may overwrite it
@@ -383,24 +397,26 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
   const int seq = blockIdx.z;
   const int C = heads * 32;
   const int nkv = ceil_div(L, AT_BKV);
+  constexpr int MMA_WARP = AT_SOFTMAX_WARPS;
+  constexpr int NSOFT = AT_SOFTMAX_WARPS * 32;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == MMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmQK);
     mbar_init(bar_q, 1);
     mbar_init(&bar_kv[0], 1); mbar_init(&bar_kv[1], 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_sfree, 128);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_sfree, NSOFT);
+    mbar_init(bar_p, NSOFT);
     mbar_init(&bar_o[0], 1); mbar_init(&bar_o[1], 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<256>(tmem_ptr);
+  if (warp == MMA_WARP) tmem_alloc<256>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64) | (1u << 16);  // bit 16: B is MN-major
@@ -454,54 +470,59 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
       }
     }
   } else {
-    const int row = warp * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    {  // ones block: logical column 0 of key row `row` is 1.0 (bf16 0x3F80), the rest 0; SW64 swizzle
+    // 8 softmax warps: warps w and w+4 share TMEM lane quarter w%4 (the only lanes either may
+    // touch) and split each query row: keys [0,64) go to warp w, keys [64,128) to warp w+4.
+    const int quarter = warp & 3;
+    const int hc = warp >> 2;  // which half of the keys / of the output columns
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    if (hc == 0) {  // ones block: logical column 0 of key row `row` is 1.0 (bf16 0x3F80), the rest 0; SW64 swizzle
       uint4* orow = reinterpret_cast<uint4*>(sOnes + row * 64);
       const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
       for (int i = 0; i < 4; ++i) orow[i] = z;
       *reinterpret_cast<uint16_t*>(sOnes + row * 64 + (((row >> 1) & 3) << 4)) = 0x3F80;
     }
-    float o[32];
+    float o[16];  // output columns [16*hc, 16*hc + 16) of this row
 #pragma unroll
-    for (int d = 0; d < 32; ++d) o[d] = 0.f;
+    for (int d = 0; d < 16; ++d) o[d] = 0.f;
     float m_run = -INFINITY, m_ref = -INFINITY, l = 0.f;
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
-      float s[128];
+      float s[64];
       {
-        uint32_t r0[32], r1[32], r2[32], r3[32];  // all four TMEM loads in flight, one wait
-        tmem_ld_32x32b_x32(tmem_base + lane_base + 0, r0);
-        tmem_ld_32x32b_x32(tmem_base + lane_base + 32, r1);
-        tmem_ld_32x32b_x32(tmem_base + lane_base + 64, r2);
-        tmem_ld_32x32b_x32(tmem_base + lane_base + 96, r3);
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_base + hc * 64, r0);
+        tmem_ld_32x32b_x32(tmem_base + lane_base + hc * 64 + 32, r1);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(bar_sfree);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]);
-          s[64 + i] = __uint_as_float(r2[i]); s[96 + i] = __uint_as_float(r3[i]);
-        }
+        for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]); }
       }
       if (j == nkv - 1) {
-        const int lim = L - j * AT_BKV;  // keys >= lim are padding
+        const int lim = L - j * AT_BKV - hc * 64;  // keys >= lim are padding
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
+        for (int i = 0; i < 64; ++i)
           if (i >= lim) s[i] = -INFINITY;
       }
-      float mxs[8];  // 8 independent max chains (a single 127-deep dependent chain stalls the warp)
+      float mxs[8];  // independent max chains
 #pragma unroll
       for (int k = 0; k < 8; ++k) mxs[k] = fmaxf(s[k], s[8 + k]);
 #pragma unroll
-      for (int i = 16; i < 128; i += 16) {
+      for (int i = 16; i < 64; i += 16) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) mxs[k] = fmaxf(mxs[k], fmaxf(s[i + k], s[i + 8 + k]));
       }
-      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
-                             fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+      float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                       fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+      {  // exchange the partial maximum with the thread that owns the other half of this row
+        float* mslot = sMax + (j & 1) * 256;
+        mslot[hc * 128 + row] = mx;
+        named_bar_sync(1 + quarter, 64);
+        mx = fmaxf(mx, mslot[(hc ^ 1) * 128 + row]);
+      }
       const float m_prev = m_run;
       const float m_new = fmaxf(m_run, mx);
       m_run = m_new;
@@ -509,9 +530,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
         mbar_wait(&bar_o[(j - 1) & 1], ((j - 1) >> 1) & 1);
         tc_fence_after();
       }
-      uint8_t* prow = sP + row * 128;
+      uint8_t* prow = sP + hc * 16384 + row * 128;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 keys (16 bytes of bf16)
+      for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys (16 bytes of bf16)
         float p[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -521,20 +542,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
         uint4 u;
         u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
         u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
-        *reinterpret_cast<uint4*>(prow + (c >> 3) * 16384 + (((c & 7) ^ (row & 7)) << 4)) = u;
+        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = u;
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_p);
       if (j >= 1) {  // deferred accumulate of tile j-1 (its P was relative to m_prev)
         const int so = (j - 1) & 1;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_base + 128 + so * 64, r);
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_base + lane_base + 128 + so * 64 + hc * 16, r);
         const uint32_t rs = tmem_ld_32x32b_x1(tmem_base + lane_base + 128 + so * 64 + 32);
         tmem_ld_wait();
         const float a = ex2_approx(m_ref - m_prev);
 #pragma unroll
-        for (int d = 0; d < 32; ++d) o[d] = fmaf(o[d], a, __uint_as_float(r[d]));
+        for (int d = 0; d < 16; ++d) o[d] = fmaf(o[d], a, __uint_as_float(r[d]));
         l = fmaf(l, a, __uint_as_float(rs));
         m_ref = m_prev;
       }
@@ -543,28 +564,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
       const int so = (nkv - 1) & 1;
       mbar_wait(&bar_o[so], ((nkv - 1) >> 1) & 1);
       tc_fence_after();
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_base + 128 + so * 64, r);
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(tmem_base + lane_base + 128 + so * 64 + hc * 16, r);
       const uint32_t rs = tmem_ld_32x32b_x1(tmem_base + lane_base + 128 + so * 64 + 32);
       tmem_ld_wait();
       const float a = ex2_approx(m_ref - m_run);
 #pragma unroll
-      for (int d = 0; d < 32; ++d) o[d] = fmaf(o[d], a, __uint_as_float(r[d]));
+      for (int d = 0; d < 16; ++d) o[d] = fmaf(o[d], a, __uint_as_float(r[d]));
       l = fmaf(l, a, __uint_as_float(rs));
     }
     const int q = q0 + row;
     if (q < L) {
       const int64_t m = static_cast<int64_t>(seq) * L + q;
       const float gsc = gates[m * heads + h] / l;
-      float v[32];
+      uint4 u[2];
+      uint32_t* w = reinterpret_cast<uint32_t*>(u);
 #pragma unroll
-      for (int d = 0; d < 32; ++d) v[d] = o[d] * gsc;
-      store_act<bf16, 32>(out + m * C + h * 32, v);
+      for (int d = 0; d < 8; ++d) w[d] = pack_bf16x2(o[2 * d] * gsc, o[2 * d + 1] * gsc);
+      uint4* dst = reinterpret_cast<uint4*>(out + m * C + h * 32 + hc * 16);
+      dst[0] = u[0];
+      dst[1] = u[1];
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<256>(tmem_base);
+  if (warp == MMA_WARP) tmem_dealloc<256>(tmem_base);
 }
 
 struct TcAttnPlan {
