@@ -376,20 +376,21 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict__ gates, bf16* __restrict__ out,
                int L, int heads) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + AT_SQ;
-  uint8_t* sV = sK + 2 * AT_SK;
-  uint8_t* sOnes = sV + 2 * AT_SV;  // [128 keys][32 cols] bf16, col 0 = 1: second N block of the PV MMA -> row sums of P
-  uint8_t* sP = sOnes + AT_SONES;
-  float* sMax = reinterpret_cast<float*>(sP + AT_SP);  // [2 parity][2 halves][128 rows] partial row maxima
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sP + AT_SP + AT_SMAX);
-  uint64_t* bar_kv = bar_q + 1;  // [2]
-  uint64_t* bar_s = bar_kv + 2;
-  uint64_t* bar_sfree = bar_s + 1;  // S_j has been copied to registers: S_{j+1} may overwrite it
-  uint64_t* bar_p = bar_sfree + 1;
-  uint64_t* bar_o = bar_p + 1;   // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_o + 2);
+  // everything below works on 32-bit shared-space addresses computed once
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = sbase;
+  const uint32_t sK = sQ + AT_SQ;
+  const uint32_t sV = sK + 2 * AT_SK;
+  const uint32_t sOnes = sV + 2 * AT_SV;  // [128 keys][32 cols] bf16, col 0 = 1: second N block of the PV MMA -> row sums of P
+  const uint32_t sP = sOnes + AT_SONES;
+  const uint32_t sMax = sP + AT_SP;       // [2 parity][2 halves][128 rows] fp32 partial row maxima
+  const uint32_t bar_q = sMax + AT_SMAX;
+  const uint32_t bar_kv = bar_q + 8;      // [2]
+  const uint32_t bar_s = bar_kv + 16;
+  const uint32_t bar_sfree = bar_s + 8;   // S_j has been copied to registers: S_{j+1} may overwrite it
+  const uint32_t bar_p = bar_sfree + 8;
+  const uint32_t bar_o = bar_p + 8;       // [2]
+  const uint32_t tmem_slot = bar_o + 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ;
@@ -402,19 +403,26 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
 
   if (warp == MMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmQK);
-    mbar_init(bar_q, 1);
-    mbar_init(&bar_kv[0], 1); mbar_init(&bar_kv[1], 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_sfree, NSOFT);
-    mbar_init(bar_p, NSOFT);
-    mbar_init(&bar_o[0], 1); mbar_init(&bar_o[1], 1);
+    auto init = [](uint32_t bar, uint32_t count) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    };
+    init(bar_q, 1);
+    init(bar_kv, 1); init(bar_kv + 8, 1);
+    init(bar_s, 1);
+    init(bar_sfree, NSOFT);
+    init(bar_p, NSOFT);
+    init(bar_o, 1); init(bar_o + 8, 1);
     fence_barrier_init();
   }
-  if (warp == MMA_WARP) tmem_alloc<256>(tmem_ptr);
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
   if (warp == MMA_WARP) {
     if (lane == 0) {
@@ -422,49 +430,48 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64) | (1u << 16);  // bit 16: B is MN-major
       auto load_kv = [&](int j) {
         const int st = j & 1;
-        mbar_expect_tx(&bar_kv[st], AT_SK + AT_SV);
-        tma_load_3d(sK + st * AT_SK, &tmQK, &bar_kv[st], C + h * 32, j * AT_BKV, seq);
-        tma_load_3d(sV + st * AT_SV, &tmQK, &bar_kv[st], 2 * C + h * 32, j * AT_BKV, seq);
+        mbar_expect_tx_a(bar_kv + 8 * st, AT_SK + AT_SV);
+        tma_load_3d_a(sK + st * AT_SK, &tmQK, bar_kv + 8 * st, C + h * 32, j * AT_BKV, seq);
+        tma_load_3d_a(sV + st * AT_SV, &tmQK, bar_kv + 8 * st, 2 * C + h * 32, j * AT_BKV, seq);
       };
       auto issue_s = [&](int j) {
-        const uint32_t a = smem_u32(sQ), b = smem_u32(sK + (j & 1) * AT_SK);
+        const uint32_t b = sK + (j & 1) * AT_SK;
 #pragma unroll
         for (int k = 0; k < 2; ++k)
-          umma_bf16(tmem_base, make_kmajor_desc<64>(a + k * 32), make_kmajor_desc<64>(b + k * 32), idesc_s,
+          umma_bf16(tmem_base, make_kmajor_desc<64>(sQ + k * 32), make_kmajor_desc<64>(b + k * 32), idesc_s,
                     k != 0 ? 1u : 0u);
-        umma_commit(bar_s);
+        umma_commit_a(bar_s);
       };
-      mbar_expect_tx(bar_q, AT_SQ);
-      tma_load_3d(sQ, &tmQK, bar_q, h * 32, q0, seq);
+      mbar_expect_tx_a(bar_q, AT_SQ);
+      tma_load_3d_a(sQ, &tmQK, bar_q, h * 32, q0, seq);
       load_kv(0);
       if (nkv > 1) load_kv(1);
-      mbar_wait(bar_q, 0);
-      mbar_wait(&bar_kv[0], 0);
+      mbar_wait_a(bar_q, 0);
+      mbar_wait_a(bar_kv, 0);
       tc_fence_after();
       issue_s(0);
-      const uint32_t pa = smem_u32(sP);
       for (int j = 0; j < nkv; ++j) {
         const int st = j & 1;
         if (j + 1 < nkv) {  // S_{j+1} is computed while the softmax warps work on S_j
-          mbar_wait(bar_sfree, j & 1);
-          mbar_wait(&bar_kv[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          mbar_wait_a(bar_sfree, j & 1);
+          mbar_wait_a(bar_kv + 8 * ((j + 1) & 1), ((j + 1) >> 1) & 1);
           tc_fence_after();
           issue_s(j + 1);
         }
-        mbar_wait(bar_p, j & 1);  // P_j written
+        mbar_wait_a(bar_p, j & 1);  // P_j written
         tc_fence_after();
-        const uint32_t vb = smem_u32(sV + st * AT_SV);
-        const uint32_t lbo = smem_u32(sOnes) - vb;
+        const uint32_t vb = sV + st * AT_SV;
+        const uint32_t lbo = sOnes - vb;
         const uint32_t d_o = tmem_base + 128 + st * 64;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t aoff = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_bf16(d_o, make_kmajor_desc<128>(pa + aoff), make_mnmajor_desc_sw64(vb + k * 1024, lbo), idesc_o,
+          umma_bf16(d_o, make_kmajor_desc<128>(sP + aoff), make_mnmajor_desc_sw64(vb + k * 1024, lbo), idesc_o,
                     k != 0 ? 1u : 0u);
         }
-        umma_commit(&bar_o[st]);
+        umma_commit_a(bar_o + 8 * st);
         if (j + 2 < nkv) {
-          mbar_wait(&bar_o[st], (j >> 1) & 1);  // PV_j done -> K/V stage reusable
+          mbar_wait_a(bar_o + 8 * st, (j >> 1) & 1);  // PV_j done -> K/V stage reusable
           load_kv(j + 2);
         }
       }
@@ -477,27 +484,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     if (hc == 0) {  // ones block: logical column 0 of key row `row` is 1.0 (bf16 0x3F80), the rest 0; SW64 swizzle
-      uint4* orow = reinterpret_cast<uint4*>(sOnes + row * 64);
-      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      const uint32_t orow = sOnes + row * 64;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) orow[i] = z;
-      *reinterpret_cast<uint16_t*>(sOnes + row * 64 + (((row >> 1) & 3) << 4)) = 0x3F80;
+      for (int i = 0; i < 4; ++i) {
+        const bool one = i == ((row >> 1) & 3);
+        st_shared_v4(orow + 16 * i, one ? 0x3F80u : 0u, 0u, 0u, 0u);
+      }
     }
     float o[16];  // output columns [16*hc, 16*hc + 16) of this row
 #pragma unroll
     for (int d = 0; d < 16; ++d) o[d] = 0.f;
     float m_run = -INFINITY, m_ref = -INFINITY, l = 0.f;
+    const uint32_t prow = sP + hc * 16384 + row * 128;
+    const uint32_t sw = static_cast<uint32_t>(row & 7) << 4;
+    const uint32_t s_tmem = tmem_base + lane_base + hc * 64;
+    const uint32_t o_tmem = tmem_base + lane_base + 128 + hc * 16;
+    const uint32_t my_max = sMax + (hc * 128 + row) * 4, other_max = sMax + ((hc ^ 1) * 128 + row) * 4;
     for (int j = 0; j < nkv; ++j) {
-      mbar_wait(bar_s, j & 1);
+      mbar_wait_a(bar_s, j & 1);
       tc_fence_after();
       float s[64];
       {
         uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_base + hc * 64, r0);
-        tmem_ld_32x32b_x32(tmem_base + lane_base + hc * 64 + 32, r1);
+        tmem_ld_32x32b_x32(s_tmem, r0);
+        tmem_ld_32x32b_x32(s_tmem + 32, r1);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(bar_sfree);
+        mbar_arrive_a(bar_sfree);
 #pragma unroll
         for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]); }
       }
@@ -518,19 +531,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
       float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
                        fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
       {  // exchange the partial maximum with the thread that owns the other half of this row
-        float* mslot = sMax + (j & 1) * 256;
-        mslot[hc * 128 + row] = mx;
+        const uint32_t par = (j & 1) * 1024;
+        st_shared_f32(my_max + par, mx);
         named_bar_sync(1 + quarter, 64);
-        mx = fmaxf(mx, mslot[(hc ^ 1) * 128 + row]);
+        mx = fmaxf(mx, ld_shared_f32(other_max + par));
       }
       const float m_prev = m_run;
       const float m_new = fmaxf(m_run, mx);
       m_run = m_new;
       if (j >= 1) {  // PV_{j-1} complete: the P buffer is free again and O_{j-1} (+ its row sums) is ready
-        mbar_wait(&bar_o[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        mbar_wait_a(bar_o + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
         tc_fence_after();
       }
-      uint8_t* prow = sP + hc * 16384 + row * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys (16 bytes of bf16)
         float p[8];
@@ -539,18 +551,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
           const float x = s[c * 8 + i] - m_new;
           p[i] = (i % AT_POLY_MOD == AT_POLY_MOD - 1) ? ex2_poly(x) : ex2_approx(x);
         }
-        uint4 u;
-        u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
-        u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
-        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = u;
+        st_shared_v4(prow + ((c << 4) ^ sw), pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]),
+                     pack_bf16x2(p[6], p[7]));
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_p);
+      mbar_arrive_a(bar_p);
       if (j >= 1) {  // deferred accumulate of tile j-1 (its P was relative to m_prev)
         const int so = (j - 1) & 1;
         uint32_t r[16];
-        tmem_ld_32x32b_x16(tmem_base + lane_base + 128 + so * 64 + hc * 16, r);
+        tmem_ld_32x32b_x16(o_tmem + so * 64, r);
         const uint32_t rs = tmem_ld_32x32b_x1(tmem_base + lane_base + 128 + so * 64 + 32);
         tmem_ld_wait();
         const float a = ex2_approx(m_ref - m_prev);
@@ -562,10 +572,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
     }
     {
       const int so = (nkv - 1) & 1;
-      mbar_wait(&bar_o[so], ((nkv - 1) >> 1) & 1);
+      mbar_wait_a(bar_o + 8 * so, ((nkv - 1) >> 1) & 1);
       tc_fence_after();
       uint32_t r[16];
-      tmem_ld_32x32b_x16(tmem_base + lane_base + 128 + so * 64 + hc * 16, r);
+      tmem_ld_32x32b_x16(o_tmem + so * 64, r);
       const uint32_t rs = tmem_ld_32x32b_x1(tmem_base + lane_base + 128 + so * 64 + 32);
       tmem_ld_wait();
       const float a = ex2_approx(m_ref - m_run);
