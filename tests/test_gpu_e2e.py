@@ -139,3 +139,36 @@ def test_pipeline_matches_batch(small0_ckpt, lib_built):
     for out in outs:
         for (b, d), (rb, rd) in zip(out, ref):
             assert np.array_equal(b, rb) and np.array_equal(d, rd)
+
+
+def test_file2beats_and_file2file(small0_ckpt, lib_built, tmp_path):
+    """File2Beats / File2File on int16 WAV files (BASELINE config 3 shape, tiny): same beats as feeding
+    the decoded samples to Audio2Beats, and the .beats TSV the reference's save_beat_tsv would write."""
+    from scipy.io import wavfile
+
+    from beat_this_b200 import synthetic
+    from beat_this_b200.inference import Audio2Beats, File2Beats, File2File
+    from beat_this_b200.preprocessing import load_audio
+
+    paths = []
+    for i, secs in enumerate((6.0, 9.5)):
+        x = synthetic.synth_clip(40 + i, secs)
+        p = tmp_path / f"clip{i}.wav"
+        wavfile.write(p, 22050, np.round(x * 32767).astype(np.int16))
+        paths.append(p)
+    f2b = File2Beats(small0_ckpt, "cuda:0", float16=False)
+    a2b = Audio2Beats(small0_ckpt, "cuda:0", float16=False)
+    batch = f2b.batch(paths)
+    for p, (bb, bd) in zip(paths, batch):
+        sig, sr = load_audio(p)
+        assert sr == 22050 and sig.dtype == np.float64
+        b1, d1 = f2b(p)
+        b2, d2 = a2b(sig, sr)
+        assert np.array_equal(b1, b2) and np.array_equal(d1, d2)
+        assert np.array_equal(b1, bb) and np.array_equal(d1, bd)
+    out = tmp_path / "out" / "clip0.beats"
+    File2File(small0_ckpt, "cuda:0", float16=False)(paths[0], out)
+    lines = out.read_text().splitlines()
+    assert len(lines) == len(batch[0][0]) and all("\t" in ln for ln in lines)
+    with pytest.raises(RuntimeError):
+        f2b(tmp_path / "missing.wav")
