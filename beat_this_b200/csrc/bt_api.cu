@@ -61,9 +61,6 @@ struct bt_ctx {
   int wave = 128;
   int ws_wave = 0;
   float *X0 = nullptr, *X1 = nullptr, *GATES = nullptr;
-  float* SS[2] = {nullptr, nullptr};  // deferred-RMSNorm row sums of squares (tensor-core path), ping-pong
-  int ss_cur = 0;
-  int64_t ss_rows = 0;
   void *XB = nullptr, *XN = nullptr, *QKV = nullptr, *O = nullptr, *H = nullptr;
   // spectrogram scratch for bt_audio2frames
   float* spect_ws = nullptr;
@@ -219,8 +216,7 @@ int upload_stage(bt_ctx* c, size_t bytes, cudaStream_t st) {
 
 void free_ws(bt_ctx* c) {
   void** ptrs[] = {reinterpret_cast<void**>(&c->X0), reinterpret_cast<void**>(&c->X1),
-                   reinterpret_cast<void**>(&c->GATES), reinterpret_cast<void**>(&c->SS[0]),
-                   reinterpret_cast<void**>(&c->SS[1]), &c->XB, &c->XN, &c->QKV, &c->O, &c->H};
+                   reinterpret_cast<void**>(&c->GATES), &c->XB, &c->XN, &c->QKV, &c->O, &c->H};
   for (auto p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -279,9 +275,6 @@ int ensure_ws(bt_ctx* c, int need_chunks) {
   BT_CUDA(c, cudaMalloc(&c->H, G * 4 * xe * act));
   if (c->dtype == BT_DTYPE_BF16) {
     BT_CUDA(c, cudaMalloc(&c->XB, G * xe * 2));
-    c->ss_rows = G * std::max<int64_t>(fe / c->hp.stem_dim, BT_CHUNK);
-    BT_CUDA(c, cudaMalloc(&c->SS[0], c->ss_rows * 4));
-    BT_CUDA(c, cudaMalloc(&c->SS[1], c->ss_rows * 4));
   }
   c->ws_wave = want;
   return BT_OK;
@@ -335,33 +328,15 @@ EpiParams epi_generic(const Param* bias, int gelu, const float* resid, int ldr, 
   return e;
 }
 
-// Tensor-core path: the residual stream x travels as (X fp32, XB = bf16(x), SS = row sums of
-// squares).  Consumers of RMSNorm(x) read XB and scale their accumulator rows by 1/|x| (ss_in);
-// producers of a new x write all three (ss_out into the zeroed other half of the ping-pong).
-int ss_begin_producer(bt_ctx* c, int64_t rows, cudaStream_t st, float** ss_out) {
-  const int nxt = c->ss_cur ^ 1;
-  BT_CUDA(c, cudaMemsetAsync(c->SS[nxt], 0, rows * 4, st));
-  *ss_out = c->SS[nxt];
-  return BT_OK;
-}
-
 // x += attention(x) over `planes` planes of L tokens with dim C (reference roformer.py:114-132).
 // freq == true: sequences run over the F planes of each chunk (PartialFTTransformer attnF).
-// xb: bf16 copy of x (tensor-core path), updated in place together with X.
-int attention_block(bt_ctx* c, float* X, void* xb, int planes, int L, int C, int F, bool freq, const AttnW& w,
+int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool freq, const AttnW& w,
                     AttnPlans* tp, int nb, cudaStream_t st) {
   const bool tc = c->dtype == BT_DTYPE_BF16;
   const int heads = C / kHeadDim;
   const int64_t M = static_cast<int64_t>(planes) * L;
-  const void* xin = xb;
-  const float* ss_in = nullptr;
-  if (tc) {
-    ss_in = c->SS[c->ss_cur];
-  } else {
-    launch_norm(X, c->XN, M, C, 0, st);
-    BT_LAUNCHED(c, "norm", st);
-    xin = c->XN;
-  }
+  launch_norm(X, c->XN, M, C, tc, st);
+  BT_LAUNCHED(c, "norm", st);
   {  // gates = sigmoid(to_gates(x_normed)): a [heads -> 32 padded] x C GEMM on the same normalised rows
     GemmShape gg = plain_shape(planes, L, 32, C, C);
     EpiParams eg{};
@@ -369,8 +344,7 @@ int attention_block(bt_ctx* c, float* X, void* xb, int planes, int L, int C, int
     eg.bias = w.bg->f32;
     eg.heads = heads;
     eg.out_f32 = c->GATES;
-    eg.ss_in = ss_in;
-    int rg = run_gemm(c, xin, w.wg, tp ? tp->gates : nullptr, gg, eg, "gemm_gates", st);
+    int rg = run_gemm(c, c->XN, w.wg, tp ? tp->gates : nullptr, gg, eg, "gemm_gates", st);
     if (rg != BT_OK) return rg;
   }
   const float inv_sqrt_d = 0.17677669529663687f;  // 1/sqrt(32): SDPA default scale (roformer.py:78-80)
@@ -380,11 +354,10 @@ int attention_block(bt_ctx* c, float* X, void* xb, int planes, int L, int C, int
   e.rope_cos = find_param(c, "rope.cos")->f32;
   e.rope_sin = find_param(c, "rope.sin")->f32;
   e.C = C; e.heads = heads; e.posmode = freq ? 1 : 0; e.F = F;
-  e.ss_in = ss_in;
   const bool tc_time = tc && !freq;
   e.qscale = tc_time ? inv_sqrt_d * 1.4426950408889634f : 1.0f;
   GemmShape g = plain_shape(planes, L, 3 * C, C, C);
-  int r = run_gemm(c, xin, w.wqkv, tp ? tp->qkv : nullptr, g, e, "gemm_qkv", st);
+  int r = run_gemm(c, c->XN, w.wqkv, tp ? tp->qkv : nullptr, g, e, "gemm_qkv", st);
   if (r != BT_OK) return r;
   if (freq) {
     launch_attn_freq(c->QKV, c->GATES, c->O, nb, F, L, heads, inv_sqrt_d, tc, st);
@@ -398,42 +371,24 @@ int attention_block(bt_ctx* c, float* X, void* xb, int planes, int L, int C, int
     BT_LAUNCHED(c, "attn_time_simt", st);
   }
   GemmShape go = plain_shape(planes, L, C, C, C);
-  EpiParams eo = epi_generic(nullptr, 0, X, C, X, C, tc ? xb : nullptr, C);
-  if (tc) {
-    if ((r = ss_begin_producer(c, M, st, &eo.ss_out)) != BT_OK) return r;
-  }
-  r = run_gemm(c, c->O, w.wout, tp ? tp->out : nullptr, go, eo, "gemm_attn_out", st);
-  if (tc) c->ss_cur ^= 1;
-  return r;
+  EpiParams eo = epi_generic(nullptr, 0, X, C, X, C, nullptr, 0);
+  return run_gemm(c, c->O, w.wout, tp ? tp->out : nullptr, go, eo, "gemm_attn_out", st);
 }
 
-// x += ff(x) (reference roformer.py:38-61).
-int ff_block(bt_ctx* c, float* X, void* xb, int planes, int L, int C, int mult, const FfW& w, FfPlans* tp,
+// x += ff(x) (reference roformer.py:38-61); optionally also writes a bf16 copy of the result.
+int ff_block(bt_ctx* c, float* X, int planes, int L, int C, int mult, const FfW& w, FfPlans* tp, void* copy_act,
              cudaStream_t st) {
   const bool tc = c->dtype == BT_DTYPE_BF16;
   const int64_t M = static_cast<int64_t>(planes) * L;
-  const void* xin = xb;
-  const float* ss_in = nullptr;
-  if (tc) {
-    ss_in = c->SS[c->ss_cur];
-  } else {
-    launch_norm(X, c->XN, M, C, 0, st);
-    BT_LAUNCHED(c, "norm", st);
-    xin = c->XN;
-  }
+  launch_norm(X, c->XN, M, C, tc, st);
+  BT_LAUNCHED(c, "norm", st);
   GemmShape g1 = plain_shape(planes, L, mult * C, C, C);
   EpiParams e1 = epi_generic(w.b1, 1, nullptr, 0, nullptr, 0, c->H, mult * C);
-  e1.ss_in = ss_in;
-  int r = run_gemm(c, xin, w.w1, tp ? tp->ff1 : nullptr, g1, e1, "gemm_ff1", st);
+  int r = run_gemm(c, c->XN, w.w1, tp ? tp->ff1 : nullptr, g1, e1, "gemm_ff1", st);
   if (r != BT_OK) return r;
   GemmShape g2 = plain_shape(planes, L, C, mult * C, mult * C);
-  EpiParams e2 = epi_generic(w.b2, 0, X, C, X, C, tc ? xb : nullptr, C);
-  if (tc) {
-    if ((r = ss_begin_producer(c, M, st, &e2.ss_out)) != BT_OK) return r;
-  }
-  r = run_gemm(c, c->H, w.w2, tp ? tp->ff2 : nullptr, g2, e2, "gemm_ff2", st);
-  if (tc) c->ss_cur ^= 1;
-  return r;
+  EpiParams e2 = epi_generic(w.b2, 0, X, C, X, C, copy_act, C);
+  return run_gemm(c, c->H, w.w2, tp ? tp->ff2 : nullptr, g2, e2, "gemm_ff2", st);
 }
 
 AttnW attn_w(const bt_ctx* c, const std::string& p) {
@@ -473,10 +428,10 @@ int build_plans(bt_ctx* c, int nb, int L, WavePlans** out) {
   auto mk = [&](const void* A, const Param* W, const GemmShape& g, int planes_in) -> TcGemmPlan* {
     return tc_gemm_plan_create(A, W->b16, g, planes_in, err, sizeof(err));
   };
-  auto mk_attn = [&](AttnPlans& a, const AttnW& aw, const void* xb, int planes, int C, bool freq) -> bool {
-    a.qkv = mk(xb, aw.wqkv, plain_shape(planes, L, 3 * C, C, C), planes);
+  auto mk_attn = [&](AttnPlans& a, const AttnW& aw, int planes, int C, bool freq) -> bool {
+    a.qkv = mk(c->XN, aw.wqkv, plain_shape(planes, L, 3 * C, C, C), planes);
     a.out = mk(c->O, aw.wout, plain_shape(planes, L, C, C, C), planes);
-    a.gates = mk(xb, aw.wg, plain_shape(planes, L, 32, C, C), planes);
+    a.gates = mk(c->XN, aw.wg, plain_shape(planes, L, 32, C, C), planes);
     if (!a.qkv || !a.out || !a.gates) return false;
     if (!freq) {
       a.attn = tc_attn_plan_create(c->QKV, planes, L, C / 32, err, sizeof(err));
@@ -484,8 +439,8 @@ int build_plans(bt_ctx* c, int nb, int L, WavePlans** out) {
     }
     return true;
   };
-  auto mk_ff = [&](FfPlans& f, const FfW& fw, const void* xb, int planes, int C, int mult) -> bool {
-    f.ff1 = mk(xb, fw.w1, plain_shape(planes, L, mult * C, C, C), planes);
+  auto mk_ff = [&](FfPlans& f, const FfW& fw, int planes, int C, int mult) -> bool {
+    f.ff1 = mk(c->XN, fw.w1, plain_shape(planes, L, mult * C, C, C), planes);
     f.ff2 = mk(c->H, fw.w2, plain_shape(planes, L, C, mult * C, mult * C), planes);
     return f.ff1 && f.ff2;
   };
@@ -493,15 +448,14 @@ int build_plans(bt_ctx* c, int nb, int L, WavePlans** out) {
   int C = c->hp.stem_dim, F = c->hp.spect_dim / 4;
   for (int i = 0; i < 3 && ok; ++i) {
     const std::string p = "b" + std::to_string(i);
-    const void* xb = (i & 1) ? c->XN : c->XB;  // bf16 copy of this block's x (the conv writes the next block's into the other)
     if (c->hp.partial_transformers) {
-      ok = ok && mk_attn(w->fa[i], attn_w(c, p + ".attnF"), xb, nb * F, C, true);
-      ok = ok && mk_ff(w->ff_f[i], ff_w(c, p + ".ffF"), xb, nb * F, C, 4);
-      ok = ok && mk_attn(w->ta[i], attn_w(c, p + ".attnT"), xb, nb * F, C, false);
-      ok = ok && mk_ff(w->ff_t[i], ff_w(c, p + ".ffT"), xb, nb * F, C, 4);
+      ok = ok && mk_attn(w->fa[i], attn_w(c, p + ".attnF"), nb * F, C, true);
+      ok = ok && mk_ff(w->ff_f[i], ff_w(c, p + ".ffF"), nb * F, C, 4);
+      ok = ok && mk_attn(w->ta[i], attn_w(c, p + ".attnT"), nb * F, C, false);
+      ok = ok && mk_ff(w->ff_t[i], ff_w(c, p + ".ffT"), nb * F, C, 4);
     }
     if (ok) {
-      w->conv[i] = mk(xb, find_param(c, p + ".conv.w"), conv_shape(nb, F, L, C), nb * F);
+      w->conv[i] = mk(c->XB, find_param(c, p + ".conv.w"), conv_shape(nb, F, L, C), nb * F);
       ok = w->conv[i] != nullptr;
     }
     C *= 2; F /= 2;
@@ -515,8 +469,8 @@ int build_plans(bt_ctx* c, int nb, int L, WavePlans** out) {
   w->lf.resize(c->hp.n_layers);
   for (int l = 0; l < c->hp.n_layers && ok; ++l) {
     const std::string p = "l" + std::to_string(l);
-    ok = ok && mk_attn(w->la[l], attn_w(c, p + ".attn"), c->XB, nb, D, false);
-    ok = ok && mk_ff(w->lf[l], ff_w(c, p + ".ff"), c->XB, nb, D, c->hp.ff_mult);
+    ok = ok && mk_attn(w->la[l], attn_w(c, p + ".attn"), nb, D, false);
+    ok = ok && mk_ff(w->lf[l], ff_w(c, p + ".ff"), nb, D, c->hp.ff_mult);
   }
   if (!ok) return fail(c, BT_ERR_CUDA, "tensor-core plan creation failed: %s", err);
   *out = w;
@@ -536,40 +490,36 @@ int run_wave(bt_ctx* c, const float* spect, const Wave& wv, float* beat, float* 
   float* X = c->X0;
   float* Xalt = c->X1;
   int C = c->hp.stem_dim, F = c->hp.spect_dim / 4;
-  c->ss_cur = 0;
   launch_stem(spect, wv.chunks_dev, nb, L, find_param(c, "stem.bn1_scale")->f32,
               find_param(c, "stem.bn1_shift")->f32, find_param(c, "stem.w")->f32,
-              find_param(c, "stem.bias")->f32, X, tc ? c->XB : nullptr, tc ? c->SS[0] : nullptr, st);
+              find_param(c, "stem.bias")->f32, X, st);
   BT_LAUNCHED(c, "stem", st);
   if ((r = do_tap(c, "stem", X, static_cast<int64_t>(nb) * F * L * C, false, st)) != BT_OK) return r;
   for (int i = 0; i < 3; ++i) {
     const std::string p = "b" + std::to_string(i);
     const int planes = nb * F;
     const int64_t elems = static_cast<int64_t>(planes) * L * C;
-    void* xb = (i & 1) ? c->XN : c->XB;       // bf16 copy of this block's x (tensor-core path)
-    void* xb_next = (i & 1) ? c->XB : c->XN;  // where the conv puts the next block's
+    void* copy_for_conv = tc ? c->XB : nullptr;
     if (c->hp.partial_transformers) {
-      if ((r = attention_block(c, X, xb, planes, L, C, F, true, attn_w(c, p + ".attnF"), wp ? &wp->fa[i] : nullptr, nb, st)) != BT_OK) return r;
+      if ((r = attention_block(c, X, planes, L, C, F, true, attn_w(c, p + ".attnF"), wp ? &wp->fa[i] : nullptr, nb, st)) != BT_OK) return r;
       if ((r = do_tap(c, (p + ".attnF").c_str(), X, elems, false, st)) != BT_OK) return r;
-      if ((r = ff_block(c, X, xb, planes, L, C, 4, ff_w(c, p + ".ffF"), wp ? &wp->ff_f[i] : nullptr, st)) != BT_OK) return r;
+      if ((r = ff_block(c, X, planes, L, C, 4, ff_w(c, p + ".ffF"), wp ? &wp->ff_f[i] : nullptr, nullptr, st)) != BT_OK) return r;
       if ((r = do_tap(c, (p + ".ffF").c_str(), X, elems, false, st)) != BT_OK) return r;
-      if ((r = attention_block(c, X, xb, planes, L, C, F, false, attn_w(c, p + ".attnT"), wp ? &wp->ta[i] : nullptr, nb, st)) != BT_OK) return r;
+      if ((r = attention_block(c, X, planes, L, C, F, false, attn_w(c, p + ".attnT"), wp ? &wp->ta[i] : nullptr, nb, st)) != BT_OK) return r;
       if ((r = do_tap(c, (p + ".attnT").c_str(), X, elems, false, st)) != BT_OK) return r;
-      if ((r = ff_block(c, X, xb, planes, L, C, 4, ff_w(c, p + ".ffT"), wp ? &wp->ff_t[i] : nullptr, st)) != BT_OK) return r;
+      if ((r = ff_block(c, X, planes, L, C, 4, ff_w(c, p + ".ffT"), wp ? &wp->ff_t[i] : nullptr, copy_for_conv, st)) != BT_OK) return r;
       if ((r = do_tap(c, (p + ".ffT").c_str(), X, elems, false, st)) != BT_OK) return r;
+    } else if (tc) {
+      launch_f32_to_bf16(X, c->XB, elems, st);
+      BT_LAUNCHED(c, "f32_to_bf16", st);
     }
-    // conv C -> 2C (+ folded BN2d + GELU).  Blocks 0/1 produce the next block's x (fp32 + bf16 copy +
-    // row sums of squares); the last block feeds frontend.linear (activation dtype only).
+    // conv C -> 2C (+ folded BN2d + GELU); the last block feeds frontend.linear (activation dtype)
     GemmShape g = conv_shape(nb, F, L, C);
     const bool last = i == 2;
     EpiParams e = epi_generic(find_param(c, p + ".conv.bias"), 1, nullptr, 0, last ? nullptr : Xalt, 2 * C,
-                              (last || tc) ? (last ? c->XN : xb_next) : nullptr, 2 * C);
-    if (tc && !last) {
-      if ((r = ss_begin_producer(c, static_cast<int64_t>(planes / 2) * L, st, &e.ss_out)) != BT_OK) return r;
-    }
-    if ((r = run_gemm(c, tc ? static_cast<const void*>(xb) : static_cast<const void*>(X), find_param(c, p + ".conv.w"),
+                              last ? c->XN : nullptr, 2 * C);
+    if ((r = run_gemm(c, tc ? c->XB : static_cast<const void*>(X), find_param(c, p + ".conv.w"),
                       wp ? wp->conv[i] : nullptr, g, e, "gemm_conv", st)) != BT_OK) return r;
-    if (tc && !last) c->ss_cur ^= 1;
     C *= 2; F /= 2;
     if (!last) std::swap(X, Xalt);
     if ((r = do_tap(c, (p + ".conv").c_str(), last ? c->XN : static_cast<const void*>(X),
@@ -578,19 +528,15 @@ int run_wave(bt_ctx* c, const float* spect, const Wave& wv, float* beat, float* 
   const int D = c->hp.transformer_dim;
   {
     GemmShape g = lin_shape(nb, L, D, F, C);
-    EpiParams e = epi_generic(find_param(c, "lin.b"), 0, nullptr, 0, X, D, tc ? c->XB : nullptr, D);
-    if (tc) {
-      if ((r = ss_begin_producer(c, static_cast<int64_t>(nb) * L, st, &e.ss_out)) != BT_OK) return r;
-    }
+    EpiParams e = epi_generic(find_param(c, "lin.b"), 0, nullptr, 0, X, D, nullptr, 0);
     if ((r = run_gemm(c, c->XN, find_param(c, "lin.w"), wp ? wp->lin : nullptr, g, e, "gemm_frontend_linear", st)) != BT_OK) return r;
-    if (tc) c->ss_cur ^= 1;
     if ((r = do_tap(c, "frontend", X, static_cast<int64_t>(nb) * L * D, false, st)) != BT_OK) return r;
   }
   for (int l = 0; l < c->hp.n_layers; ++l) {
     const std::string p = "l" + std::to_string(l);
-    if ((r = attention_block(c, X, c->XB, nb, L, D, 1, false, attn_w(c, p + ".attn"), wp ? &wp->la[l] : nullptr, nb, st)) != BT_OK) return r;
+    if ((r = attention_block(c, X, nb, L, D, 1, false, attn_w(c, p + ".attn"), wp ? &wp->la[l] : nullptr, nb, st)) != BT_OK) return r;
     if ((r = do_tap(c, (p + ".attn").c_str(), X, static_cast<int64_t>(nb) * L * D, false, st)) != BT_OK) return r;
-    if ((r = ff_block(c, X, c->XB, nb, L, D, c->hp.ff_mult, ff_w(c, p + ".ff"), wp ? &wp->lf[l] : nullptr, st)) != BT_OK) return r;
+    if ((r = ff_block(c, X, nb, L, D, c->hp.ff_mult, ff_w(c, p + ".ff"), wp ? &wp->lf[l] : nullptr, nullptr, st)) != BT_OK) return r;
     if ((r = do_tap(c, (p + ".ff").c_str(), X, static_cast<int64_t>(nb) * L * D, false, st)) != BT_OK) return r;
   }
   launch_head(X, D, find_param(c, "head.w")->f32, find_param(c, "head.b")->f32, wv.chunks_dev, nb, L, beat, down, st);

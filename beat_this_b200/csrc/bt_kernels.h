@@ -45,12 +45,6 @@ struct EpiParams {
   int posmode;  // 0: position = m % L (time attention)   1: position = (m / L) % F (freq attention)
   int F;
   float qscale;  // multiplied into q after RoPE
-  // Deferred RMSNorm (tensor-core path): a producer of the residual stream also accumulates the
-  // row sums of squares of what it stores (ss_out, pre-zeroed, atomicAdd); a consumer multiplies
-  // its accumulator rows by 1/max(sqrt(ss_in[m]),1e-12) -- (x/|x|) W == (x W)/|x| -- so the
-  // normalised activations are never written to memory.
-  float* ss_out;
-  const float* ss_in;
 };
 
 // ---- fp32 CUDA-core path -------------------------------------------------------------------
@@ -75,9 +69,8 @@ struct ChunkSrc {
   int32_t write_lo;    // chunk-local frame range [write_lo, write_hi) this chunk owns
   int32_t write_hi;
 };
-// xb / ss (optional, tensor-core path): bf16 copy of the output and its per-row sum of squares
 void launch_stem(const float* spect, const ChunkSrc* chunks, int nchunks, int L, const float* bn1_scale,
-                 const float* bn1_shift, const float* w, const float* bias, float* out, void* xb, float* ss,
+                 const float* bn1_shift, const float* w, const float* bias, float* out,
                  cudaStream_t st);
 void launch_head(const float* x, int D, const float* w, const float* b, const ChunkSrc* chunks,
                  int nchunks, int L, float* beat, float* down, cudaStream_t st);

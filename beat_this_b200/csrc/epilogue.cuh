@@ -80,20 +80,14 @@ __device__ __forceinline__ float gelu_for(float x) {
 template <typename TAct, int CNT>
 __device__ __forceinline__ void epilogue_apply(const EpiParams& e, int L, int64_t m, int n0,
                                                float (&v)[CNT], const float (&pre)[CNT], bool use_pre) {
-  float inv = 1.0f;
-  if (e.ss_in) inv = 1.0f / fmaxf(sqrtf(__ldg(e.ss_in + m)), 1e-12f);
   if (e.kind == 0) {
     if (e.bias) {
       const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
 #pragma unroll
       for (int i = 0; i < CNT / 4; ++i) {
         const float4 q = __ldg(b4 + i);
-        v[4 * i] = fmaf(v[4 * i], inv, q.x); v[4 * i + 1] = fmaf(v[4 * i + 1], inv, q.y);
-        v[4 * i + 2] = fmaf(v[4 * i + 2], inv, q.z); v[4 * i + 3] = fmaf(v[4 * i + 3], inv, q.w);
+        v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
       }
-    } else if (e.ss_in) {
-#pragma unroll
-      for (int i = 0; i < CNT; ++i) v[i] *= inv;
     }
     if (e.gelu) {
 #pragma unroll
@@ -115,24 +109,18 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& e, int L, int64_
     }
     if (e.out_f32) store_act<float, CNT>(e.out_f32 + m * e.ldo_f32 + n0, v);
     if (e.out_act) store_act<TAct, CNT>(reinterpret_cast<TAct*>(e.out_act) + m * e.ldo_act + n0, v);
-    if (e.ss_out) {
-      float ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < CNT; ++i) ss = fmaf(v[i], v[i], ss);
-      atomicAdd(e.ss_out + m, ss);
-    }
   } else if (e.kind == 2) {
     // attention gates (reference roformer.py:127-128): sigmoid(to_gates(x_normed)), N padded to 32
 #pragma unroll
     for (int i = 0; i < CNT; ++i)
-      if (n0 + i < e.heads) e.out_f32[m * e.heads + n0 + i] = sigmoidf_(fmaf(v[i], inv, __ldg(e.bias + n0 + i)));
+      if (n0 + i < e.heads) e.out_f32[m * e.heads + n0 + i] = sigmoidf_(v[i] + __ldg(e.bias + n0 + i));
   } else {
     // qkv: RoPE on interleaved pairs (rotary_embedding_torch semantics, reference
     // roformer.py:121-123): out[2i] = x[2i] cos - x[2i+1] sin ; out[2i+1] = x[2i+1] cos + x[2i] sin
     const int which = n0 / e.C;          // 0 q, 1 k, 2 v
     TAct* dst = reinterpret_cast<TAct*>(e.out_act) + m * e.ldo_act + n0;
     if (which < 2) {
-      const float sc = (which == 0 ? e.qscale : 1.0f) * inv;
+      const float sc = which == 0 ? e.qscale : 1.0f;
       if (use_pre && CNT == 32) {  // cos[16] | sin[16] of this row's position, preloaded by the caller
 #pragma unroll
         for (int i = 0; i < CNT / 2; ++i) {
@@ -156,10 +144,6 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& e, int L, int64_
       }
       store_act<TAct, CNT>(dst, v);
     } else {
-      if (e.ss_in) {
-#pragma unroll
-        for (int i = 0; i < CNT; ++i) v[i] *= inv;
-      }
       store_act<TAct, CNT>(dst, v);
     }
   }

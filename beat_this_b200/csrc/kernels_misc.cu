@@ -114,8 +114,7 @@ void launch_logmel(const float* audio, const int64_t* sample_off_dev, const int6
 __global__ void __launch_bounds__(128)
 stem_kernel(const float* __restrict__ spect, const ChunkSrc* __restrict__ chunks, int L,
             const float* __restrict__ bn1_scale, const float* __restrict__ bn1_shift,
-            const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
-            bf16* __restrict__ xb, float* __restrict__ ssq) {
+            const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out) {
   __shared__ float ws[32 * 12];
   __shared__ float bs[32];
   for (int i = threadIdx.x; i < 32 * 12; i += 128) ws[i] = w[i];
@@ -141,9 +140,7 @@ stem_kernel(const float* __restrict__ spect, const ChunkSrc* __restrict__ chunks
     for (int df = 0; df < 4; ++df)
       in[df][dt] = conv_ok ? fmaf(vv[df], bn1_scale[4 * f + df], bn1_shift[4 * f + df]) : 0.f;
   }
-  const int64_t mrow = (static_cast<int64_t>(b) * 32 + f) * L + t;
-  float* op = out + mrow * 32;
-  float ss = 0.f;
+  float* op = out + ((static_cast<int64_t>(b) * 32 + f) * L + t) * 32;
 #pragma unroll
   for (int c4 = 0; c4 < 8; ++c4) {
     float r[4];
@@ -156,24 +153,16 @@ stem_kernel(const float* __restrict__ spect, const ChunkSrc* __restrict__ chunks
 #pragma unroll
         for (int dt = 0; dt < 3; ++dt) a = fmaf(in[df][dt], ws[co * 12 + df * 3 + dt], a);
       r[i] = gelu_erf(a);
-      ss = fmaf(r[i], r[i], ss);
     }
     reinterpret_cast<float4*>(op)[c4] = make_float4(r[0], r[1], r[2], r[3]);
-    if (xb) {
-      uint2 u;
-      u.x = pack_bf16x2(r[0], r[1]);
-      u.y = pack_bf16x2(r[2], r[3]);
-      reinterpret_cast<uint2*>(xb + mrow * 32)[c4] = u;
-    }
   }
-  if (ssq) ssq[mrow] = ss;
 }
 
 void launch_stem(const float* spect, const ChunkSrc* chunks, int nchunks, int L, const float* bn1_scale,
-                 const float* bn1_shift, const float* w, const float* bias, float* out, void* xb, float* ss,
+                 const float* bn1_shift, const float* w, const float* bias, float* out,
                  cudaStream_t st) {
   dim3 grid(ceil_div(L, 128), 32, nchunks);
-  stem_kernel<<<grid, 128, 0, st>>>(spect, chunks, L, bn1_scale, bn1_shift, w, bias, out, reinterpret_cast<bf16*>(xb), ss);
+  stem_kernel<<<grid, 128, 0, st>>>(spect, chunks, L, bn1_scale, bn1_shift, w, bias, out);
 }
 
 // ------------------------------------------------------------------------------------------
