@@ -335,9 +335,10 @@ int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool f
   const bool tc = c->dtype == BT_DTYPE_BF16;
   const int heads = C / kHeadDim;
   const int64_t M = static_cast<int64_t>(planes) * L;
-  launch_norm(X, c->XN, M, C, tc, st);
-  BT_LAUNCHED(c, "norm", st);
-  {  // gates = sigmoid(to_gates(x_normed)): a [heads -> 32 padded] x C GEMM on the same normalised rows
+  const bool gates_in_norm = heads <= 4;  // frontend attentions: 1/2/4 heads
+  launch_norm(X, c->XN, M, C, tc, st, gates_in_norm ? c->GATES : nullptr, w.wg->f32, w.bg->f32, heads);
+  BT_LAUNCHED(c, gates_in_norm ? "norm_gates" : "norm", st);
+  if (!gates_in_norm) {  // gates = sigmoid(to_gates(x_normed)): a [heads -> 32 padded] x C GEMM on the same rows
     GemmShape gg = plain_shape(planes, L, 32, C, C);
     EpiParams eg{};
     eg.kind = 2;

@@ -58,8 +58,10 @@ void launch_attn_time_simt(const float* qkv, const float* gates, float* out, int
 // frequency-direction attention: tokens m = (b*F + f)*L + t, sequences over f.
 void launch_attn_freq(const void* qkv, const float* gates, void* out, int B, int F, int L,
                       int heads, float scale, int act_bf16, cudaStream_t st);
-// RMSNorm without gamma (folded into the next weight).
-void launch_norm(const float* x, void* xn, int64_t M, int C, int act_bf16, cudaStream_t st);
+// RMSNorm without gamma (folded into the next weight); optionally also the attention gates
+// sigmoid(xn . wg[h] + bg[h]) for h < heads (used when heads <= 4; wg is [>=heads, C] fp32).
+void launch_norm(const float* x, void* xn, int64_t M, int C, int act_bf16, cudaStream_t st, float* gates = nullptr,
+                 const float* wg = nullptr, const float* bg = nullptr, int heads = 0);
 // per-chunk source description for the stem (chunk gather from per-clip spectrograms)
 struct ChunkSrc {
   int64_t frame_base;  // first frame of the clip inside the concatenated spectrogram

@@ -173,7 +173,8 @@ void launch_stem(const float* spect, const ChunkSrc* chunks, int nchunks, int L,
 // ------------------------------------------------------------------------------------------
 template <typename TAct, int C>
 __global__ void __launch_bounds__(256)
-norm_kernel(const float* __restrict__ x, TAct* __restrict__ xn, int64_t M) {
+norm_kernel(const float* __restrict__ x, TAct* __restrict__ xn, int64_t M, float* __restrict__ gates,
+            const float* __restrict__ wg, const float* __restrict__ bg, int heads) {
   constexpr int LPR = C / 4 < 32 ? C / 4 : 32;  // lanes per row
   constexpr int RPW = 32 / LPR;                 // rows per warp
   constexpr int VPL = C / 4 / LPR;              // float4 per lane
@@ -194,29 +195,49 @@ norm_kernel(const float* __restrict__ x, TAct* __restrict__ xn, int64_t M) {
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) { v[i].x *= inv; v[i].y *= inv; v[i].z *= inv; v[i].w *= inv; }
+  if (gates) {
+    // attention gates sigmoid(to_gates(x_normed)) (reference roformer.py:127-128) for the few-head
+    // frontend attentions (1, 2 or 4 heads): a handful of FMAs per row inside this HBM-bound kernel
+    // instead of a separate padded-N GEMM launch over the same rows.
+    for (int h = 0; h < heads; ++h) {
+      const float4* w4 = reinterpret_cast<const float4*>(wg + h * C);
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const float4 w = __ldg(w4 + li + LPR * i);
+        a = fmaf(v[i].x, w.x, a); a = fmaf(v[i].y, w.y, a); a = fmaf(v[i].z, w.z, a); a = fmaf(v[i].w, w.w, a);
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (ok && li == 0) gates[row * heads + h] = sigmoidf_(a + __ldg(bg + h));
+    }
+  }
   if (!ok) return;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const float o4[4] = {v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv};
     TAct* dst = xn + row * C + 4 * (li + LPR * i);
     if constexpr (sizeof(TAct) == 4) {
-      *reinterpret_cast<float4*>(dst) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+      *reinterpret_cast<float4*>(dst) = v[i];
     } else {
       uint2 u;
-      u.x = pack_bf16x2(o4[0], o4[1]);
-      u.y = pack_bf16x2(o4[2], o4[3]);
+      u.x = pack_bf16x2(v[i].x, v[i].y);
+      u.y = pack_bf16x2(v[i].z, v[i].w);
       *reinterpret_cast<uint2*>(dst) = u;
     }
   }
 }
 
 template <typename TAct>
-static void norm_dispatch(const float* x, void* xn, int64_t M, int C, cudaStream_t st) {
+static void norm_dispatch(const float* x, void* xn, int64_t M, int C, float* gates, const float* wg, const float* bg,
+                          int heads, cudaStream_t st) {
   TAct* o = reinterpret_cast<TAct*>(xn);
-#define BT_NORM_CASE(c)                                                                         \
-  case c: {                                                                                     \
-    constexpr int rpw = (c / 4 < 32) ? 32 / (c / 4) : 1;                                        \
-    norm_kernel<TAct, c><<<static_cast<unsigned>(ceil_div64(M, 8 * rpw)), 256, 0, st>>>(x, o, M); \
+#define BT_NORM_CASE(c)                                                                                   \
+  case c: {                                                                                               \
+    constexpr int rpw = (c / 4 < 32) ? 32 / (c / 4) : 1;                                                  \
+    norm_kernel<TAct, c><<<static_cast<unsigned>(ceil_div64(M, 8 * rpw)), 256, 0, st>>>(x, o, M, gates, wg, \
+                                                                                          bg, heads);     \
   } break;
   switch (C) {
     BT_NORM_CASE(32) BT_NORM_CASE(64) BT_NORM_CASE(128) BT_NORM_CASE(256) BT_NORM_CASE(512) BT_NORM_CASE(1024)
@@ -225,9 +246,10 @@ static void norm_dispatch(const float* x, void* xn, int64_t M, int C, cudaStream
 #undef BT_NORM_CASE
 }
 
-void launch_norm(const float* x, void* xn, int64_t M, int C, int act_bf16, cudaStream_t st) {
-  if (act_bf16) norm_dispatch<bf16>(x, xn, M, C, st);
-  else norm_dispatch<float>(x, xn, M, C, st);
+void launch_norm(const float* x, void* xn, int64_t M, int C, int act_bf16, cudaStream_t st, float* gates,
+                 const float* wg, const float* bg, int heads) {
+  if (act_bf16) norm_dispatch<bf16>(x, xn, M, C, gates, wg, bg, heads, st);
+  else norm_dispatch<float>(x, xn, M, C, gates, wg, bg, heads, st);
 }
 
 // ------------------------------------------------------------------------------------------
