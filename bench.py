@@ -307,9 +307,16 @@ def run_ours(args, rank, world, local):
     key = "attn_time_tc" if bf16 else "attn_time_simt"
     a_ms, a_n = prof.get(key, (0.0, 0))
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    # DRAM traffic of the kernel from the committed ncu --set full capture of the same configuration
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "attn_traffic.json")
+    if bf16 and os.path.exists(tpath) and args.batch == 64 and args.seconds == 30.0:
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("dram_bytes_per_launch_mean"), tj.get("source")
     roof = {"bound": "tensor", "kernel": key, "achieved": (attn_flops / (a_ms / 1000.0) / 1e12) if a_ms > 0 else None,
             "peak": peak_tf, "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
-            "unit": "TFLOP/s", "traffic": None, "launches": a_n, "avg_launch_ms": (a_ms / a_n) if a_n else None,
+            "unit": "TFLOP/s", "traffic": traffic, "traffic_source": traffic_src, "launches": a_n, "avg_launch_ms": (a_ms / a_n) if a_n else None,
             "algorithmic_flops_per_launch": attn_flops / a_n if a_n else None}
     roof["frac"] = (roof["achieved"] / peak_tf) if roof["achieved"] else None
     tot_ms = sum(v[0] for v in prof.values()) or 1.0

@@ -195,3 +195,28 @@ def test_stage_parity_bf16(small_bf16, small0_ckpt):
     for name, err, mag in rows:
         print(f"bf16 stage {name:10s} max abs err {err:.3e} (|ref| max {mag:.2f})")
     assert max(r[1] / max(r[2], 1.0) for r in rows) < 0.05
+
+
+def test_postprocessor_batched_with_padding_mask(lib_built, dev):
+    """Postprocessor API parity (reference postprocessor.py:39-83): batched [B,T] logits with a padding
+    mask give, per piece, what the un-batched call gives on the un-padded logits."""
+    from beat_this_b200.postprocessor import Postprocessor
+    from oracle import beat_this_oracle as O
+
+    rng = np.random.default_rng(11)
+    T, lens = 400, [400, 250, 31]
+    beat = torch.tensor(rng.standard_normal((3, T)).astype(np.float32) * 2)
+    down = torch.tensor(rng.standard_normal((3, T)).astype(np.float32) * 2 - 1)
+    mask = torch.zeros(3, T, dtype=torch.bool)
+    for i, n in enumerate(lens):
+        mask[i, :n] = True
+    post = Postprocessor("minimal", device=dev)
+    pb, pd = post(beat, down, mask)
+    assert isinstance(pb, tuple) and len(pb) == 3
+    for i, n in enumerate(lens):
+        ob, od = O.postp_minimal(beat[i, :n], down[i, :n])
+        assert np.array_equal(pb[i], ob) and np.array_equal(pd[i], od)
+        ub, ud = post(beat[i, :n], down[i, :n])
+        assert np.array_equal(ub, ob) and np.array_equal(ud, od)
+    with pytest.raises(AssertionError):
+        Postprocessor("viterbi")
