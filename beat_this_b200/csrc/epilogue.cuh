@@ -79,14 +79,26 @@ __device__ __forceinline__ float gelu_for(float x) {
 // q/k/v boundary because C % 32 == 0.
 template <typename TAct, int CNT>
 __device__ __forceinline__ void epilogue_apply(const EpiParams& e, int L, int64_t m, int n0,
-                                               float (&v)[CNT], const float (&pre)[CNT], bool use_pre) {
+                                               float (&v)[CNT], const float (&pre)[CNT], bool use_pre,
+                                               uint32_t bias_smem = 0) {
   if (e.kind == 0) {
     if (e.bias) {
-      const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
+      if (bias_smem) {  // bias vector staged in shared memory by the caller (short-latency broadcast reads)
 #pragma unroll
-      for (int i = 0; i < CNT / 4; ++i) {
-        const float4 q = __ldg(b4 + i);
-        v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+        for (int i = 0; i < CNT / 4; ++i) {
+          float4 q;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
+                       : "r"(bias_smem + static_cast<uint32_t>(n0 + 4 * i) * 4u));
+          v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+        }
+      } else {
+        const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
+#pragma unroll
+        for (int i = 0; i < CNT / 4; ++i) {
+          const float4 q = __ldg(b4 + i);
+          v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+        }
       }
     }
     if (e.gelu) {

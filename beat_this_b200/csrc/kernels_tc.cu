@@ -60,7 +60,8 @@ struct TgCfg {
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
   static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int TCOLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int BIAS_BYTES = 16384;  // bias vector (N <= 4096 floats) staged for the epilogue
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BIAS_BYTES;
   static constexpr int SWZ = BK * 2;  // 128 or 64 byte rows
 };
 
@@ -79,9 +80,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sBias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool stage_bias = e.kind == 0 && e.bias != nullptr && g.N <= Cfg::BIAS_BYTES / 4;
+  if (stage_bias)
+    for (int i = threadIdx.x; i < g.N; i += TG_THREADS) sBias[i] = __ldg(e.bias + i);
+  const uint32_t bias_smem = stage_bias ? smem_u32(sBias) : 0u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -222,7 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-            epilogue_apply<bf16, 32>(e, g.L, m, nt * BN + c * 32, v, cur, has_rope || has_resid);
+            epilogue_apply<bf16, 32>(e, g.L, m, nt * BN + c * 32, v, cur, has_rope || has_resid, bias_smem);
           }
         }
       }
