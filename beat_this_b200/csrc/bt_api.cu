@@ -33,7 +33,7 @@ struct FfW { const Param *w1, *b1, *w2, *b2; };
 
 // tensor-core plans for one (wave size, chunk length) geometry
 struct AttnPlans { TcGemmPlan *qkv = nullptr, *out = nullptr, *gates = nullptr; TcAttnPlan* attn = nullptr; };
-struct FfPlans { TcGemmPlan *ff1 = nullptr, *ff2 = nullptr; };
+struct FfPlans { TcGemmPlan *ff1 = nullptr, *ff2 = nullptr; TcFfPlan* fused = nullptr; };
 struct WavePlans {
   AttnPlans fa[3], ta[3];
   FfPlans ff_f[3], ff_t[3];
@@ -56,6 +56,7 @@ struct bt_ctx {
   mutable char err[1024] = "";
   int64_t launches = 0;
   bool sync_debug = false;
+  bool fuse_ff = true;  // BT_FUSE_FF=0 falls back to norm + two GEMMs for the narrow frontend FFNs
 
   // workspace: sized for ws_wave chunks of BT_CHUNK frames; grows on demand up to `wave`
   int wave = 128;
@@ -234,6 +235,7 @@ void free_plans(bt_ctx* c) {
       if (a.attn) tc_attn_plan_destroy(a.attn);
     };
     auto ff = [](FfPlans& f) {
+      if (f.fused) tc_ff_plan_destroy(f.fused);
       if (f.ff1) tc_gemm_plan_destroy(f.ff1);
       if (f.ff2) tc_gemm_plan_destroy(f.ff2);
     };
@@ -381,6 +383,11 @@ int ff_block(bt_ctx* c, float* X, int planes, int L, int C, int mult, const FfW&
              cudaStream_t st) {
   const bool tc = c->dtype == BT_DTYPE_BF16;
   const int64_t M = static_cast<int64_t>(planes) * L;
+  if (tc && tp && tp->fused) {
+    if (launch_fused_ff(tp->fused, X, w.b1->f32, w.b2->f32, copy_act, st) != 0) return fail(c, BT_ERR_CUDA, "fused ff launch failed");
+    BT_LAUNCHED(c, "ff_fused", st);
+    return BT_OK;
+  }
   launch_norm(X, c->XN, M, C, tc, st);
   BT_LAUNCHED(c, "norm", st);
   GemmShape g1 = plain_shape(planes, L, mult * C, C, C);
@@ -441,6 +448,10 @@ int build_plans(bt_ctx* c, int nb, int L, WavePlans** out) {
     return true;
   };
   auto mk_ff = [&](FfPlans& f, const FfW& fw, int planes, int C, int mult) -> bool {
+    if (c->fuse_ff && mult == 4 && (C == 32 || C == 64)) {  // narrow frontend FFNs: one fused kernel
+      f.fused = tc_ff_plan_create(fw.w1->b16, fw.w2->b16, C, static_cast<int64_t>(planes) * L, err, sizeof(err));
+      return f.fused != nullptr;
+    }
     f.ff1 = mk(c->XN, fw.w1, plain_shape(planes, L, mult * C, C, C), planes);
     f.ff2 = mk(c->H, fw.w2, plain_shape(planes, L, C, mult * C, mult * C), planes);
     return f.ff1 && f.ff2;
@@ -612,6 +623,8 @@ int bt_create(bt_ctx** out, int device_ordinal, const bt_hparams* hp, int comput
   c->dtype = compute_dtype;
   const char* dbg = getenv("BT_SYNC_DEBUG");
   c->sync_debug = dbg && dbg[0] == '1';
+  const char* ffe = getenv("BT_FUSE_FF");
+  c->fuse_ff = !(ffe && ffe[0] == '0');
 
   if (cudaEventCreateWithFlags(&c->stage_ev, cudaEventDisableTiming) != cudaSuccess) {
     delete c;

@@ -630,6 +630,240 @@ int launch_attn_time_tc(const TcAttnPlan* p, const float* gates, void* out, cuda
   return 0;
 }
 
+// ==================================================================== fused frontend FFN
+// x += W2 gelu(W1 rmsnorm(x) + b1) + b2 for the narrow frontend FFNs (C = 32 / 64, hidden 4C) in ONE
+// kernel (reference roformer.py:38-61): the hidden activations never leave the SM.  Unfused, this
+// block streams 32 bytes per element through HBM (norm 6 + ff1 10 + ff2 16); fused it is 8.
+// CTA = 128 tokens; warps 0-3: one token row per thread (RMSNorm, bias+GELU, residual), warp 4
+// lane 0: TMA (weights) + tcgen05.mma issue.  Hidden units are processed in chunks of 128:
+//   H_h = Xn W1_h^T (N=128, K=C) -> TMEM cols [0,128) -> bias+GELU -> bf16 tile in smem ->
+//   OUT (+)= H_h W2_h^T (N=C, K=128) -> TMEM cols [128,128+C).
+constexpr int FF_THREADS = 160;
+template <int C>
+struct FfCfg {
+  static constexpr int NH = 4 * C / 128;            // hidden chunks
+  static constexpr int A_BYTES = 128 * C * 2;       // normalised tokens, K-major
+  static constexpr int W1_BYTES = 4 * C * C * 2;    // all chunks resident
+  static constexpr int W2C_BYTES = C * 128 * 2;     // one K-chunk of W2
+  static constexpr int H_BYTES = 128 * 128 * 2;
+  static constexpr int SMEM = A_BYTES + W1_BYTES + W2C_BYTES + H_BYTES + 5 * C * 4 + 1024 + 128;
+  static constexpr int SWZ_A = C * 2 < 128 ? C * 2 : 128;  // 64-byte rows for C=32, 128 for C=64
+};
+
+template <int C>
+__global__ void __launch_bounds__(FF_THREADS, 2)
+fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                float* __restrict__ X, const float* __restrict__ b1, const float* __restrict__ b2,
+                bf16* __restrict__ xb_out, int64_t M) {
+  using Cfg = FfCfg<C>;
+  constexpr int NH = Cfg::NH;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = sbase;
+  const uint32_t sW1 = sA + Cfg::A_BYTES;
+  const uint32_t sW2 = sW1 + Cfg::W1_BYTES;
+  const uint32_t sH = sW2 + Cfg::W2C_BYTES;
+  const uint32_t sB = sH + Cfg::H_BYTES;          // b1[4C] | b2[C] fp32
+  const uint32_t bar_w1 = sB + 5 * C * 4;
+  const uint32_t bar_w2 = bar_w1 + 8;
+  const uint32_t bar_a = bar_w2 + 8;
+  const uint32_t bar_h = bar_a + 8;
+  const uint32_t bar_h2 = bar_h + 8;
+  const uint32_t bar_o = bar_h2 + 8;
+  const uint32_t tmem_slot = bar_o + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * 128;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    auto init = [](uint32_t bar, uint32_t count) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    };
+    init(bar_w1, 1); init(bar_w2, 1); init(bar_a, 128); init(bar_h, 1); init(bar_h2, 128); init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 5 * C; i += FF_THREADS)
+    st_shared_f32(sB + 4 * i, i < 4 * C ? __ldg(b1 + i) : __ldg(b2 + i - 4 * C));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc_bf16(128, 128);
+      constexpr uint32_t idesc2 = make_idesc_bf16(128, C);
+      // weights: W1 [4C, C] all chunks (boxes of 128 rows), W2 [C, 4C] first K-chunk (two 64-wide boxes)
+      mbar_expect_tx_a(bar_w1, Cfg::W1_BYTES);
+      for (int h = 0; h < NH; ++h) {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(sW1 + h * (128 * C * 2)), "l"(reinterpret_cast<uint64_t>(&tmW1)), "r"(bar_w1), "r"(0), "r"(h * 128) : "memory");
+      }
+      auto load_w2 = [&](int h) {
+        mbar_expect_tx_a(bar_w2, Cfg::W2C_BYTES);
+        for (int a = 0; a < 2; ++a)
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+              ::"r"(sW2 + a * (C * 128)), "l"(reinterpret_cast<uint64_t>(&tmW2)), "r"(bar_w2), "r"(h * 128 + a * 64), "r"(0) : "memory");
+      };
+      load_w2(0);
+      auto issue_mma1 = [&](int h) {
+#pragma unroll
+        for (int k = 0; k < C / 16; ++k)
+          umma_bf16(tmem_base, make_kmajor_desc<Cfg::SWZ_A>(sA + k * 32),
+                    make_kmajor_desc<Cfg::SWZ_A>(sW1 + h * (128 * C * 2) + k * 32), idesc1, k != 0 ? 1u : 0u);
+        umma_commit_a(bar_h);
+      };
+      mbar_wait_a(bar_a, 0);
+      mbar_wait_a(bar_w1, 0);
+      tc_fence_after();
+      issue_mma1(0);
+      for (int h = 0; h < NH; ++h) {
+        mbar_wait_a(bar_h2, h & 1);  // bf16 H_h tile written, accumulator H consumed
+        tc_fence_after();
+        if (h + 1 < NH) issue_mma1(h + 1);
+        mbar_wait_a(bar_w2, h & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_base + 128, make_kmajor_desc<128>(sH + (k >> 2) * 16384 + (k & 3) * 32),
+                    make_kmajor_desc<128>(sW2 + (k >> 2) * (C * 128) + (k & 3) * 32), idesc2, (h | k) != 0 ? 1u : 0u);
+        umma_commit_a(bar_o);
+        if (h + 1 < NH) {
+          mbar_wait_a(bar_o, h & 1);  // MMA2_h finished reading W2_h (and the H tile)
+          load_w2(h + 1);
+        }
+      }
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const int64_t m = m0 + row;
+    const bool valid = m < M;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    // ---- RMSNorm of this token (x stays in registers for the residual) ----
+    float x[C];
+    {
+      const float4* xr = reinterpret_cast<const float4*>(X + (valid ? m : 0) * C);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < C / 4; ++i) {
+        const float4 q = valid ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
+        ss = fmaf(q.x, q.x, ss); ss = fmaf(q.y, q.y, ss); ss = fmaf(q.z, q.z, ss); ss = fmaf(q.w, q.w, ss);
+      }
+      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+      constexpr int RB = C * 2;  // bytes per A row
+      const uint32_t arow = sA + row * RB;
+      const uint32_t sw = C == 32 ? (static_cast<uint32_t>((row >> 1) & 3) << 4) : (static_cast<uint32_t>(row & 7) << 4);
+#pragma unroll
+      for (int c = 0; c < C / 8; ++c)
+        st_shared_v4(arow + ((c << 4) ^ sw), pack_bf16x2(x[8 * c] * inv, x[8 * c + 1] * inv),
+                     pack_bf16x2(x[8 * c + 2] * inv, x[8 * c + 3] * inv), pack_bf16x2(x[8 * c + 4] * inv, x[8 * c + 5] * inv),
+                     pack_bf16x2(x[8 * c + 6] * inv, x[8 * c + 7] * inv));
+      fence_proxy_async_smem();
+      mbar_arrive_a(bar_a);
+    }
+    const uint32_t hrow = sH + row * 128;
+    const uint32_t hsw = static_cast<uint32_t>(row & 7) << 4;
+    for (int h = 0; h < NH; ++h) {
+      mbar_wait_a(bar_h, h & 1);
+      tc_fence_after();
+      if (h >= 1) {  // the single H tile is free once MMA2_{h-1} has completed
+        mbar_wait_a(bar_o, (h - 1) & 1);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_base + c4 * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {  // 4 chunks of 8 hidden units
+          const float4 ba = ld_shared_v4_f32(sB + 4 * (h * 128 + c4 * 32 + 8 * c));
+          const float4 bb = ld_shared_v4_f32(sB + 4 * (h * 128 + c4 * 32 + 8 * c + 4));
+          const float bq[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+          float g[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = gelu_tanh_fast(__uint_as_float(r[8 * c + i]) + bq[i]);
+          const int cc = c4 * 4 + c;  // 16-byte chunk index inside the 128-wide row: atom = cc >> 3
+          st_shared_v4(hrow + (cc >> 3) * 16384 + (((cc & 7) << 4) ^ hsw), pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
+                       pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive_a(bar_h2);
+    }
+    mbar_wait_a(bar_o, (NH - 1) & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int c4 = 0; c4 < C / 32; ++c4) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_base + 128 + c4 * 32, r);
+      tmem_ld_wait();
+      if (valid) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bq = ld_shared_v4_f32(sB + 4 * (4 * C + c4 * 32 + 4 * i));
+          v[4 * i] = __uint_as_float(r[4 * i]) + bq.x + x[c4 * 32 + 4 * i];
+          v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bq.y + x[c4 * 32 + 4 * i + 1];
+          v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bq.z + x[c4 * 32 + 4 * i + 2];
+          v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bq.w + x[c4 * 32 + 4 * i + 3];
+        }
+        store_act<float, 32>(X + m * C + c4 * 32, v);
+        if (xb_out) store_act<bf16, 32>(xb_out + m * C + c4 * 32, v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<256>(tmem_base);
+}
+
+struct TcFfPlan {
+  CUtensorMap tmW1, tmW2;
+  int C;
+  int64_t M;
+};
+
+TcFfPlan* tc_ff_plan_create(const void* w1_bf16, const void* w2_bf16, int C, int64_t M, char* err, int errlen) {
+  if (C != 32 && C != 64) { snprintf(err, errlen, "fused ff: C must be 32 or 64"); return nullptr; }
+  TcFfPlan* p = new TcFfPlan();
+  p->C = C; p->M = M;
+  {  // W1 [4C, C] row-major: box = {C, 128 rows}
+    const uint64_t dims[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(4 * C)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(C) * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(C), 128};
+    if (!make_tmap(&p->tmW1, w1_bf16, 2, dims, strides, box, C * 2 < 128 ? C * 2 : 128, err, errlen)) { delete p; return nullptr; }
+  }
+  {  // W2 [C, 4C] row-major: box = {64 K, C rows}
+    const uint64_t dims[2] = {static_cast<uint64_t>(4 * C), static_cast<uint64_t>(C)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(4 * C) * 2};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(C)};
+    if (!make_tmap(&p->tmW2, w2_bf16, 2, dims, strides, box, 128, err, errlen)) { delete p; return nullptr; }
+  }
+  return p;
+}
+void tc_ff_plan_destroy(TcFfPlan* p) { delete p; }
+
+int launch_fused_ff(const TcFfPlan* p, float* X, const float* b1, const float* b2, void* xb_out, cudaStream_t st) {
+  const unsigned grid = static_cast<unsigned>((p->M + 127) / 128);
+  bf16* xb = reinterpret_cast<bf16*>(xb_out);
+  if (p->C == 32)
+    fused_ff_kernel<32><<<grid, FF_THREADS, FfCfg<32>::SMEM, st>>>(p->tmW1, p->tmW2, X, b1, b2, xb, p->M);
+  else
+    fused_ff_kernel<64><<<grid, FF_THREADS, FfCfg<64>::SMEM, st>>>(p->tmW1, p->tmW2, X, b1, b2, xb, p->M);
+  return 0;
+}
+
 int tc_init(char* err, int errlen) {
   if (!g_encode) {
     void* fn = nullptr;
@@ -645,8 +879,10 @@ int tc_init(char* err, int errlen) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   cudaError_t r = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<32>::SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<64>::SMEM);
   if (r != cudaSuccess) {
-    snprintf(err, errlen, "cudaFuncSetAttribute(attn_tc_kernel) failed: %s", cudaGetErrorString(r));
+    snprintf(err, errlen, "cudaFuncSetAttribute(attn_tc_kernel / fused_ff_kernel) failed: %s", cudaGetErrorString(r));
     return -1;
   }
   return 0;
