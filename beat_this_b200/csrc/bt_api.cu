@@ -32,7 +32,7 @@ struct AttnW { const Param *wqkv, *wg, *bg, *wout; };
 struct FfW { const Param *w1, *b1, *w2, *b2; };
 
 // tensor-core plans for one (wave size, chunk length) geometry
-struct AttnPlans { TcGemmPlan *qkv = nullptr, *out = nullptr, *gates = nullptr; TcAttnPlan* attn = nullptr; };
+struct AttnPlans { TcGemmPlan *qkv = nullptr, *out = nullptr, *gates = nullptr; TcAttnPlan* attn = nullptr; TcQkvPlan* fqkv = nullptr; };
 struct FfPlans { TcGemmPlan *ff1 = nullptr, *ff2 = nullptr; TcFfPlan* fused = nullptr; };
 struct WavePlans {
   AttnPlans fa[3], ta[3];
@@ -232,6 +232,7 @@ void free_plans(bt_ctx* c) {
       if (a.qkv) tc_gemm_plan_destroy(a.qkv);
       if (a.out) tc_gemm_plan_destroy(a.out);
       if (a.gates) tc_gemm_plan_destroy(a.gates);
+      if (a.fqkv) tc_qkv_plan_destroy(a.fqkv);
       if (a.attn) tc_attn_plan_destroy(a.attn);
     };
     auto ff = [](FfPlans& f) {
@@ -337,31 +338,40 @@ int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool f
   const bool tc = c->dtype == BT_DTYPE_BF16;
   const int heads = C / kHeadDim;
   const int64_t M = static_cast<int64_t>(planes) * L;
-  const bool gates_in_norm = heads <= 4;  // frontend attentions: 1/2/4 heads
-  launch_norm(X, c->XN, M, C, tc, st, gates_in_norm ? c->GATES : nullptr, w.wg->f32, w.bg->f32, heads);
-  BT_LAUNCHED(c, gates_in_norm ? "norm_gates" : "norm", st);
-  if (!gates_in_norm) {  // gates = sigmoid(to_gates(x_normed)): a [heads -> 32 padded] x C GEMM on the same rows
-    GemmShape gg = plain_shape(planes, L, 32, C, C);
-    EpiParams eg{};
-    eg.kind = 2;
-    eg.bias = w.bg->f32;
-    eg.heads = heads;
-    eg.out_f32 = c->GATES;
-    int rg = run_gemm(c, c->XN, w.wg, tp ? tp->gates : nullptr, gg, eg, "gemm_gates", st);
-    if (rg != BT_OK) return rg;
-  }
   const float inv_sqrt_d = 0.17677669529663687f;  // 1/sqrt(32): SDPA default scale (roformer.py:78-80)
-  EpiParams e{};
-  e.kind = 1;
-  e.out_act = c->QKV; e.ldo_act = 3 * C;
-  e.rope_cos = find_param(c, "rope.cos")->f32;
-  e.rope_sin = find_param(c, "rope.sin")->f32;
-  e.C = C; e.heads = heads; e.posmode = freq ? 1 : 0; e.F = F;
   const bool tc_time = tc && !freq;
-  e.qscale = tc_time ? inv_sqrt_d * 1.4426950408889634f : 1.0f;
-  GemmShape g = plain_shape(planes, L, 3 * C, C, C);
-  int r = run_gemm(c, c->XN, w.wqkv, tp ? tp->qkv : nullptr, g, e, "gemm_qkv", st);
-  if (r != BT_OK) return r;
+  const float qscale = tc_time ? inv_sqrt_d * 1.4426950408889634f : 1.0f;
+  int r = BT_OK;
+  if (tc && tp && tp->fqkv) {  // narrow frontend attentions: norm + gates + QKV + RoPE in one kernel
+    if (launch_fused_qkv(tp->fqkv, X, w.wg->f32, w.bg->f32, find_param(c, "rope.cos")->f32, find_param(c, "rope.sin")->f32,
+                         c->QKV, c->GATES, L, F, freq ? 1 : 0, qscale, st) != 0)
+      return fail(c, BT_ERR_CUDA, "fused qkv launch failed");
+    BT_LAUNCHED(c, "qkv_fused", st);
+  } else {
+    const bool gates_in_norm = heads <= 4;  // 1/2/4 heads
+    launch_norm(X, c->XN, M, C, tc, st, gates_in_norm ? c->GATES : nullptr, w.wg->f32, w.bg->f32, heads);
+    BT_LAUNCHED(c, gates_in_norm ? "norm_gates" : "norm", st);
+    if (!gates_in_norm) {  // gates = sigmoid(to_gates(x_normed)): a [heads -> 32 padded] x C GEMM on the same rows
+      GemmShape gg = plain_shape(planes, L, 32, C, C);
+      EpiParams eg{};
+      eg.kind = 2;
+      eg.bias = w.bg->f32;
+      eg.heads = heads;
+      eg.out_f32 = c->GATES;
+      int rg = run_gemm(c, c->XN, w.wg, tp ? tp->gates : nullptr, gg, eg, "gemm_gates", st);
+      if (rg != BT_OK) return rg;
+    }
+    EpiParams e{};
+    e.kind = 1;
+    e.out_act = c->QKV; e.ldo_act = 3 * C;
+    e.rope_cos = find_param(c, "rope.cos")->f32;
+    e.rope_sin = find_param(c, "rope.sin")->f32;
+    e.C = C; e.heads = heads; e.posmode = freq ? 1 : 0; e.F = F;
+    e.qscale = qscale;
+    GemmShape g = plain_shape(planes, L, 3 * C, C, C);
+    r = run_gemm(c, c->XN, w.wqkv, tp ? tp->qkv : nullptr, g, e, "gemm_qkv", st);
+    if (r != BT_OK) return r;
+  }
   if (freq) {
     launch_attn_freq(c->QKV, c->GATES, c->O, nb, F, L, heads, inv_sqrt_d, tc, st);
     BT_LAUNCHED(c, "attn_freq", st);
@@ -437,6 +447,10 @@ int build_plans(bt_ctx* c, int nb, int L, WavePlans** out) {
     return tc_gemm_plan_create(A, W->b16, g, planes_in, err, sizeof(err));
   };
   auto mk_attn = [&](AttnPlans& a, const AttnW& aw, int planes, int C, bool freq) -> bool {
+    if (c->fuse_ff && (C == 32 || C == 64)) {
+      a.fqkv = tc_qkv_plan_create(aw.wqkv->b16, C, static_cast<int64_t>(planes) * L, err, sizeof(err));
+      if (!a.fqkv) return false;
+    }
     a.qkv = mk(c->XN, aw.wqkv, plain_shape(planes, L, 3 * C, C, C), planes);
     a.out = mk(c->O, aw.wout, plain_shape(planes, L, C, C, C), planes);
     a.gates = mk(c->XN, aw.wg, plain_shape(planes, L, 32, C, C), planes);

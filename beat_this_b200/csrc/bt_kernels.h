@@ -108,6 +108,14 @@ TcFfPlan* tc_ff_plan_create(const void* w1_bf16, const void* w2_bf16, int C, int
 void tc_ff_plan_destroy(TcFfPlan*);
 int launch_fused_ff(const TcFfPlan* plan, float* X, const float* b1, const float* b2, void* xb_out, cudaStream_t st);
 
+// fused RMSNorm + gates + QKV projection + RoPE for C in {32, 64} (frontend attentions)
+struct TcQkvPlan;
+TcQkvPlan* tc_qkv_plan_create(const void* wqkv_bf16, int C, int64_t M, char* err, int errlen);
+void tc_qkv_plan_destroy(TcQkvPlan*);
+int launch_fused_qkv(const TcQkvPlan* plan, const float* X, const float* wg, const float* bg, const float* rope_cos,
+                     const float* rope_sin, void* qkv, float* gates, int L, int F, int posmode, float qscale,
+                     cudaStream_t st);
+
 int tc_init(char* err, int errlen);  // resolves cuTensorMapEncodeTiled, sets smem attributes
 
 }  // namespace bt

@@ -864,6 +864,181 @@ int launch_fused_ff(const TcFfPlan* p, float* X, const float* b1, const float* b
   return 0;
 }
 
+// ================================================================ fused frontend QKV projection
+// RMSNorm -> gates -> to_qkv GEMM -> RoPE (+ q scaling) for the narrow frontend attentions (C = 32 /
+// 64) in one kernel (reference roformer.py:114-123,127-128): replaces norm_kernel + the QKV GEMM
+// (16 bytes/element through HBM) by 4 in + 6 out.  CTA = 128 tokens; warps 0-3 one token row per
+// thread, warp 4 lane 0 TMA (weights) + tcgen05.mma.  N = 3C fits one MMA and 128/256 TMEM columns.
+template <int C>
+struct QkvCfg {
+  static constexpr int A_BYTES = 128 * C * 2;
+  static constexpr int W_BYTES = 3 * C * C * 2;
+  static constexpr int SMEM = A_BYTES + W_BYTES + 1024 + 128;
+  static constexpr int TCOLS = 3 * C <= 128 ? 128 : 256;
+  static constexpr int SWZ = C * 2 < 128 ? C * 2 : 128;
+};
+
+template <int C>
+__global__ void __launch_bounds__(FF_THREADS, (C == 32 ? 3 : 2))
+fused_qkv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ X, const float* __restrict__ wg,
+                 const float* __restrict__ bg, const float* __restrict__ rope_cos, const float* __restrict__ rope_sin,
+                 bf16* __restrict__ qkv, float* __restrict__ gates, int64_t M, int L, int F, int posmode, float qscale) {
+  using Cfg = QkvCfg<C>;
+  constexpr int heads = C / 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = sbase;
+  const uint32_t sW = sA + Cfg::A_BYTES;
+  const uint32_t bar_w = sW + Cfg::W_BYTES;
+  const uint32_t bar_a = bar_w + 8;
+  const uint32_t bar_d = bar_a + 8;
+  const uint32_t tmem_slot = bar_d + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * 128;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmW);
+    auto init = [](uint32_t bar, uint32_t count) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    };
+    init(bar_w, 1); init(bar_a, 128); init(bar_d, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::TCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 3 * C);
+      mbar_expect_tx_a(bar_w, Cfg::W_BYTES);
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+          ::"r"(sW), "l"(reinterpret_cast<uint64_t>(&tmW)), "r"(bar_w), "r"(0), "r"(0) : "memory");
+      mbar_wait_a(bar_a, 0);
+      mbar_wait_a(bar_w, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < C / 16; ++k)
+        umma_bf16(tmem_base, make_kmajor_desc<Cfg::SWZ>(sA + k * 32), make_kmajor_desc<Cfg::SWZ>(sW + k * 32), idesc,
+                  k != 0 ? 1u : 0u);
+      umma_commit_a(bar_d);
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const int64_t m = m0 + row;
+    const bool valid = m < M;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    {
+      float x[C];
+      const float4* xr = reinterpret_cast<const float4*>(X + (valid ? m : 0) * C);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < C / 4; ++i) {
+        const float4 q = valid ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
+        ss = fmaf(q.x, q.x, ss); ss = fmaf(q.y, q.y, ss); ss = fmaf(q.z, q.z, ss); ss = fmaf(q.w, q.w, ss);
+      }
+      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+      for (int i = 0; i < C; ++i) x[i] *= inv;
+      // gates = sigmoid(to_gates(x_normed)) (gamma*sqrt(C) folded into wg)
+#pragma unroll
+      for (int h = 0; h < heads; ++h) {
+        const float4* w4 = reinterpret_cast<const float4*>(wg + h * C);
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < C / 4; ++i) {
+          const float4 w = __ldg(w4 + i);
+          a = fmaf(x[4 * i], w.x, a); a = fmaf(x[4 * i + 1], w.y, a); a = fmaf(x[4 * i + 2], w.z, a); a = fmaf(x[4 * i + 3], w.w, a);
+        }
+        if (valid) gates[m * heads + h] = sigmoidf_(a + __ldg(bg + h));
+      }
+      constexpr int RB = C * 2;
+      const uint32_t arow = sA + row * RB;
+      const uint32_t sw = C == 32 ? (static_cast<uint32_t>((row >> 1) & 3) << 4) : (static_cast<uint32_t>(row & 7) << 4);
+#pragma unroll
+      for (int c = 0; c < C / 8; ++c)
+        st_shared_v4(arow + ((c << 4) ^ sw), pack_bf16x2(x[8 * c], x[8 * c + 1]), pack_bf16x2(x[8 * c + 2], x[8 * c + 3]),
+                     pack_bf16x2(x[8 * c + 4], x[8 * c + 5]), pack_bf16x2(x[8 * c + 6], x[8 * c + 7]));
+      fence_proxy_async_smem();
+      mbar_arrive_a(bar_a);
+    }
+    // RoPE row of this token (interleaved pairs, rotary_embedding_torch semantics)
+    float cs[16], sn[16];
+    {
+      const int pos = valid ? (posmode == 0 ? static_cast<int>(m % L) : static_cast<int>((m / L) % F)) : 0;
+      const float4* c4 = reinterpret_cast<const float4*>(rope_cos + pos * 16);
+      const float4* s4 = reinterpret_cast<const float4*>(rope_sin + pos * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = __ldg(c4 + i), b = __ldg(s4 + i);
+        cs[4 * i] = a.x; cs[4 * i + 1] = a.y; cs[4 * i + 2] = a.z; cs[4 * i + 3] = a.w;
+        sn[4 * i] = b.x; sn[4 * i + 1] = b.y; sn[4 * i + 2] = b.z; sn[4 * i + 3] = b.w;
+      }
+    }
+    mbar_wait_a(bar_d, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 3 * C / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_base + c * 32, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      const int which = (c * 32) / C;  // 0 q, 1 k, 2 v (compile-time after unrolling)
+      if (which < 2) {
+        const float sc = which == 0 ? qscale : 1.0f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float x0 = v[2 * i], x1 = v[2 * i + 1];
+          v[2 * i] = (x0 * cs[i] - x1 * sn[i]) * sc;
+          v[2 * i + 1] = (x1 * cs[i] + x0 * sn[i]) * sc;
+        }
+      }
+      if (valid) store_act<bf16, 32>(qkv + m * (3 * C) + c * 32, v);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<Cfg::TCOLS>(tmem_base);
+}
+
+struct TcQkvPlan {
+  CUtensorMap tmW;
+  int C;
+  int64_t M;
+};
+TcQkvPlan* tc_qkv_plan_create(const void* wqkv_bf16, int C, int64_t M, char* err, int errlen) {
+  if (C != 32 && C != 64) { snprintf(err, errlen, "fused qkv: C must be 32 or 64"); return nullptr; }
+  TcQkvPlan* p = new TcQkvPlan();
+  p->C = C; p->M = M;
+  const uint64_t dims[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(3 * C)};
+  const uint64_t strides[1] = {static_cast<uint64_t>(C) * 2};
+  const uint32_t box[2] = {static_cast<uint32_t>(C), static_cast<uint32_t>(3 * C)};
+  if (!make_tmap(&p->tmW, wqkv_bf16, 2, dims, strides, box, C * 2 < 128 ? C * 2 : 128, err, errlen)) { delete p; return nullptr; }
+  return p;
+}
+void tc_qkv_plan_destroy(TcQkvPlan* p) { delete p; }
+int launch_fused_qkv(const TcQkvPlan* p, const float* X, const float* wg, const float* bg, const float* rope_cos,
+                     const float* rope_sin, void* qkv, float* gates, int L, int F, int posmode, float qscale,
+                     cudaStream_t st) {
+  const unsigned grid = static_cast<unsigned>((p->M + 127) / 128);
+  bf16* q = reinterpret_cast<bf16*>(qkv);
+  if (p->C == 32)
+    fused_qkv_kernel<32><<<grid, FF_THREADS, QkvCfg<32>::SMEM, st>>>(p->tmW, X, wg, bg, rope_cos, rope_sin, q, gates, p->M, L, F, posmode, qscale);
+  else
+    fused_qkv_kernel<64><<<grid, FF_THREADS, QkvCfg<64>::SMEM, st>>>(p->tmW, X, wg, bg, rope_cos, rope_sin, q, gates, p->M, L, F, posmode, qscale);
+  return 0;
+}
+
 int tc_init(char* err, int errlen) {
   if (!g_encode) {
     void* fn = nullptr;
@@ -881,6 +1056,8 @@ int tc_init(char* err, int errlen) {
   cudaError_t r = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
   if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<32>::SMEM);
   if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<64>::SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_qkv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, QkvCfg<32>::SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_qkv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, QkvCfg<64>::SMEM);
   if (r != cudaSuccess) {
     snprintf(err, errlen, "cudaFuncSetAttribute(attn_tc_kernel / fused_ff_kernel) failed: %s", cudaGetErrorString(r));
     return -1;
