@@ -65,11 +65,21 @@ struct TgCfg {
   static constexpr int SWZ = BK * 2;  // 128 or 64 byte rows
 };
 
-template <int BN, int BK>
+// MC (multicast): launched as clusters of 2 CTAs that work on two M tiles of the SAME N tile in
+// lock step; each CTA fetches one half of the W tile and TMA-multicasts it into both CTAs' shared
+// memory, which cuts the L2 -> SM operand traffic of a 128x256 tile from 48 to 32 KB per k-block
+// (the compute-bound GEMMs run into the L2 bandwidth otherwise).  Stage release is cluster-wide:
+// both CTAs' MMAs must have consumed a stage before either producer may overwrite it.
+template <int BN, int BK, bool MC>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const GemmShape g, const EpiParams e, int num_tiles, int t_tiles, int n_tiles) {
+               const GemmShape g, const EpiParams e, int num_tiles, int t_tiles, int n_tiles, int m_tiles) {
   using Cfg = TgCfg<BN, BK>;
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
+  // tile walk: non-MC: tile -> (mt, nt).  MC: pair-tile -> (pair, nt), this CTA takes mt = 2*pair + rank.
+  const int walk_start = MC ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int walk_step = MC ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  auto tile_mt = [&](int tile) { return MC ? 2 * (tile / n_tiles) + static_cast<int>(crank) : tile / n_tiles; };
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -94,13 +104,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmW);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], MC ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], BN <= 64 ? TG_EPI_WARPS / 2 : TG_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TCOLS>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();  // peer barriers initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -111,9 +122,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
-        const int p_out = mt / t_tiles;
+      for (int tile = walk_start; tile < num_tiles; tile += walk_step) {
+        const int mt = tile_mt(tile), nt = tile % n_tiles;
+        const int p_out = mt / t_tiles;  // beyond the last plane for the dummy half of an odd pair: TMA zero-fills
         const int t0 = (mt - p_out * t_tiles) * TG_BM;
         for (int kb = 0; kb < num_kb; ++kb) {
           const int s = kb / kb_per_slab;
@@ -122,7 +133,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
           tma_load_3d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], k0, t0 + g.t_shift[s],
                       p_out * g.plane_mul + g.plane_add[s]);
-          tma_load_2d(sW + stage * Cfg::W_BYTES, &tmW, &full[stage], s * g.Kslab + k0, nt * BN);
+          if constexpr (MC)  // my half of the W tile, delivered to both CTAs of the pair
+            tma_load_2d_mc(sW + stage * Cfg::W_BYTES + crank * (Cfg::W_BYTES / 2), &tmW, &full[stage], s * g.Kslab + k0,
+                           nt * BN + static_cast<int>(crank) * (BN / 2), 0x3);
+          else
+            tma_load_2d(sW + stage * Cfg::W_BYTES, &tmW, &full[stage], s * g.Kslab + k0, nt * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -134,7 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = walk_start; tile < num_tiles; tile += walk_step) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -148,7 +163,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_bf16(d_tmem, make_kmajor_desc<Cfg::SWZ>(a_base + k * 32),
                       make_kmajor_desc<Cfg::SWZ>(b_base + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          if constexpr (MC) umma_commit_mc(&empty[stage], 0x3);
+          else umma_commit(&empty[stage]);
           if (kb == num_kb - 1) umma_commit(&tfull[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -176,16 +192,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     int iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+    for (int tile = walk_start; tile < num_tiles; tile += walk_step, ++iter) {
       if (TILE_SPLIT && (iter & 1) != half) {
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
         continue;
       }
-      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      const int mt = tile_mt(tile), nt = tile % n_tiles;
       const int p_out = mt / t_tiles;
       const int t = (mt - p_out * t_tiles) * TG_BM + row;
-      const bool valid = t < g.L;
+      const bool valid = t < g.L && mt < m_tiles;
       const int64_t m = static_cast<int64_t>(p_out) * g.L + t;
       float ra[32], rb[32];
       const bool has_resid = e.kind == 0 && e.resid != nullptr && valid;
@@ -241,6 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's smem
   if (warp == 1) tmem_dealloc<Cfg::TCOLS>(tmem_base);
 }
 
@@ -248,7 +265,8 @@ struct TcGemmPlan {
   CUtensorMap tmA, tmW;
   GemmShape g;
   int BN, BK;
-  int num_tiles, t_tiles, n_tiles, grid;
+  int num_tiles, t_tiles, n_tiles, m_tiles, grid;
+  bool mc;
 };
 
 static int g_num_sms = 148;
@@ -260,18 +278,34 @@ static int pick_bn(int N) {
   return 0;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool MC>
 static int gemm_tc_launch(const TcGemmPlan* p, const EpiParams& e, cudaStream_t st) {
   using Cfg = TgCfg<BN, BK>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t r = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t r = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (r != cudaSuccess) return -1;
     attr_set = true;
   }
-  gemm_tc_kernel<BN, BK><<<p->grid, TG_THREADS, Cfg::SMEM, st>>>(p->tmA, p->tmW, p->g, e, p->num_tiles,
-                                                                   p->t_tiles, p->n_tiles);
-  return 0;
+  if constexpr (MC) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(p->grid);
+    cfg.blockDim = dim3(TG_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t r = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, BK, MC>, p->tmA, p->tmW, p->g, e, p->num_tiles, p->t_tiles,
+                                       p->n_tiles, p->m_tiles);
+    return r == cudaSuccess ? 0 : -1;
+  } else {
+    gemm_tc_kernel<BN, BK, MC><<<p->grid, TG_THREADS, Cfg::SMEM, st>>>(p->tmA, p->tmW, p->g, e, p->num_tiles, p->t_tiles,
+                                                                         p->n_tiles, p->m_tiles);
+    return 0;
+  }
 }
 
 TcGemmPlan* tc_gemm_plan_create(const void* A, const void* W, const GemmShape& g, int planes_in, char* err,
@@ -285,6 +319,9 @@ TcGemmPlan* tc_gemm_plan_create(const void* A, const void* W, const GemmShape& g
     delete p;
     return nullptr;
   }
+  static int mc_enabled = -1;
+  if (mc_enabled < 0) { const char* e = getenv("BT_GEMM_MULTICAST"); mc_enabled = !(e && e[0] == '0'); }
+  p->mc = mc_enabled && p->BN == 256 && p->BK == 64;
   const int swz = p->BK * 2;
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(g.Kslab), static_cast<uint64_t>(g.L),
@@ -297,20 +334,28 @@ TcGemmPlan* tc_gemm_plan_create(const void* A, const void* W, const GemmShape& g
     const uint64_t Ktot = static_cast<uint64_t>(g.Kslab) * g.nslab;
     const uint64_t dims[2] = {Ktot, static_cast<uint64_t>(g.N)};
     const uint64_t strides[1] = {Ktot * 2};
-    const uint32_t box[2] = {static_cast<uint32_t>(p->BK), static_cast<uint32_t>(p->BN)};
+    const uint32_t box[2] = {static_cast<uint32_t>(p->BK), static_cast<uint32_t>(p->mc ? p->BN / 2 : p->BN)};
     if (!make_tmap(&p->tmW, W, 2, dims, strides, box, swz, err, errlen)) { delete p; return nullptr; }
   }
   p->t_tiles = ceil_div(g.L, TG_BM);
   p->n_tiles = g.N / p->BN;
-  p->num_tiles = p->t_tiles * g.planes_out * p->n_tiles;
-  p->grid = p->num_tiles < g_num_sms ? p->num_tiles : g_num_sms;
+  p->m_tiles = p->t_tiles * g.planes_out;
+  if (p->mc) {
+    p->num_tiles = ceil_div(p->m_tiles, 2) * p->n_tiles;  // pair tiles
+    const int want = 2 * p->num_tiles;
+    p->grid = (want < g_num_sms ? want : g_num_sms) & ~1;
+  } else {
+    p->num_tiles = p->m_tiles * p->n_tiles;
+    p->grid = p->num_tiles < g_num_sms ? p->num_tiles : g_num_sms;
+  }
   return p;
 }
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 
 int launch_gemm_tc(const TcGemmPlan* p, const EpiParams& e, cudaStream_t st) {
 #define BT_TG_CASE(bn, bk) \
-  if (p->BN == bn && p->BK == bk) return gemm_tc_launch<bn, bk>(p, e, st);
+  if (p->BN == bn && p->BK == bk) return gemm_tc_launch<bn, bk, false>(p, e, st);
+  if (p->mc) return gemm_tc_launch<256, 64, true>(p, e, st);
   BT_TG_CASE(256, 64) BT_TG_CASE(192, 64) BT_TG_CASE(128, 64) BT_TG_CASE(96, 64) BT_TG_CASE(64, 64)
   BT_TG_CASE(32, 64) BT_TG_CASE(128, 32) BT_TG_CASE(96, 32) BT_TG_CASE(64, 32) BT_TG_CASE(32, 32)
 #undef BT_TG_CASE
