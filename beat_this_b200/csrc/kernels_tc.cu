@@ -319,8 +319,8 @@ TcGemmPlan* tc_gemm_plan_create(const void* A, const void* W, const GemmShape& g
     delete p;
     return nullptr;
   }
-  static int mc_enabled = -1;
-  if (mc_enabled < 0) { const char* e = getenv("BT_GEMM_MULTICAST"); mc_enabled = !(e && e[0] == '0'); }
+  static int mc_enabled = -1;  // measured: no gain (the 128x256 tiles are bound by SM-side smem bandwidth, not L2)
+  if (mc_enabled < 0) { const char* e = getenv("BT_GEMM_MULTICAST"); mc_enabled = (e && e[0] == '1'); }
   p->mc = mc_enabled && p->BN == 256 && p->BK == 64;
   const int swz = p->BK * 2;
   {
