@@ -261,12 +261,193 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc<Cfg::TCOLS>(tmem_base);
 }
 
+// ----------------------------------------------------------------------------- 2-SM GEMM
+// cta_group::2: a cluster of two CTAs (an SM pair) computes a 256 x 256 output tile with ONE stream
+// of tcgen05.mma instructions issued by the leader CTA.  Each CTA stages its own 128 rows of A and
+// one HALF (128 rows) of the W tile and keeps its own 128 x 256 accumulator in TMEM, so every SM
+// reads/receives 32 KB of operands per k-block instead of 48 KB -- the 1-SM kernel above is bound by
+// the 128 B/clk shared-memory port (96 B/clk of MMA operand reads + 96 B/clk of TMA fills).
+//   full[s]  : leader's barrier, 2 arrivals (one producer per CTA) + the bytes of both CTAs' TMA loads
+//   empty[s] : per CTA, released by the leader's tcgen05.commit multicast to both CTAs
+//   tfull[a] : per CTA, same multicast commit after the last k-block
+//   tempty[a]: leader's barrier, 16 arrivals (8 epilogue warps of each CTA)
+constexpr int T2_BN = 256, T2_BK = 64, T2_STAGES = 6;
+constexpr int T2_A_BYTES = 128 * T2_BK * 2, T2_W_BYTES = 128 * T2_BK * 2, T2_STAGE_BYTES = T2_A_BYTES + T2_W_BYTES;
+constexpr int T2_SMEM = T2_STAGES * T2_STAGE_BYTES + 1024 + 256 + 16384;
+
+__global__ void __launch_bounds__(TG_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmShape g,
+                const EpiParams e, int num_tiles, int t_tiles, int n_tiles, int m_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = sbase;
+  const uint32_t sW = sA + T2_STAGES * T2_A_BYTES;
+  const uint32_t full = sW + T2_STAGES * T2_W_BYTES;  // 8 bytes each
+  const uint32_t empty = full + 8 * T2_STAGES;
+  const uint32_t tfull = empty + 8 * T2_STAGES;
+  const uint32_t tempty = tfull + 16;
+  const uint32_t tmem_slot = tempty + 16;
+  const uint32_t sBias = full + 256;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const bool stage_bias = e.kind == 0 && e.bias != nullptr && g.N <= 4096;
+  if (stage_bias)
+    for (int i = threadIdx.x; i < g.N; i += TG_THREADS) st_shared_f32(sBias + 4 * i, __ldg(e.bias + i));
+  const uint32_t bias_smem = stage_bias ? sBias : 0u;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    auto init = [](uint32_t bar, uint32_t count) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    };
+    for (int i = 0; i < T2_STAGES; ++i) { init(full + 8 * i, 2); init(empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { init(tfull + 8 * i, 1); init(tempty + 8 * i, 2 * TG_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int kb_per_slab = g.Kslab / T2_BK;
+  const int num_kb = g.nslab * kb_per_slab;
+  const int walk_start = static_cast<int>(blockIdx.x >> 1), walk_step = static_cast<int>(gridDim.x >> 1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = walk_start; tile < num_tiles; tile += walk_step) {
+        const int mt = 2 * (tile / n_tiles) + static_cast<int>(crank), nt = tile % n_tiles;
+        const int p_out = mt / t_tiles;
+        const int t0 = (mt - p_out * t_tiles) * TG_BM;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int s = kb / kb_per_slab;
+          const int k0 = (kb - s * kb_per_slab) * T2_BK;
+          mbar_wait_a(empty + 8 * stage, phase ^ 1);
+          const uint32_t lead_full = mapa_cluster(full + 8 * stage, 0);
+          if (leader) mbar_expect_tx_a(full + 8 * stage, 2 * T2_STAGE_BYTES);
+          else mbar_arrive_cluster(lead_full);
+          tma_load_3d_2sm(sA + stage * T2_A_BYTES, &tmA, lead_full, k0, t0 + g.t_shift[s], p_out * g.plane_mul + g.plane_add[s]);
+          tma_load_2d_2sm(sW + stage * T2_W_BYTES, &tmW, lead_full, s * g.Kslab + k0, nt * T2_BN + static_cast<int>(crank) * 128);
+          if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, T2_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = walk_start; tile < num_tiles; tile += walk_step) {
+        mbar_wait_a(tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * T2_BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait_a(full + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t da = make_kmajor_desc<128>(sA + stage * T2_A_BYTES), db = make_kmajor_desc<128>(sW + stage * T2_W_BYTES);
+#pragma unroll
+          for (int k = 0; k < T2_BK / 16; ++k) umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(empty + 8 * stage, 0x3);
+          if (kb == num_kb - 1) umma_commit_2sm(tfull + 8 * acc, 0x3);
+          if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    constexpr int NCH = T2_BN / 32;
+    const int c_begin = half * (NCH / 2);
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = walk_start; tile < num_tiles; tile += walk_step) {
+      const int mt = 2 * (tile / n_tiles) + static_cast<int>(crank), nt = tile % n_tiles;
+      const int p_out = mt / t_tiles;
+      const int t = (mt - p_out * t_tiles) * TG_BM + row;
+      const bool valid = t < g.L && mt < m_tiles;
+      const int64_t m = static_cast<int64_t>(p_out) * g.L + t;
+      float ra[32], rb[32];
+      const bool has_resid = e.kind == 0 && e.resid != nullptr && valid;
+      const bool has_rope = e.kind == 1 && valid;
+      auto load_resid = [&](int c, float (&dst)[32]) {
+        const float4* r4 = reinterpret_cast<const float4*>(e.resid + m * e.ldr + nt * T2_BN + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 q = r4[i];
+          dst[4 * i] = q.x; dst[4 * i + 1] = q.y; dst[4 * i + 2] = q.z; dst[4 * i + 3] = q.w;
+        }
+      };
+      if (has_rope) {
+        const int pos = e.posmode == 0 ? t : static_cast<int>((m / g.L) % e.F);
+        const float4* c4 = reinterpret_cast<const float4*>(e.rope_cos + pos * 16);
+        const float4* s4 = reinterpret_cast<const float4*>(e.rope_sin + pos * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 a = __ldg(c4 + i), b = __ldg(s4 + i);
+          ra[4 * i] = a.x; ra[4 * i + 1] = a.y; ra[4 * i + 2] = a.z; ra[4 * i + 3] = a.w;
+          ra[16 + 4 * i] = b.x; ra[16 + 4 * i + 1] = b.y; ra[16 + 4 * i + 2] = b.z; ra[16 + 4 * i + 3] = b.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rb[i] = ra[i];
+      }
+      if (has_resid) load_resid(c_begin, ra);
+      mbar_wait_a(tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < NCH / 2; ++k) {
+        const int c = c_begin + k;
+        float (&cur)[32] = (k & 1) ? rb : ra;
+        float (&nxt)[32] = (k & 1) ? ra : rb;
+        if (has_resid && k + 1 < NCH / 2) load_resid(c + 1, nxt);
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * T2_BN + c * 32, r);
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          epilogue_apply<bf16, 32>(e, g.L, m, nt * T2_BN + c * 32, v, cur, has_rope || has_resid, bias_smem);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive_a(tempty + 8 * acc);
+        else mbar_arrive_cluster(mapa_cluster(tempty + 8 * acc, 0));
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2sm<512>(tmem_base);
+}
+
 struct TcGemmPlan {
   CUtensorMap tmA, tmW;
   GemmShape g;
   int BN, BK;
   int num_tiles, t_tiles, n_tiles, m_tiles, grid;
-  bool mc;
+  bool mc;      // 2-CTA cluster, W tile multicast, cta_group::1 MMAs
+  bool two_sm;  // 2-CTA cluster, cta_group::2 MMAs (256 x 256 tile per pair)
 };
 
 static int g_num_sms = 148;
@@ -321,7 +502,10 @@ TcGemmPlan* tc_gemm_plan_create(const void* A, const void* W, const GemmShape& g
   }
   static int mc_enabled = -1;  // measured: no gain (the 128x256 tiles are bound by SM-side smem bandwidth, not L2)
   if (mc_enabled < 0) { const char* e = getenv("BT_GEMM_MULTICAST"); mc_enabled = (e && e[0] == '1'); }
-  p->mc = mc_enabled && p->BN == 256 && p->BK == 64;
+  static int two_sm_enabled = -1;
+  if (two_sm_enabled < 0) { const char* e2 = getenv("BT_GEMM_2SM"); two_sm_enabled = !(e2 && e2[0] == '0'); }
+  p->two_sm = two_sm_enabled && p->BN == 256 && p->BK == 64;
+  p->mc = !p->two_sm && mc_enabled && p->BN == 256 && p->BK == 64;
   const int swz = p->BK * 2;
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(g.Kslab), static_cast<uint64_t>(g.L),
@@ -334,13 +518,13 @@ TcGemmPlan* tc_gemm_plan_create(const void* A, const void* W, const GemmShape& g
     const uint64_t Ktot = static_cast<uint64_t>(g.Kslab) * g.nslab;
     const uint64_t dims[2] = {Ktot, static_cast<uint64_t>(g.N)};
     const uint64_t strides[1] = {Ktot * 2};
-    const uint32_t box[2] = {static_cast<uint32_t>(p->BK), static_cast<uint32_t>(p->mc ? p->BN / 2 : p->BN)};
+    const uint32_t box[2] = {static_cast<uint32_t>(p->BK), static_cast<uint32_t>((p->mc || p->two_sm) ? p->BN / 2 : p->BN)};
     if (!make_tmap(&p->tmW, W, 2, dims, strides, box, swz, err, errlen)) { delete p; return nullptr; }
   }
   p->t_tiles = ceil_div(g.L, TG_BM);
   p->n_tiles = g.N / p->BN;
   p->m_tiles = p->t_tiles * g.planes_out;
-  if (p->mc) {
+  if (p->mc || p->two_sm) {
     p->num_tiles = ceil_div(p->m_tiles, 2) * p->n_tiles;  // pair tiles
     const int want = 2 * p->num_tiles;
     p->grid = (want < g_num_sms ? want : g_num_sms) & ~1;
@@ -355,6 +539,25 @@ void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 int launch_gemm_tc(const TcGemmPlan* p, const EpiParams& e, cudaStream_t st) {
 #define BT_TG_CASE(bn, bk) \
   if (p->BN == bn && p->BK == bk) return gemm_tc_launch<bn, bk, false>(p, e, st);
+  if (p->two_sm) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM) != cudaSuccess) return -1;
+      attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(p->grid);
+    cfg.blockDim = dim3(TG_THREADS);
+    cfg.dynamicSmemBytes = T2_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel, p->tmA, p->tmW, p->g, e, p->num_tiles, p->t_tiles, p->n_tiles,
+                              p->m_tiles) == cudaSuccess ? 0 : -1;
+  }
   if (p->mc) return gemm_tc_launch<256, 64, true>(p, e, st);
   BT_TG_CASE(256, 64) BT_TG_CASE(192, 64) BT_TG_CASE(128, 64) BT_TG_CASE(96, 64) BT_TG_CASE(64, 64)
   BT_TG_CASE(32, 64) BT_TG_CASE(128, 32) BT_TG_CASE(96, 32) BT_TG_CASE(64, 32) BT_TG_CASE(32, 32)
