@@ -503,7 +503,8 @@ TcGemmPlan* tc_gemm_plan_create(const void* A, const void* W, const GemmShape& g
   static int mc_enabled = -1;  // measured: no gain (the 128x256 tiles are bound by SM-side smem bandwidth, not L2)
   if (mc_enabled < 0) { const char* e = getenv("BT_GEMM_MULTICAST"); mc_enabled = (e && e[0] == '1'); }
   static int two_sm_enabled = -1;
-  if (two_sm_enabled < 0) { const char* e2 = getenv("BT_GEMM_2SM"); two_sm_enabled = !(e2 && e2[0] == '0'); }
+  // measured 40 % SLOWER than the 1-SM kernel on the K = 512 / 2048 layer GEMMs (profiles/r1_notes.md): opt-in
+  if (two_sm_enabled < 0) { const char* e2 = getenv("BT_GEMM_2SM"); two_sm_enabled = (e2 && e2[0] == '1'); }
   p->two_sm = two_sm_enabled && p->BN == 256 && p->BK == 64;
   p->mc = !p->two_sm && mc_enabled && p->BN == 256 && p->BK == 64;
   const int swz = p->BK * 2;
