@@ -847,7 +847,10 @@ int bt_logmel(bt_ctx* c, const float* audio_dev, const int64_t* sample_offsets_h
   const int64_t f0 = frame_offsets_host[0];
   const int64_t total = frame_offsets_host[n_clips] - f0;
   if (f0 != 0) return fail(c, BT_ERR_ARG, "bt_logmel: frame_offsets_host[0] must be 0");
-  launch_logmel(audio_dev, d, d + n_clips + 1, n_clips, total, find_param(c, "mel.window")->f32,
+  int64_t max_frames = 0;
+  for (int i = 0; i < n_clips; ++i) max_frames = std::max(max_frames, frame_offsets_host[i + 1] - frame_offsets_host[i]);
+  (void)total;
+  launch_logmel(audio_dev, d, d + n_clips + 1, n_clips, max_frames, find_param(c, "mel.window")->f32,
                 find_param(c, "mel.twiddle")->f32, find_param(c, "mel.fb_start")->i32,
                 find_param(c, "mel.fb_ptr")->i32, find_param(c, "mel.fb_w")->f32, spect_dev, st);
   BT_LAUNCHED(c, "logmel", st);

@@ -77,7 +77,7 @@ void launch_stem(const float* spect, const ChunkSrc* chunks, int nchunks, int L,
 void launch_head(const float* x, int D, const float* w, const float* b, const ChunkSrc* chunks,
                  int nchunks, int L, float* beat, float* down, cudaStream_t st);
 void launch_logmel(const float* audio, const int64_t* sample_off_dev, const int64_t* frame_off_dev,
-                   int n_clips, int64_t total_frames, const float* window, const float* twiddle,
+                   int n_clips, int64_t max_frames, const float* window, const float* twiddle,
                    const int32_t* fb_start, const int32_t* fb_ptr, const float* fb_w, float* spect,
                    cudaStream_t st);
 void launch_peakpick(const float* beat, const float* down, const int64_t* frame_off_dev, int n_clips,

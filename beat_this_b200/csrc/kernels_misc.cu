@@ -11,40 +11,50 @@ namespace bt {
 // log-mel: reference LogMelSpect.forward (beat_this/preprocessing.py:56-59) =
 //   torch.stft(n_fft 1024, hop 441, periodic hann, center reflect, normalized) -> abs ->
 //   mel filterbank (slaney, 128 bins, 30..11000 Hz) -> log1p(1000 x).
-// One CTA (128 threads) per frame: windowed frame -> 1024-point radix-2 FFT in shared
-// memory -> |X|/32 -> sparse triangular filterbank -> log1p.  Algorithmic HBM bytes:
+// One CTA (128 threads) per PAIR of frames: windowed frames -> one 1024-point radix-2 FFT in
+// shared memory -> |X|/32 -> sparse triangular filterbank -> log1p.  Algorithmic HBM bytes:
 // 441 new samples * 4 B read + 128 * 4 B written per frame.
 // ------------------------------------------------------------------------------------------
+// Two frames per CTA: frames 2j and 2j+1 of a clip are packed as the real and imaginary part of ONE
+// complex 1024-point FFT (z = x_a + i x_b) and separated afterwards
+//   X_a[k] = (Z[k] + conj(Z[N-k])) / 2,   X_b[k] = (Z[k] - conj(Z[N-k])) / (2i),
+// which halves the butterfly work per frame.  grid = (ceil(max_frames/2), n_clips): no clip search.
 __global__ void __launch_bounds__(128)
 logmel_kernel(const float* __restrict__ audio, const int64_t* __restrict__ sample_off,
-              const int64_t* __restrict__ frame_off, int n_clips, const float* __restrict__ window,
+              const int64_t* __restrict__ frame_off, const float* __restrict__ window,
               const float2* __restrict__ twiddle, const int32_t* __restrict__ fb_start,
               const int32_t* __restrict__ fb_ptr, const float* __restrict__ fb_w,
               float* __restrict__ spect) {
   __shared__ float re[1024];
   __shared__ float im[1024];
   __shared__ float2 tw[512];
-  const int64_t frame = blockIdx.x;
-  // locate the clip (frame_off is ascending, n_clips+1 entries)
-  int lo = 0, hi = n_clips;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (frame_off[mid] <= frame) lo = mid; else hi = mid;
-  }
-  const int clip = lo;
-  const int64_t t = frame - frame_off[clip];
+  __shared__ float ma[516];
+  __shared__ float mb[516];
+  const int clip = blockIdx.y;
+  const int64_t f0 = frame_off[clip];
+  const int T = static_cast<int>(frame_off[clip + 1] - f0);
+  const int ta = 2 * blockIdx.x, tb = ta + 1;
+  if (ta >= T) return;
+  const bool has_b = tb < T;
   const int64_t s0 = sample_off[clip];
   const int64_t len = sample_off[clip + 1] - s0;
   const int tid = threadIdx.x;
   for (int i = tid; i < 512; i += 128) tw[i] = twiddle[i];
   for (int n = tid; n < 1024; n += 128) {
-    int64_t i = 441 * t + n - 512;
-    if (i < 0) i = -i;                       // reflect (no edge repeat), torch pad_mode="reflect"
-    if (i >= len) i = 2 * (len - 1) - i;
-    const float v = audio[s0 + i] * window[n];
+    const float w = window[n];
+    int64_t ia = 441ll * ta + n - 512;
+    if (ia < 0) ia = -ia;                      // reflect (no edge repeat), torch pad_mode="reflect"
+    if (ia >= len) ia = 2 * (len - 1) - ia;
+    float vb = 0.f;
+    if (has_b) {
+      int64_t ib = 441ll * tb + n - 512;
+      if (ib < 0) ib = -ib;
+      if (ib >= len) ib = 2 * (len - 1) - ib;
+      vb = audio[s0 + ib] * w;
+    }
     const int r = __brev(static_cast<unsigned>(n)) >> 22;  // 10-bit reversal
-    re[r] = v;
-    im[r] = 0.f;
+    re[r] = audio[s0 + ia] * w;
+    im[r] = vb;
   }
   __syncthreads();
   // decimation-in-time butterflies; stage s has half-span h = 2^s, twiddle index (j * 512/h)
@@ -67,40 +77,40 @@ logmel_kernel(const float* __restrict__ audio, const int64_t* __restrict__ sampl
     }
     __syncthreads();
   }
-  // magnitudes of bins 0..512 (normalized=True -> 1/sqrt(1024)); reuse re[] (im[512] for the Nyquist bin)
-  float mags[4];
-#pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    const int k = tid + b * 128;
-    mags[b] = sqrtf(re[k] * re[k] + im[k] * im[k]) * 0.03125f;
+  // split the packed spectrum, magnitudes of bins 0..512 (normalized=True -> 1/sqrt(1024))
+  for (int k = tid; k <= 512; k += 128) {
+    const int nk = (1024 - k) & 1023;
+    const float zr = re[k], zi = im[k], yr = re[nk], yi = im[nk];
+    const float ar = 0.5f * (zr + yr), ai = 0.5f * (zi - yi);   // X_a[k]
+    const float br = 0.5f * (zi + yi), bi = 0.5f * (yr - zr);   // X_b[k]
+    ma[k] = sqrtf(ar * ar + ai * ai) * 0.03125f;
+    mb[k] = sqrtf(br * br + bi * bi) * 0.03125f;
   }
-  const float nyq = sqrtf(re[512] * re[512] + im[512] * im[512]) * 0.03125f;
-  __syncthreads();
-#pragma unroll
-  for (int b = 0; b < 4; ++b) re[tid + b * 128] = mags[b];
-  if (tid == 0) im[0] = nyq;  // bin 512 (never inside the 30..11000 Hz filters, kept for safety)
   __syncthreads();
   {
     const int m = tid;  // mel bin
     const int p0 = fb_ptr[m], p1 = fb_ptr[m + 1];
     const int k0 = fb_start[m];
-    float acc = 0.f;
+    float acc_a = 0.f, acc_b = 0.f;
     for (int p = p0; p < p1; ++p) {
       const int k = k0 + (p - p0);
-      acc = fmaf(k < 512 ? re[k] : im[0], fb_w[p], acc);
+      const float w = fb_w[p];
+      acc_a = fmaf(ma[k], w, acc_a);
+      acc_b = fmaf(mb[k], w, acc_b);
     }
-    spect[frame * 128 + m] = log1pf(1000.0f * acc);
+    spect[(f0 + ta) * 128 + m] = log1pf(1000.0f * acc_a);
+    if (has_b) spect[(f0 + tb) * 128 + m] = log1pf(1000.0f * acc_b);
   }
 }
 
 void launch_logmel(const float* audio, const int64_t* sample_off_dev, const int64_t* frame_off_dev,
-                   int n_clips, int64_t total_frames, const float* window, const float* twiddle,
+                   int n_clips, int64_t max_frames, const float* window, const float* twiddle,
                    const int32_t* fb_start, const int32_t* fb_ptr, const float* fb_w, float* spect,
                    cudaStream_t st) {
-  if (total_frames <= 0) return;
-  logmel_kernel<<<static_cast<unsigned>(total_frames), 128, 0, st>>>(
-      audio, sample_off_dev, frame_off_dev, n_clips, window,
-      reinterpret_cast<const float2*>(twiddle), fb_start, fb_ptr, fb_w, spect);
+  if (max_frames <= 0 || n_clips <= 0) return;
+  dim3 grid(static_cast<unsigned>((max_frames + 1) / 2), static_cast<unsigned>(n_clips));
+  logmel_kernel<<<grid, 128, 0, st>>>(audio, sample_off_dev, frame_off_dev, window,
+                                      reinterpret_cast<const float2*>(twiddle), fb_start, fb_ptr, fb_w, spect);
 }
 
 // ------------------------------------------------------------------------------------------
