@@ -567,33 +567,43 @@ int launch_gemm_tc(const TcGemmPlan* p, const EpiParams& e, cudaStream_t st) {
 }
 
 // ========================================================================== attention
-// One CTA per (sequence, head, 128-query tile).  Warps 0-3: softmax (one query row per
-// thread, the tcgen05.ld 32x32b lane mapping); warp 4 lane 0: TMA producer + MMA issuer.
-//   S = Q K^T      : A = Q  [128 x 32] bf16 (K-major, SW64), B = K tile [128 keys x 32] bf16 (K-major,
-//                    SW64) -> TMEM cols [0,128)
-//   O_j = P_j V_j  : A = P  [128 x 128] bf16 written by the softmax threads in the SW128 K-major
-//                    layout, B = V tile [128 keys x 32] bf16 exactly as the QKV GEMM stored it
-//                    (MN-major operand, SW64) -> TMEM cols 128 + 32*(j%2)
-// The running output lives in registers (o = o*alpha + O_j), so TMEM is never read-modify-
-// written.  q is pre-scaled by log2(e)/sqrt(32) in the QKV GEMM epilogue -> exp2 softmax.
+// One CTA per (sequence, head, 128-query tile), 2 CTAs/SM.  Warps 0-7: softmax, two threads per
+// query row (warps w and w+4 share TMEM lane quarter w%4; keys [0,64) / [64,128) of each tile);
+// warp 8 lane 0: TMA producer + MMA issuer.  TMEM (256 columns): S [0,128) | O [128,192) | P [192,256).
+//   S_j = Q K_j^T  : A = Q  [128 x 32] bf16 (K-major, SW64), B = K tile [128 keys x 32] (K-major, SW64)
+//   O  += P_j [V_j | 1] : A = P_j [128 x 128] bf16 **in tensor memory** (written by the softmax
+//                    threads with tcgen05.st, two keys per 32-bit column), B = V tile exactly as the
+//                    QKV GEMM stored it (MN-major operand, SW64) + a constant ones block ->
+//                    TMEM cols [128,160) = O, col 160 = row sum of P
+// Shared memory only carries Q/K/V: the probabilities never touch it.  (Measured by ablation on the
+// previous design, profiles/r1_notes.md: the 32 KB/tile of st.shared for P plus the MMA reading it
+// back cost 20-30 % of the kernel -- the shared-memory pipe, not MUFU or the tensor pipe, was the
+// contended resource.)
+// The output accumulates in TMEM over all key tiles (tensor-core accumulate) with FlashAttention-4
+// style lazy rescaling: P_j = exp2(S_j - m_ref) with a per-row reference that is only raised -- and O
+// rescaled through tcgen05.ld/st -- when the tile maximum exceeds it by more than AT_TAU (P <= 2^AT_TAU
+// stays far inside bf16/fp32 range; numerator and row sum share the same scaling).
+// q is pre-scaled by log2(e)/sqrt(32) in the QKV epilogue -> exp2 softmax.
 // (ex2.approx.f16x2 -- two exponentials per MUFU op -- was measured: 28% SLOWER than fp32
 // ex2 + bf16 pack on B200, profiles/r1_notes.md.)
 constexpr int AT_BQ = 128, AT_BKV = 128;
 constexpr int AT_SOFTMAX_WARPS = 8;                      // two threads per query row (64 keys each)
 constexpr int AT_THREADS = 32 * (AT_SOFTMAX_WARPS + 1);  // + 1 TMA/MMA warp
-constexpr int AT_SQ = 8192, AT_SK = 8192, AT_SV = 8192, AT_SONES = 8192, AT_SP = 32768, AT_SMAX = 2048;
-constexpr int AT_SMEM = AT_SQ + 2 * AT_SK + 2 * AT_SV + AT_SONES + AT_SP + AT_SMAX + 1024 + 128;
+constexpr int AT_SQ = 8192, AT_SK = 8192, AT_SV = 8192, AT_SONES = 8192, AT_SMAX = 2048;
+constexpr int AT_SMEM = AT_SQ + 2 * AT_SK + 2 * AT_SV + AT_SONES + AT_SMAX + 1024 + 128;
 constexpr int AT_POLY_MOD = 4;  // every AT_POLY_MOD-th exponential runs on the FMA pipe instead of MUFU
+constexpr float AT_TAU = 8.0f;  // log2 units: rescale O only when the row maximum grew by more than this
+constexpr uint32_t AT_TM_O = 128, AT_TM_L = 160, AT_TM_P = 192;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x for x <= 0 on the FMA/ALU pipes (Cody-Waite split + degree-3 polynomial, rel. error
-// 8e-5, far below the bf16 rounding of P).  The MUFU pipe (16 ex2/clk/SM) is the bottleneck
+// 2^x for x <= AT_TAU on the FMA/ALU pipes (Cody-Waite split + degree-3 polynomial, rel. error
+// 8e-5, far below the bf16 rounding of P).  The MUFU pipe (16 ex2/clk/SM) is one bottleneck
 // of head_dim-32 attention -- 128 tensor FLOPs per exponential -- so a fixed fraction of the
-// exponentials is moved to the otherwise idle FMA pipe (the FlashAttention-4 trick).
+// exponentials is moved to the FMA pipe (the FlashAttention-4 trick).
 __device__ __forceinline__ float ex2_poly(float x) {
   x = fmaxf(x, -120.0f);
   const float t = x + 12582912.0f;        // 1.5 * 2^23: round(x) lands in the low mantissa bits
@@ -617,6 +627,29 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32b_x1(uint32_t taddr, uint32_t r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: A is read from tensor memory (lane = row, one 32-bit column
+// per two K elements), kind::f16 with bf16 operands.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -634,18 +667,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
   // everything below works on 32-bit shared-space addresses computed once
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = sbase;
-  const uint32_t sK = sQ + AT_SQ;
-  const uint32_t sV = sK + 2 * AT_SK;
+  const uint32_t sK = sQ + AT_SQ;         // [2]
+  const uint32_t sV = sK + 2 * AT_SK;     // [2]
   const uint32_t sOnes = sV + 2 * AT_SV;  // [128 keys][32 cols] bf16, col 0 = 1: second N block of the PV MMA -> row sums of P
-  const uint32_t sP = sOnes + AT_SONES;
-  const uint32_t sMax = sP + AT_SP;       // [2 parity][2 halves][128 rows] fp32 partial row maxima
+  const uint32_t sMax = sOnes + AT_SONES; // [2 parity][2 halves][128 rows] fp32 partial row maxima
   const uint32_t bar_q = sMax + AT_SMAX;
   const uint32_t bar_kv = bar_q + 8;      // [2]
   const uint32_t bar_s = bar_kv + 16;
   const uint32_t bar_sfree = bar_s + 8;   // S_j has been copied to registers: S_{j+1} may overwrite it
-  const uint32_t bar_p = bar_sfree + 8;
-  const uint32_t bar_o = bar_p + 8;       // [2]
-  const uint32_t tmem_slot = bar_o + 16;
+  const uint32_t bar_p = bar_sfree + 8;   // P_j sits in TMEM (and O was rescaled if the maximum jumped)
+  const uint32_t bar_pv = bar_p + 8;      // [2] PV_j complete: P and K/V stage j&1 free, O holds tiles 0..j
+  const uint32_t tmem_slot = bar_pv + 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ;
@@ -666,7 +698,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
     init(bar_s, 1);
     init(bar_sfree, NSOFT);
     init(bar_p, NSOFT);
-    init(bar_o, 1); init(bar_o + 8, 1);
+    init(bar_pv, 1); init(bar_pv + 8, 1);
     fence_barrier_init();
   }
   if (warp == MMA_WARP) {
@@ -690,10 +722,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
         tma_load_3d_a(sV + st * AT_SV, &tmQK, bar_kv + 8 * st, 2 * C + h * 32, j * AT_BKV, seq);
       };
       auto issue_s = [&](int j) {
-        const uint32_t b = sK + (j & 1) * AT_SK;
+        const uint32_t kb = sK + (j & 1) * AT_SK;
 #pragma unroll
         for (int k = 0; k < 2; ++k)
-          umma_bf16(tmem_base, make_kmajor_desc<64>(sQ + k * 32), make_kmajor_desc<64>(b + k * 32), idesc_s,
+          umma_bf16(tmem_base, make_kmajor_desc<64>(sQ + k * 32), make_kmajor_desc<64>(kb + k * 32), idesc_s,
                     k != 0 ? 1u : 0u);
         umma_commit_a(bar_s);
       };
@@ -708,32 +740,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
       for (int j = 0; j < nkv; ++j) {
         const int st = j & 1;
         if (j + 1 < nkv) {  // S_{j+1} is computed while the softmax warps work on S_j
-          mbar_wait_a(bar_sfree, j & 1);
+          mbar_wait_a(bar_sfree, j & 1);  // S_j copied to registers by every softmax thread
           mbar_wait_a(bar_kv + 8 * ((j + 1) & 1), ((j + 1) >> 1) & 1);
           tc_fence_after();
           issue_s(j + 1);
         }
-        mbar_wait_a(bar_p, j & 1);  // P_j written
+        mbar_wait_a(bar_p, j & 1);  // P_j written to TMEM (and O rescaled if the maximum jumped)
         tc_fence_after();
         const uint32_t vb = sV + st * AT_SV;
         const uint32_t lbo = sOnes - vb;
-        const uint32_t d_o = tmem_base + 128 + st * 64;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t aoff = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_bf16(d_o, make_kmajor_desc<128>(sP + aoff), make_mnmajor_desc_sw64(vb + k * 1024, lbo), idesc_o,
-                    k != 0 ? 1u : 0u);
-        }
-        umma_commit_a(bar_o + 8 * st);
+        for (int k = 0; k < 8; ++k)  // 16 keys = 8 TMEM columns of P per MMA
+          umma_bf16_ts(tmem_base + AT_TM_O, tmem_base + AT_TM_P + k * 8, make_mnmajor_desc_sw64(vb + k * 1024, lbo),
+                       idesc_o, (j != 0 || k != 0) ? 1u : 0u);
+        umma_commit_a(bar_pv + 8 * st);
         if (j + 2 < nkv) {
-          mbar_wait_a(bar_o + 8 * st, (j >> 1) & 1);  // PV_j done -> K/V stage reusable
+          mbar_wait_a(bar_pv + 8 * st, (j >> 1) & 1);  // PV_j done -> K/V stage reusable
           load_kv(j + 2);
         }
       }
     }
   } else {
-    // 8 softmax warps: warps w and w+4 share TMEM lane quarter w%4 (the only lanes either may
-    // touch) and split each query row: keys [0,64) go to warp w, keys [64,128) to warp w+4.
     const int quarter = warp & 3;
     const int hc = warp >> 2;  // which half of the keys / of the output columns
     const int row = quarter * 32 + lane;
@@ -745,15 +772,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
         const bool one = i == ((row >> 1) & 3);
         st_shared_v4(orow + 16 * i, one ? 0x3F80u : 0u, 0u, 0u, 0u);
       }
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the MMA (async proxy) after bar_p
     }
-    float o[16];  // output columns [16*hc, 16*hc + 16) of this row
-#pragma unroll
-    for (int d = 0; d < 16; ++d) o[d] = 0.f;
-    float m_run = -INFINITY, m_ref = -INFINITY, l = 0.f;
-    const uint32_t prow = sP + hc * 16384 + row * 128;
-    const uint32_t sw = static_cast<uint32_t>(row & 7) << 4;
+    float m_ref = -INFINITY;
     const uint32_t s_tmem = tmem_base + lane_base + hc * 64;
-    const uint32_t o_tmem = tmem_base + lane_base + 128 + hc * 16;
+    const uint32_t o_tmem = tmem_base + lane_base + AT_TM_O + hc * 16;  // this thread's 16 output columns
+    const uint32_t l_tmem = tmem_base + lane_base + AT_TM_L;            // row sum of P (ones block column)
+    const uint32_t p_tmem = tmem_base + lane_base + AT_TM_P + hc * 32;  // this thread's 64 keys = 32 columns
     const uint32_t my_max = sMax + (hc * 128 + row) * 4, other_max = sMax + ((hc ^ 1) * 128 + row) * 4;
     for (int j = 0; j < nkv; ++j) {
       mbar_wait_a(bar_s, j & 1);
@@ -791,64 +816,69 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
         named_bar_sync(1 + quarter, 64);
         mx = fmaxf(mx, ld_shared_f32(other_max + par));
       }
-      const float m_prev = m_run;
-      const float m_new = fmaxf(m_run, mx);
-      m_run = m_new;
-      if (j >= 1) {  // PV_{j-1} complete: the P buffer is free again and O_{j-1} (+ its row sums) is ready
-        mbar_wait_a(bar_o + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
-        tc_fence_after();
-      }
+      // lazy rescale: identical decision in both threads of a row (same m_ref, same mx)
+      const bool need = mx > m_ref + AT_TAU;  // always true for j == 0 (m_ref = -inf)
+      const bool any_need = __any_sync(0xffffffffu, need);
+      const float a_corr = (need && j > 0) ? ex2_approx(m_ref - mx) : 1.0f;
+      if (need) m_ref = mx;
+      uint32_t pk[32];  // P_j of this thread: 64 keys, two per register
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys (16 bytes of bf16)
+      for (int c = 0; c < 8; ++c) {
         float p[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float x = s[c * 8 + i] - m_new;
+          const float x = s[c * 8 + i] - m_ref;
           p[i] = (i % AT_POLY_MOD == AT_POLY_MOD - 1) ? ex2_poly(x) : ex2_approx(x);
         }
-        st_shared_v4(prow + ((c << 4) ^ sw), pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]),
-                     pack_bf16x2(p[6], p[7]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pk[c * 4 + i] = pack_bf16x2(p[2 * i], p[2 * i + 1]);
       }
-      fence_proxy_async_smem();
+      if (j >= 1) {  // PV_{j-1} complete: P may be overwritten, O holds tiles 0..j-1
+        mbar_wait_a(bar_pv + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        if (any_need) {  // warp-uniform; rare after the first tiles
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(o_tmem, r);
+          uint32_t rs = 0;
+          if (hc == 0) rs = tmem_ld_32x32b_x1(l_tmem);
+          tmem_ld_wait();
+#pragma unroll
+          for (int d = 0; d < 16; ++d) r[d] = __float_as_uint(__uint_as_float(r[d]) * a_corr);
+          tmem_st_32x32b_x16(o_tmem, r);
+          if (hc == 0) tmem_st_32x32b_x1(l_tmem, __float_as_uint(__uint_as_float(rs) * a_corr));
+        }
+      }
+      {
+        uint32_t (&lo)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[0]);
+        uint32_t (&hi)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[16]);
+        tmem_st_32x32b_x16(p_tmem, lo);
+        tmem_st_32x32b_x16(p_tmem + 16, hi);
+      }
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive_a(bar_p);
-      if (j >= 1) {  // deferred accumulate of tile j-1 (its P was relative to m_prev)
-        const int so = (j - 1) & 1;
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(o_tmem + so * 64, r);
-        const uint32_t rs = tmem_ld_32x32b_x1(tmem_base + lane_base + 128 + so * 64 + 32);
-        tmem_ld_wait();
-        const float a = ex2_approx(m_ref - m_prev);
-#pragma unroll
-        for (int d = 0; d < 16; ++d) o[d] = fmaf(o[d], a, __uint_as_float(r[d]));
-        l = fmaf(l, a, __uint_as_float(rs));
-        m_ref = m_prev;
-      }
     }
     {
       const int so = (nkv - 1) & 1;
-      mbar_wait_a(bar_o + 8 * so, ((nkv - 1) >> 1) & 1);
+      mbar_wait_a(bar_pv + 8 * so, ((nkv - 1) >> 1) & 1);
       tc_fence_after();
       uint32_t r[16];
-      tmem_ld_32x32b_x16(o_tmem + so * 64, r);
-      const uint32_t rs = tmem_ld_32x32b_x1(tmem_base + lane_base + 128 + so * 64 + 32);
+      tmem_ld_32x32b_x16(o_tmem, r);
+      const uint32_t rs = tmem_ld_32x32b_x1(l_tmem);
       tmem_ld_wait();
-      const float a = ex2_approx(m_ref - m_run);
+      const int q = q0 + row;
+      if (q < L) {
+        const int64_t m = static_cast<int64_t>(seq) * L + q;
+        const float gsc = gates[m * heads + h] / __uint_as_float(rs);
+        uint4 u[2];
+        uint32_t* w = reinterpret_cast<uint32_t*>(u);
 #pragma unroll
-      for (int d = 0; d < 16; ++d) o[d] = fmaf(o[d], a, __uint_as_float(r[d]));
-      l = fmaf(l, a, __uint_as_float(rs));
-    }
-    const int q = q0 + row;
-    if (q < L) {
-      const int64_t m = static_cast<int64_t>(seq) * L + q;
-      const float gsc = gates[m * heads + h] / l;
-      uint4 u[2];
-      uint32_t* w = reinterpret_cast<uint32_t*>(u);
-#pragma unroll
-      for (int d = 0; d < 8; ++d) w[d] = pack_bf16x2(o[2 * d] * gsc, o[2 * d + 1] * gsc);
-      uint4* dst = reinterpret_cast<uint4*>(out + m * C + h * 32 + hc * 16);
-      dst[0] = u[0];
-      dst[1] = u[1];
+        for (int d = 0; d < 8; ++d)
+          w[d] = pack_bf16x2(__uint_as_float(r[2 * d]) * gsc, __uint_as_float(r[2 * d + 1]) * gsc);
+        uint4* dst = reinterpret_cast<uint4*>(out + m * C + h * 32 + hc * 16);
+        dst[0] = u[0];
+        dst[1] = u[1];
+      }
     }
   }
   tc_fence_before();
