@@ -587,11 +587,10 @@ int launch_gemm_tc(const TcGemmPlan* p, const EpiParams& e, cudaStream_t st) {
 // (ex2.approx.f16x2 -- two exponentials per MUFU op -- was measured: 28% SLOWER than fp32
 // ex2 + bf16 pack on B200, profiles/r1_notes.md.)
 constexpr int AT_BQ = 128, AT_BKV = 128;
-constexpr int AT_SOFTMAX_WARPS = 8;                      // two threads per query row (64 keys each)
-constexpr int AT_THREADS = 32 * (AT_SOFTMAX_WARPS + 1);  // + 1 TMA/MMA warp
-constexpr int AT_SQ = 8192, AT_SK = 8192, AT_SV = 8192, AT_SONES = 8192, AT_SMAX = 2048;
-constexpr int AT_SMEM = AT_SQ + 2 * AT_SK + 2 * AT_SV + AT_SONES + AT_SMAX + 1024 + 128;
-constexpr int AT_POLY_MOD = 4;  // every AT_POLY_MOD-th exponential runs on the FMA pipe instead of MUFU
+constexpr int AT_SQ = 8192, AT_SK = 8192, AT_SV = 8192, AT_SONES = 8192, AT_SMAX = 4096;
+constexpr int AT_NST = 4;  // K/V stages: tile j+3 is in flight while tile j is consumed (TMA latency >> one tile otherwise)
+constexpr int AT_SMEM = AT_SQ + AT_NST * (AT_SK + AT_SV) + AT_SONES + AT_SMAX + 1024 + 128;
+constexpr int AT_POLY_MOD = 0;  // every AT_POLY_MOD-th exponential runs on the FMA pipe instead of MUFU (0: none)
 constexpr float AT_TAU = 8.0f;  // log2 units: rescale O only when the row maximum grew by more than this
 constexpr uint32_t AT_TM_O = 128, AT_TM_L = 160, AT_TM_P = 192;
 
@@ -611,7 +610,9 @@ __device__ __forceinline__ float ex2_poly(float x) {
   float p = fmaf(0.05508868f, r, 0.24260405f);
   p = fmaf(p, r, 0.69327623f);
   p = fmaf(p, r, 0.99992895f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+  int y;  // p * 2^round(x): add round(x) (low mantissa bits of t) to the exponent field, one IMAD
+  asm("mad.lo.s32 %0, %1, 8388608, %2;" : "=r"(y) : "r"(__float_as_int(t)), "r"(__float_as_int(p)));
+  return __int_as_float(y);
 }
 __device__ __forceinline__ uint32_t tmem_ld_32x32b_x1(uint32_t taddr) {
   uint32_t r;
@@ -638,6 +639,23 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+template <int N> __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]);
+template <> __device__ __forceinline__ void tmem_ld_n<8>(uint32_t taddr, uint32_t (&r)[8]) { tmem_ld_32x32b_x8(taddr, r); }
+template <> __device__ __forceinline__ void tmem_ld_n<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x32b_x16(taddr, r); }
+template <int N> __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t (&r)[N]);
+template <> __device__ __forceinline__ void tmem_st_n<8>(uint32_t taddr, const uint32_t (&r)[8]) { tmem_st_32x32b_x8(taddr, r); }
+template <> __device__ __forceinline__ void tmem_st_n<16>(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st_32x32b_x16(taddr, r); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem]: A is read from tensor memory (lane = row, one 32-bit column
 // per two K elements), kind::f16 with bf16 operands.
@@ -650,6 +668,50 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Predicated forms for a CONVERGED issuer warp: every lane executes the asm block with warp-uniform
+// operands, only the lane with `on != 0` (picked once with elect.sync) performs the operation.
+// Keeping the warp converged lets ptxas keep descriptors in uniform registers instead of wrapping
+// every tcgen05.mma of a divergent `if (lane == 0)` region in a vote loop (measured: ~85 cycles
+// per MMA issue in the divergent form).
+__device__ __forceinline__ void umma_bf16_p(uint32_t on, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_p(uint32_t on, uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint32_t on, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_p(uint32_t on, uint32_t smem_dst, const void* tmap, uint32_t bar, int32_t c0,
+                                              int32_t c1, int32_t c2) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];\n\t}" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_p(uint32_t on, uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes), "r"(on)
+      : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -660,20 +722,23 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc_sw64(uint32_t smem_addr, u
          (static_cast<uint64_t>(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
+// KS = softmax threads per query row (2: 8 softmax warps, 64 keys each; 4: 16 warps, 32 keys each);
+// POLY: every POLY-th exponential on the FMA pipe (0 = all on MUFU).
+template <int KS, int POLY>
+__global__ void __launch_bounds__(32 * (4 * KS + 1), 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict__ gates, bf16* __restrict__ out,
                int L, int heads) {
   extern __shared__ uint8_t smem_raw[];
   // everything below works on 32-bit shared-space addresses computed once
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = sbase;
-  const uint32_t sK = sQ + AT_SQ;         // [2]
-  const uint32_t sV = sK + 2 * AT_SK;     // [2]
-  const uint32_t sOnes = sV + 2 * AT_SV;  // [128 keys][32 cols] bf16, col 0 = 1: second N block of the PV MMA -> row sums of P
-  const uint32_t sMax = sOnes + AT_SONES; // [2 parity][2 halves][128 rows] fp32 partial row maxima
+  const uint32_t sK = sQ + AT_SQ;              // [AT_NST]
+  const uint32_t sV = sK + AT_NST * AT_SK;     // [AT_NST]
+  const uint32_t sOnes = sV + AT_NST * AT_SV;  // [128 keys][32 cols] bf16, col 0 = 1: second N block of the PV MMA -> row sums of P
+  const uint32_t sMax = sOnes + AT_SONES; // [2 parity][KS parts][128 rows] fp32 partial row maxima
   const uint32_t bar_q = sMax + AT_SMAX;
-  const uint32_t bar_kv = bar_q + 8;      // [2]
-  const uint32_t bar_s = bar_kv + 16;
+  const uint32_t bar_kv = bar_q + 8;      // [AT_NST]
+  const uint32_t bar_s = bar_kv + 8 * AT_NST;
   const uint32_t bar_sfree = bar_s + 8;   // S_j has been copied to registers: S_{j+1} may overwrite it
   const uint32_t bar_p = bar_sfree + 8;   // P_j sits in TMEM (and O was rescaled if the maximum jumped)
   const uint32_t bar_pv = bar_p + 8;      // [2] PV_j complete: P and K/V stage j&1 free, O holds tiles 0..j
@@ -685,8 +750,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
   const int seq = blockIdx.z;
   const int C = heads * 32;
   const int nkv = ceil_div(L, AT_BKV);
-  constexpr int MMA_WARP = AT_SOFTMAX_WARPS;
-  constexpr int NSOFT = AT_SOFTMAX_WARPS * 32;
+  constexpr int MMA_WARP = 4 * KS;
+  constexpr int NSOFT = 4 * KS * 32;
+  constexpr int NK = 128 / KS;  // keys per softmax thread and tile
+  constexpr int NO = 32 / KS;   // output columns per softmax thread
 
   if (warp == MMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmQK);
@@ -694,7 +761,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
     };
     init(bar_q, 1);
-    init(bar_kv, 1); init(bar_kv + 8, 1);
+    for (int i = 0; i < AT_NST; ++i) init(bar_kv + 8 * i, 1);
     init(bar_s, 1);
     init(bar_sfree, NSOFT);
     init(bar_p, NSOFT);
@@ -712,60 +779,58 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
   if (warp == MMA_WARP) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64) | (1u << 16);  // bit 16: B is MN-major
-      auto load_kv = [&](int j) {
-        const int st = j & 1;
-        mbar_expect_tx_a(bar_kv + 8 * st, AT_SK + AT_SV);
-        tma_load_3d_a(sK + st * AT_SK, &tmQK, bar_kv + 8 * st, C + h * 32, j * AT_BKV, seq);
-        tma_load_3d_a(sV + st * AT_SV, &tmQK, bar_kv + 8 * st, 2 * C + h * 32, j * AT_BKV, seq);
-      };
-      auto issue_s = [&](int j) {
-        const uint32_t kb = sK + (j & 1) * AT_SK;
+    // the whole warp runs this loop converged; `on` marks the one lane that issues TMA / MMA / commit
+    const uint32_t on = elect_one() ? 1u : 0u;
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64) | (1u << 16);  // bit 16: B is MN-major
+    auto load_kv = [&](int j) {
+      const int st = j % AT_NST;
+      mbar_expect_tx_p(on, bar_kv + 8 * st, AT_SK + AT_SV);
+      tma_load_3d_p(on, sK + st * AT_SK, &tmQK, bar_kv + 8 * st, C + h * 32, j * AT_BKV, seq);
+      tma_load_3d_p(on, sV + st * AT_SV, &tmQK, bar_kv + 8 * st, 2 * C + h * 32, j * AT_BKV, seq);
+    };
+    auto issue_s = [&](int j) {
+      const uint32_t kb = sK + (j % AT_NST) * AT_SK;
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
-          umma_bf16(tmem_base, make_kmajor_desc<64>(sQ + k * 32), make_kmajor_desc<64>(kb + k * 32), idesc_s,
+      for (int k = 0; k < 2; ++k)
+        umma_bf16_p(on, tmem_base, make_kmajor_desc<64>(sQ + k * 32), make_kmajor_desc<64>(kb + k * 32), idesc_s,
                     k != 0 ? 1u : 0u);
-        umma_commit_a(bar_s);
-      };
-      mbar_expect_tx_a(bar_q, AT_SQ);
-      tma_load_3d_a(sQ, &tmQK, bar_q, h * 32, q0, seq);
-      load_kv(0);
-      if (nkv > 1) load_kv(1);
-      mbar_wait_a(bar_q, 0);
-      mbar_wait_a(bar_kv, 0);
-      tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        if (j + 1 < nkv) {  // S_{j+1} is computed while the softmax warps work on S_j
-          mbar_wait_a(bar_sfree, j & 1);  // S_j copied to registers by every softmax thread
-          mbar_wait_a(bar_kv + 8 * ((j + 1) & 1), ((j + 1) >> 1) & 1);
-          tc_fence_after();
-          issue_s(j + 1);
-        }
-        mbar_wait_a(bar_p, j & 1);  // P_j written to TMEM (and O rescaled if the maximum jumped)
+      umma_commit_p(on, bar_s);
+    };
+    mbar_expect_tx_p(on, bar_q, AT_SQ);
+    tma_load_3d_p(on, sQ, &tmQK, bar_q, h * 32, q0, seq);
+    for (int j = 0; j < AT_NST && j < nkv; ++j) load_kv(j);
+    mbar_wait_a(bar_q, 0);
+    mbar_wait_a(bar_kv, 0);
+    tc_fence_after();
+    issue_s(0);
+    for (int j = 0; j < nkv; ++j) {
+      if (j + 1 < nkv) {  // S_{j+1} is computed while the softmax warps work on S_j
+        mbar_wait_a(bar_sfree, j & 1);  // S_j copied to registers by every softmax thread
+        mbar_wait_a(bar_kv + 8 * ((j + 1) % AT_NST), ((j + 1) / AT_NST) & 1);
         tc_fence_after();
-        const uint32_t vb = sV + st * AT_SV;
-        const uint32_t lbo = sOnes - vb;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)  // 16 keys = 8 TMEM columns of P per MMA
-          umma_bf16_ts(tmem_base + AT_TM_O, tmem_base + AT_TM_P + k * 8, make_mnmajor_desc_sw64(vb + k * 1024, lbo),
-                       idesc_o, (j != 0 || k != 0) ? 1u : 0u);
-        umma_commit_a(bar_pv + 8 * st);
-        if (j + 2 < nkv) {
-          mbar_wait_a(bar_pv + 8 * st, (j >> 1) & 1);  // PV_j done -> K/V stage reusable
-          load_kv(j + 2);
-        }
+        issue_s(j + 1);
       }
+      if (j >= 1 && j - 1 + AT_NST < nkv) {  // PV_{j-1} done (issued a whole tile ago) -> refill its K/V stage
+        mbar_wait_a(bar_pv + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
+        load_kv(j - 1 + AT_NST);
+      }
+      mbar_wait_a(bar_p, j & 1);  // P_j written to TMEM (and O rescaled if the maximum jumped)
+      tc_fence_after();
+      const uint32_t vb = sV + (j % AT_NST) * AT_SV;
+      const uint32_t lbo = sOnes - vb;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)  // 16 keys = 8 TMEM columns of P per MMA
+        umma_bf16_ts_p(on, tmem_base + AT_TM_O, tmem_base + AT_TM_P + k * 8, make_mnmajor_desc_sw64(vb + k * 1024, lbo),
+                       idesc_o, (j != 0 || k != 0) ? 1u : 0u);
+      umma_commit_p(on, bar_pv + 8 * (j & 1));
     }
   } else {
     const int quarter = warp & 3;
-    const int hc = warp >> 2;  // which half of the keys / of the output columns
+    const int kq = warp >> 2;  // which part of the keys / of the output columns
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    if (hc == 0) {  // ones block: logical column 0 of key row `row` is 1.0 (bf16 0x3F80), the rest 0; SW64 swizzle
+    if (kq == 0) {  // ones block: logical column 0 of key row `row` is 1.0 (bf16 0x3F80), the rest 0; SW64 swizzle
       const uint32_t orow = sOnes + row * 64;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -775,60 +840,68 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the MMA (async proxy) after bar_p
     }
     float m_ref = -INFINITY;
-    const uint32_t s_tmem = tmem_base + lane_base + hc * 64;
-    const uint32_t o_tmem = tmem_base + lane_base + AT_TM_O + hc * 16;  // this thread's 16 output columns
-    const uint32_t l_tmem = tmem_base + lane_base + AT_TM_L;            // row sum of P (ones block column)
-    const uint32_t p_tmem = tmem_base + lane_base + AT_TM_P + hc * 32;  // this thread's 64 keys = 32 columns
-    const uint32_t my_max = sMax + (hc * 128 + row) * 4, other_max = sMax + ((hc ^ 1) * 128 + row) * 4;
+    const uint32_t s_tmem = tmem_base + lane_base + kq * NK;
+    const uint32_t o_tmem = tmem_base + lane_base + AT_TM_O + kq * NO;        // this thread's output columns
+    const uint32_t l_tmem = tmem_base + lane_base + AT_TM_L;                  // row sum of P (ones block column)
+    const uint32_t p_tmem = tmem_base + lane_base + AT_TM_P + kq * (NK / 2);  // this thread's keys, two per column
+    const uint32_t max_row = sMax + row * 4;
     for (int j = 0; j < nkv; ++j) {
       mbar_wait_a(bar_s, j & 1);
       tc_fence_after();
-      float s[64];
+      float s[NK];
       {
-        uint32_t r0[32], r1[32];
+        uint32_t r0[32];
         tmem_ld_32x32b_x32(s_tmem, r0);
-        tmem_ld_32x32b_x32(s_tmem + 32, r1);
-        tmem_ld_wait();
+        if constexpr (NK == 64) {
+          uint32_t r1[32];
+          tmem_ld_32x32b_x32(s_tmem + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[32 + (i & (NK - 33))] = __uint_as_float(r1[i]);
+        } else {
+          tmem_ld_wait();
+        }
         tc_fence_before();
         mbar_arrive_a(bar_sfree);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]); }
+        for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r0[i]);
       }
       if (j == nkv - 1) {
-        const int lim = L - j * AT_BKV - hc * 64;  // keys >= lim are padding
+        const int lim = L - j * AT_BKV - kq * NK;  // keys >= lim are padding
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
+        for (int i = 0; i < NK; ++i)
           if (i >= lim) s[i] = -INFINITY;
       }
       float mxs[8];  // independent max chains
 #pragma unroll
       for (int k = 0; k < 8; ++k) mxs[k] = fmaxf(s[k], s[8 + k]);
 #pragma unroll
-      for (int i = 16; i < 64; i += 16) {
+      for (int i = 16; i < NK; i += 16) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) mxs[k] = fmaxf(mxs[k], fmaxf(s[i + k], s[i + 8 + k]));
       }
       float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
                        fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
-      {  // exchange the partial maximum with the thread that owns the other half of this row
-        const uint32_t par = (j & 1) * 1024;
-        st_shared_f32(my_max + par, mx);
-        named_bar_sync(1 + quarter, 64);
-        mx = fmaxf(mx, ld_shared_f32(other_max + par));
+      {  // exchange the partial maxima between the KS threads that share this row
+        const uint32_t par = max_row + (j & 1) * (KS * 512);
+        st_shared_f32(par + kq * 512, mx);
+        named_bar_sync(1 + quarter, 32 * KS);
+#pragma unroll
+        for (int kk = 1; kk < KS; ++kk) mx = fmaxf(mx, ld_shared_f32(par + ((kq + kk) & (KS - 1)) * 512));
       }
-      // lazy rescale: identical decision in both threads of a row (same m_ref, same mx)
+      // lazy rescale: identical decision in all threads of a row (same m_ref, same mx)
       const bool need = mx > m_ref + AT_TAU;  // always true for j == 0 (m_ref = -inf)
       const bool any_need = __any_sync(0xffffffffu, need);
       const float a_corr = (need && j > 0) ? ex2_approx(m_ref - mx) : 1.0f;
       if (need) m_ref = mx;
-      uint32_t pk[32];  // P_j of this thread: 64 keys, two per register
+      uint32_t pk[NK / 2];  // P_j of this thread, two keys per register
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < NK / 8; ++c) {
         float p[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float x = s[c * 8 + i] - m_ref;
-          p[i] = (i % AT_POLY_MOD == AT_POLY_MOD - 1) ? ex2_poly(x) : ex2_approx(x);
+          p[i] = (POLY > 0 && i % (POLY > 0 ? POLY : 1) == (POLY > 0 ? POLY : 1) - 1) ? ex2_poly(x) : ex2_approx(x);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) pk[c * 4 + i] = pack_bf16x2(p[2 * i], p[2 * i + 1]);
@@ -837,23 +910,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
         mbar_wait_a(bar_pv + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
         tc_fence_after();
         if (any_need) {  // warp-uniform; rare after the first tiles
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(o_tmem, r);
+          uint32_t r[NO];
+          tmem_ld_n<NO>(o_tmem, r);
           uint32_t rs = 0;
-          if (hc == 0) rs = tmem_ld_32x32b_x1(l_tmem);
+          if (kq == 0) rs = tmem_ld_32x32b_x1(l_tmem);
           tmem_ld_wait();
 #pragma unroll
-          for (int d = 0; d < 16; ++d) r[d] = __float_as_uint(__uint_as_float(r[d]) * a_corr);
-          tmem_st_32x32b_x16(o_tmem, r);
-          if (hc == 0) tmem_st_32x32b_x1(l_tmem, __float_as_uint(__uint_as_float(rs) * a_corr));
+          for (int d = 0; d < NO; ++d) r[d] = __float_as_uint(__uint_as_float(r[d]) * a_corr);
+          tmem_st_n<NO>(o_tmem, r);
+          if (kq == 0) tmem_st_32x32b_x1(l_tmem, __float_as_uint(__uint_as_float(rs) * a_corr));
         }
       }
-      {
-        uint32_t (&lo)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[0]);
-        uint32_t (&hi)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[16]);
-        tmem_st_32x32b_x16(p_tmem, lo);
-        tmem_st_32x32b_x16(p_tmem + 16, hi);
-      }
+#pragma unroll
+      for (int i = 0; i < NK / 32; ++i)
+        tmem_st_32x32b_x16(p_tmem + 16 * i, *reinterpret_cast<uint32_t (*)[16]>(&pk[16 * i]));
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive_a(bar_p);
@@ -862,22 +932,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const float* __restrict
       const int so = (nkv - 1) & 1;
       mbar_wait_a(bar_pv + 8 * so, ((nkv - 1) >> 1) & 1);
       tc_fence_after();
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(o_tmem, r);
+      uint32_t r[NO];
+      tmem_ld_n<NO>(o_tmem, r);
       const uint32_t rs = tmem_ld_32x32b_x1(l_tmem);
       tmem_ld_wait();
       const int q = q0 + row;
       if (q < L) {
         const int64_t m = static_cast<int64_t>(seq) * L + q;
         const float gsc = gates[m * heads + h] / __uint_as_float(rs);
-        uint4 u[2];
+        uint4 u[NO / 8];
         uint32_t* w = reinterpret_cast<uint32_t*>(u);
 #pragma unroll
-        for (int d = 0; d < 8; ++d)
+        for (int d = 0; d < NO / 2; ++d)
           w[d] = pack_bf16x2(__uint_as_float(r[2 * d]) * gsc, __uint_as_float(r[2 * d + 1]) * gsc);
-        uint4* dst = reinterpret_cast<uint4*>(out + m * C + h * 32 + hc * 16);
-        dst[0] = u[0];
-        dst[1] = u[1];
+        uint4* dst = reinterpret_cast<uint4*>(out + m * C + h * 32 + kq * NO);
+#pragma unroll
+        for (int d = 0; d < NO / 8; ++d) dst[d] = u[d];
       }
     }
   }
@@ -905,8 +975,17 @@ void tc_attn_plan_destroy(TcAttnPlan* p) { delete p; }
 
 int launch_attn_time_tc(const TcAttnPlan* p, const float* gates, void* out, cudaStream_t st) {
   dim3 grid(ceil_div(p->L, AT_BQ), p->heads, p->seqs);
-  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(p->tmQK, gates, reinterpret_cast<bf16*>(out), p->L, p->heads);
-  return 0;
+  static const int poly = getenv("BT_ATTN_POLY") ? atoi(getenv("BT_ATTN_POLY")) : AT_POLY_MOD;
+  static const int ks = getenv("BT_ATTN_KS") ? atoi(getenv("BT_ATTN_KS")) : 2;
+#define BT_AT_L(K, A)                                                                                              \
+  if (ks == K && poly == A) {                                                                                      \
+    attn_tc_kernel<K, A><<<grid, 32 * (4 * K + 1), AT_SMEM, st>>>(p->tmQK, gates, reinterpret_cast<bf16*>(out), p->L, \
+                                                                  p->heads);                                       \
+    return 0;                                                                                                      \
+  }
+  BT_AT_L(2, 0) BT_AT_L(2, 4) BT_AT_L(2, 8) BT_AT_L(4, 0)
+#undef BT_AT_L
+  return -3;
 }
 
 // ==================================================================== fused frontend FFN
@@ -1332,7 +1411,10 @@ int tc_init(char* err, int errlen) {
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaError_t r = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+  cudaFuncSetAttribute(attn_tc_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+  cudaFuncSetAttribute(attn_tc_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+  cudaFuncSetAttribute(attn_tc_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+  cudaError_t r = cudaFuncSetAttribute(attn_tc_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
   if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<32>::SMEM);
   if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<64>::SMEM);
   if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_qkv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, QkvCfg<32>::SMEM);
