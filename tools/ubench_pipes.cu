@@ -35,6 +35,15 @@ __global__ void __launch_bounds__(1024) k(float* out, long long* cyc, int iters)
       if (OP == 7) asm volatile("max.f32 %0, %0, %1; max.f32 %0, %0, %2;" : "+f"(a[i]) : "f"(a[(i + 1) & 7]), "f"(a[(i + 2) & 7]));
       if (OP == 8) asm volatile("shl.b32 %0, %0, 23; add.s32 %0, %0, %1;" : "+r"(u[i]) : "r"(u[(i + 1) & 7]));
       if (OP == 9) asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(a[i]), "f"(a[(i + 1) & 7]));
+      if (OP == 10) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u[i]));
+      if (OP == 11) {  // f16x2 softmax mix per 2 elements: 2 sub, 1 pack, 1 ex2.f16x2
+        asm volatile("add.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(a[(i + 1) & 7]));
+        asm volatile("add.f32 %0, %0, %1;" : "+f"(a[(i + 2) & 7]) : "f"(a[(i + 3) & 7]));
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(a[i]), "f"(a[(i + 2) & 7]));
+        asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u[i]));
+      }
+      if (OP == 12) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a[i]));
+      if (OP == 13) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(u[i]));
     }
   }
   const long long t1 = clock64();
@@ -69,6 +78,10 @@ int main() {
   run<3>("add.f32", 1, out, cyc);
   run<4>("fma.f32", 1, out, cyc);
   run<8>("shl+add.s32", 2, out, cyc);
+  run<10>("ex2.approx.f16x2 (instr)", 1, out, cyc);
+  run<13>("ex2.approx.ftz.bf16x2 (instr)", 1, out, cyc);
+  run<12>("tanh.approx.f32", 1, out, cyc);
+  run<11>("2 sub + pack + ex2.f16x2", 4, out, cyc);
   run<6>("ex2 + cvt pair", 2, out, cyc);
   run<5>("2 sub + 2 ex2 + 1 pack", 5, out, cyc);
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
