@@ -16,6 +16,61 @@
 
 namespace bt {
 
+// Predicated forms for a CONVERGED issuer warp: every lane executes the asm block with warp-uniform
+// operands, only the lane with `on != 0` (picked once with elect.sync) performs the operation.
+// Keeping the warp converged lets ptxas keep descriptors in uniform registers instead of wrapping
+// every tcgen05.mma of a divergent `if (lane == 0)` region in a vote loop (measured: ~85 cycles
+// per MMA issue in the divergent form).
+__device__ __forceinline__ void umma_bf16_p(uint32_t on, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_p(uint32_t on, uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint32_t on, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_p(uint32_t on, uint32_t smem_dst, const void* tmap, uint32_t bar, int32_t c0,
+                                              int32_t c1, int32_t c2) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];\n\t}" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_p(uint32_t on, uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_p(uint32_t on, uint32_t smem_dst, const void* tmap, uint32_t bar, int32_t c0,
+                                              int32_t c1) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];\n\t}" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(on)
+      : "memory");
+}
+
+
 // --------------------------------------------------------------------------- tensor maps
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -119,58 +174,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_kb = g.nslab * kb_per_slab;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = walk_start; tile < num_tiles; tile += walk_step) {
-        const int mt = tile_mt(tile), nt = tile % n_tiles;
-        const int p_out = mt / t_tiles;  // beyond the last plane for the dummy half of an odd pair: TMA zero-fills
-        const int t0 = (mt - p_out * t_tiles) * TG_BM;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int s = kb / kb_per_slab;
-          const int k0 = (kb - s * kb_per_slab) * BK;
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-          tma_load_3d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], k0, t0 + g.t_shift[s],
+    // producer and MMA warps run CONVERGED with predicated single-lane TMA / MMA / commit instructions
+    // (see umma_bf16_p): in a divergent `if (lane == 0)` block every tcgen05.mma costs ~85 issue cycles.
+    const uint32_t on = elect_one() ? 1u : 0u;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = walk_start; tile < num_tiles; tile += walk_step) {
+      const int mt = tile_mt(tile), nt = tile % n_tiles;
+      const int p_out = mt / t_tiles;  // beyond the last plane for the dummy half of an odd pair: TMA zero-fills
+      const int t0 = (mt - p_out * t_tiles) * TG_BM;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb / kb_per_slab;
+        const int k0 = (kb - s * kb_per_slab) * BK;
+        mbar_wait(&empty[stage], phase ^ 1);
+        const uint32_t fb = smem_u32(&full[stage]);
+        mbar_expect_tx_p(on, fb, Cfg::STAGE_BYTES);
+        tma_load_3d_p(on, smem_u32(sA + stage * Cfg::A_BYTES), &tmA, fb, k0, t0 + g.t_shift[s],
                       p_out * g.plane_mul + g.plane_add[s]);
-          if constexpr (MC)  // my half of the W tile, delivered to both CTAs of the pair
+        if constexpr (MC) {  // my half of the W tile, delivered to both CTAs of the pair
+          if (on)
             tma_load_2d_mc(sW + stage * Cfg::W_BYTES + crank * (Cfg::W_BYTES / 2), &tmW, &full[stage], s * g.Kslab + k0,
                            nt * BN + static_cast<int>(crank) * (BN / 2), 0x3);
-          else
-            tma_load_2d(sW + stage * Cfg::W_BYTES, &tmW, &full[stage], s * g.Kslab + k0, nt * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          __syncwarp();
+        } else {
+          tma_load_2d_p(on, smem_u32(sW + stage * Cfg::W_BYTES), &tmW, fb, s * g.Kslab + k0, nt * BN);
         }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(TG_BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = walk_start; tile < num_tiles; tile += walk_step) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+    const uint32_t on = elect_one() ? 1u : 0u;
+    constexpr uint32_t idesc = make_idesc_bf16(TG_BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = walk_start; tile < num_tiles; tile += walk_step) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + stage * Cfg::A_BYTES);
-          const uint32_t b_base = smem_u32(sW + stage * Cfg::W_BYTES);
+        const uint32_t a_base = smem_u32(sA + stage * Cfg::A_BYTES);
+        const uint32_t b_base = smem_u32(sW + stage * Cfg::W_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16(d_tmem, make_kmajor_desc<Cfg::SWZ>(a_base + k * 32),
-                      make_kmajor_desc<Cfg::SWZ>(b_base + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          if constexpr (MC) umma_commit_mc(&empty[stage], 0x3);
-          else umma_commit(&empty[stage]);
-          if (kb == num_kb - 1) umma_commit(&tfull[acc]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        for (int k = 0; k < BK / 16; ++k) {
+          umma_bf16_p(on, d_tmem, make_kmajor_desc<Cfg::SWZ>(a_base + k * 32), make_kmajor_desc<Cfg::SWZ>(b_base + k * 32),
+                      idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if constexpr (MC) {
+          if (on) umma_commit_mc(&empty[stage], 0x3);
+          __syncwarp();
+        } else {
+          umma_commit_p(on, smem_u32(&empty[stage]));
+        }
+        if (kb == num_kb - 1) umma_commit_p(on, smem_u32(&tfull[acc]));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // Epilogue warps.  A warp may only touch TMEM lanes [32*(warp%4), +32); thread = one output row.
@@ -666,50 +729,6 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Predicated forms for a CONVERGED issuer warp: every lane executes the asm block with warp-uniform
-// operands, only the lane with `on != 0` (picked once with elect.sync) performs the operation.
-// Keeping the warp converged lets ptxas keep descriptors in uniform registers instead of wrapping
-// every tcgen05.mma of a divergent `if (lane == 0)` region in a vote loop (measured: ~85 cycles
-// per MMA issue in the divergent form).
-__device__ __forceinline__ void umma_bf16_p(uint32_t on, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(on)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16_ts_p(uint32_t on, uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                               uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(on)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_p(uint32_t on, uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(on)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_p(uint32_t on, uint32_t smem_dst, const void* tmap, uint32_t bar, int32_t c0,
-                                              int32_t c1, int32_t c2) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
-      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];\n\t}" ::"r"(smem_dst),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(on)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx_p(uint32_t on, uint32_t bar, uint32_t bytes) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
-      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes), "r"(on)
       : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
