@@ -1294,50 +1294,42 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
   if (warp == 4) {
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc_bf16(128, 128);
-      constexpr uint32_t idesc2 = make_idesc_bf16(128, C);
-      // weights: W1 [4C, C] all chunks (boxes of 128 rows), W2 [C, 4C] first K-chunk (two 64-wide boxes)
-      mbar_expect_tx_a(bar_w1, Cfg::W1_BYTES);
-      for (int h = 0; h < NH; ++h) {
-        asm volatile(
-            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-            ::"r"(sW1 + h * (128 * C * 2)), "l"(reinterpret_cast<uint64_t>(&tmW1)), "r"(bar_w1), "r"(0), "r"(h * 128) : "memory");
-      }
-      auto load_w2 = [&](int h) {
-        mbar_expect_tx_a(bar_w2, Cfg::W2C_BYTES);
-        for (int a = 0; a < 2; ++a)
-          asm volatile(
-              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-              ::"r"(sW2 + a * (C * 128)), "l"(reinterpret_cast<uint64_t>(&tmW2)), "r"(bar_w2), "r"(h * 128 + a * 64), "r"(0) : "memory");
-      };
-      load_w2(0);
-      auto issue_mma1 = [&](int h) {
+    const uint32_t on = elect_one() ? 1u : 0u;  // converged issuer warp, predicated single-lane TMA / MMA (see umma_bf16_p)
+    constexpr uint32_t idesc1 = make_idesc_bf16(128, 128);
+    constexpr uint32_t idesc2 = make_idesc_bf16(128, C);
+    // weights: W1 [4C, C] all chunks (boxes of 128 rows), W2 [C, 4C] first K-chunk (two 64-wide boxes)
+    mbar_expect_tx_p(on, bar_w1, Cfg::W1_BYTES);
+    for (int h = 0; h < NH; ++h) tma_load_2d_p(on, sW1 + h * (128 * C * 2), &tmW1, bar_w1, 0, h * 128);
+    auto load_w2 = [&](int h) {
+      mbar_expect_tx_p(on, bar_w2, Cfg::W2C_BYTES);
+      for (int a = 0; a < 2; ++a) tma_load_2d_p(on, sW2 + a * (C * 128), &tmW2, bar_w2, h * 128 + a * 64, 0);
+    };
+    load_w2(0);
+    auto issue_mma1 = [&](int h) {
 #pragma unroll
-        for (int k = 0; k < C / 16; ++k)
-          umma_bf16(tmem_base, make_kmajor_desc<Cfg::SWZ_A>(sA + k * 32),
+      for (int k = 0; k < C / 16; ++k)
+        umma_bf16_p(on, tmem_base, make_kmajor_desc<Cfg::SWZ_A>(sA + k * 32),
                     make_kmajor_desc<Cfg::SWZ_A>(sW1 + h * (128 * C * 2) + k * 32), idesc1, k != 0 ? 1u : 0u);
-        umma_commit_a(bar_h);
-      };
-      mbar_wait_a(bar_a, 0);
-      mbar_wait_a(bar_w1, 0);
+      umma_commit_p(on, bar_h);
+    };
+    mbar_wait_a(bar_a, 0);
+    mbar_wait_a(bar_w1, 0);
+    tc_fence_after();
+    issue_mma1(0);
+    for (int h = 0; h < NH; ++h) {
+      mbar_wait_a(bar_h2, h & 1);  // bf16 H_h tile written, accumulator H consumed
       tc_fence_after();
-      issue_mma1(0);
-      for (int h = 0; h < NH; ++h) {
-        mbar_wait_a(bar_h2, h & 1);  // bf16 H_h tile written, accumulator H consumed
-        tc_fence_after();
-        if (h + 1 < NH) issue_mma1(h + 1);
-        mbar_wait_a(bar_w2, h & 1);
-        tc_fence_after();
+      if (h + 1 < NH) issue_mma1(h + 1);
+      mbar_wait_a(bar_w2, h & 1);
+      tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_base + 128, make_kmajor_desc<128>(sH + (k >> 2) * 16384 + (k & 3) * 32),
+      for (int k = 0; k < 8; ++k)
+        umma_bf16_p(on, tmem_base + 128, make_kmajor_desc<128>(sH + (k >> 2) * 16384 + (k & 3) * 32),
                     make_kmajor_desc<128>(sW2 + (k >> 2) * (C * 128) + (k & 3) * 32), idesc2, (h | k) != 0 ? 1u : 0u);
-        umma_commit_a(bar_o);
-        if (h + 1 < NH) {
-          mbar_wait_a(bar_o, h & 1);  // MMA2_h finished reading W2_h (and the H tile)
-          load_w2(h + 1);
-        }
+      umma_commit_p(on, bar_o);
+      if (h + 1 < NH) {
+        mbar_wait_a(bar_o, h & 1);  // MMA2_h finished reading W2_h (and the H tile)
+        load_w2(h + 1);
       }
     }
   } else {
@@ -1513,21 +1505,18 @@ fused_qkv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
   if (warp == 4) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 3 * C);
-      mbar_expect_tx_a(bar_w, Cfg::W_BYTES);
-      asm volatile(
-          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-          ::"r"(sW), "l"(reinterpret_cast<uint64_t>(&tmW)), "r"(bar_w), "r"(0), "r"(0) : "memory");
-      mbar_wait_a(bar_a, 0);
-      mbar_wait_a(bar_w, 0);
-      tc_fence_after();
+    const uint32_t on = elect_one() ? 1u : 0u;  // converged issuer warp (see umma_bf16_p)
+    constexpr uint32_t idesc = make_idesc_bf16(128, 3 * C);
+    mbar_expect_tx_p(on, bar_w, Cfg::W_BYTES);
+    tma_load_2d_p(on, sW, &tmW, bar_w, 0, 0);
+    mbar_wait_a(bar_a, 0);
+    mbar_wait_a(bar_w, 0);
+    tc_fence_after();
 #pragma unroll
-      for (int k = 0; k < C / 16; ++k)
-        umma_bf16(tmem_base, make_kmajor_desc<Cfg::SWZ>(sA + k * 32), make_kmajor_desc<Cfg::SWZ>(sW + k * 32), idesc,
+    for (int k = 0; k < C / 16; ++k)
+      umma_bf16_p(on, tmem_base, make_kmajor_desc<Cfg::SWZ>(sA + k * 32), make_kmajor_desc<Cfg::SWZ>(sW + k * 32), idesc,
                   k != 0 ? 1u : 0u);
-      umma_commit_a(bar_d);
-    }
+    umma_commit_p(on, bar_d);
   } else {
     const int row = warp * 32 + lane;
     const int64_t m = m0 + row;
