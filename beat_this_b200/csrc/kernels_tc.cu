@@ -1246,13 +1246,21 @@ struct FfCfg {
   static constexpr int H_BYTES = 128 * 128 * 2;
   static constexpr int SMEM = A_BYTES + W1_BYTES + W2C_BYTES + H_BYTES + 5 * C * 4 + 1024 + 128;
   static constexpr int SWZ_A = C * 2 < 128 ? C * 2 : 128;  // 64-byte rows for C=32, 128 for C=64
+  // TMEM: H accumulator [0,128) and OUT accumulator.  With a single hidden chunk (C = 32) OUT reuses the H
+  // columns (every thread has read H before MMA2 is issued) -> 128 columns, 3 CTAs/SM instead of 2.
+  static constexpr int OUT_COL = NH == 1 ? 0 : 128;
+  static constexpr int TCOLS = NH == 1 ? 128 : 256;
+  static constexpr int CTAS = NH == 1 ? 3 : 2;
 };
 
 template <int C>
-__global__ void __launch_bounds__(FF_THREADS, 2)
+__global__ void __launch_bounds__(FF_THREADS, FfCfg<C>::CTAS)
 fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                 float* __restrict__ X, const float* __restrict__ b1, const float* __restrict__ b2,
                 bf16* __restrict__ xb_out, int64_t M) {
+  // PERSISTENT: each CTA walks over token tiles (stride gridDim.x); W1 (and W2 when it is a single chunk) are
+  // fetched once per CTA, barriers / TMEM / bias staging are set up once.  (The one-tile-per-CTA form spent
+  // more time on set-up and on re-fetching 16-64 KB of weights per CTA than on its tile.)
   using Cfg = FfCfg<C>;
   constexpr int NH = Cfg::NH;
   extern __shared__ uint8_t smem_raw[];
@@ -1270,7 +1278,7 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
   const uint32_t bar_o = bar_h2 + 8;
   const uint32_t tmem_slot = bar_o + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * 128;
+  const int ntiles = static_cast<int>((M + 127) / 128);
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmW1);
@@ -1282,7 +1290,7 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(256) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::TCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < 5 * C; i += FF_THREADS)
@@ -1297,7 +1305,7 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
     const uint32_t on = elect_one() ? 1u : 0u;  // converged issuer warp, predicated single-lane TMA / MMA (see umma_bf16_p)
     constexpr uint32_t idesc1 = make_idesc_bf16(128, 128);
     constexpr uint32_t idesc2 = make_idesc_bf16(128, C);
-    // weights: W1 [4C, C] all chunks (boxes of 128 rows), W2 [C, 4C] first K-chunk (two 64-wide boxes)
+    // weights: W1 [4C, C] all chunks (boxes of 128 rows), W2 [C, 4C] one K-chunk at a time (two 64-wide boxes)
     mbar_expect_tx_p(on, bar_w1, Cfg::W1_BYTES);
     for (int h = 0; h < NH; ++h) tma_load_2d_p(on, sW1 + h * (128 * C * 2), &tmW1, bar_w1, 0, h * 128);
     auto load_w2 = [&](int h) {
@@ -1312,110 +1320,121 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
                     make_kmajor_desc<Cfg::SWZ_A>(sW1 + h * (128 * C * 2) + k * 32), idesc1, k != 0 ? 1u : 0u);
       umma_commit_p(on, bar_h);
     };
-    mbar_wait_a(bar_a, 0);
     mbar_wait_a(bar_w1, 0);
-    tc_fence_after();
-    issue_mma1(0);
-    for (int h = 0; h < NH; ++h) {
-      mbar_wait_a(bar_h2, h & 1);  // bf16 H_h tile written, accumulator H consumed
+    int idx = 0;      // chunk counter over all tiles of this CTA: parity of bar_h / bar_h2 / bar_o
+    int w2_loads = 0; // completed-or-in-flight W2 chunk loads minus one: parity of bar_w2
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      mbar_wait_a(bar_a, it & 1);  // normalised tile in smem (and every thread is done with the previous tile's TMEM)
       tc_fence_after();
-      if (h + 1 < NH) issue_mma1(h + 1);
-      mbar_wait_a(bar_w2, h & 1);
-      tc_fence_after();
+      issue_mma1(0);
+      for (int h = 0; h < NH; ++h, ++idx) {
+        mbar_wait_a(bar_h2, idx & 1);  // bf16 H_h tile written, accumulator H consumed
+        tc_fence_after();
+        if (h + 1 < NH) issue_mma1(h + 1);
+        if (NH > 1 || idx == 0) mbar_wait_a(bar_w2, w2_loads & 1);
+        tc_fence_after();
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_bf16_p(on, tmem_base + 128, make_kmajor_desc<128>(sH + (k >> 2) * 16384 + (k & 3) * 32),
-                    make_kmajor_desc<128>(sW2 + (k >> 2) * (C * 128) + (k & 3) * 32), idesc2, (h | k) != 0 ? 1u : 0u);
-      umma_commit_p(on, bar_o);
-      if (h + 1 < NH) {
-        mbar_wait_a(bar_o, h & 1);  // MMA2_h finished reading W2_h (and the H tile)
-        load_w2(h + 1);
+        for (int k = 0; k < 8; ++k)
+          umma_bf16_p(on, tmem_base + Cfg::OUT_COL, make_kmajor_desc<128>(sH + (k >> 2) * 16384 + (k & 3) * 32),
+                      make_kmajor_desc<128>(sW2 + (k >> 2) * (C * 128) + (k & 3) * 32), idesc2, (h | k) != 0 ? 1u : 0u);
+        umma_commit_p(on, bar_o);
+        if (NH > 1 && (h + 1 < NH || tile + static_cast<int>(gridDim.x) < ntiles)) {
+          mbar_wait_a(bar_o, idx & 1);  // MMA2 finished reading this W2 chunk (and the H tile)
+          load_w2((h + 1) % NH);
+          ++w2_loads;
+        }
       }
     }
   } else {
     const int row = warp * 32 + lane;
-    const int64_t m = m0 + row;
-    const bool valid = m < M;
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    // ---- RMSNorm of this token (x stays in registers for the residual) ----
-    float x[C];
-    {
-      const float4* xr = reinterpret_cast<const float4*>(X + (valid ? m : 0) * C);
-      float ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < C / 4; ++i) {
-        const float4 q = valid ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
-        ss = fmaf(q.x, q.x, ss); ss = fmaf(q.y, q.y, ss); ss = fmaf(q.z, q.z, ss); ss = fmaf(q.w, q.w, ss);
-      }
-      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-      constexpr int RB = C * 2;  // bytes per A row
-      const uint32_t arow = sA + row * RB;
-      const uint32_t sw = C == 32 ? (static_cast<uint32_t>((row >> 1) & 3) << 4) : (static_cast<uint32_t>(row & 7) << 4);
-#pragma unroll
-      for (int c = 0; c < C / 8; ++c)
-        st_shared_v4(arow + ((c << 4) ^ sw), pack_bf16x2(x[8 * c] * inv, x[8 * c + 1] * inv),
-                     pack_bf16x2(x[8 * c + 2] * inv, x[8 * c + 3] * inv), pack_bf16x2(x[8 * c + 4] * inv, x[8 * c + 5] * inv),
-                     pack_bf16x2(x[8 * c + 6] * inv, x[8 * c + 7] * inv));
-      fence_proxy_async_smem();
-      mbar_arrive_a(bar_a);
-    }
     const uint32_t hrow = sH + row * 128;
     const uint32_t hsw = static_cast<uint32_t>(row & 7) << 4;
-    for (int h = 0; h < NH; ++h) {
-      mbar_wait_a(bar_h, h & 1);
-      tc_fence_after();
-      if (h >= 1) {  // the single H tile is free once MMA2_{h-1} has completed
-        mbar_wait_a(bar_o, (h - 1) & 1);
+    int idx = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t m = static_cast<int64_t>(tile) * 128 + row;
+      const bool valid = m < M;
+      // ---- RMSNorm of this token (x stays in registers for the residual) ----
+      float x[C];
+      {
+        const float4* xr = reinterpret_cast<const float4*>(X + (valid ? m : 0) * C);
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < C / 4; ++i) {
+          const float4 q = valid ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
+          ss = fmaf(q.x, q.x, ss); ss = fmaf(q.y, q.y, ss); ss = fmaf(q.z, q.z, ss); ss = fmaf(q.w, q.w, ss);
+        }
+        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+        constexpr int RB = C * 2;  // bytes per A row
+        const uint32_t arow = sA + row * RB;
+        const uint32_t sw = C == 32 ? (static_cast<uint32_t>((row >> 1) & 3) << 4) : (static_cast<uint32_t>(row & 7) << 4);
+        // the A tile is free: the last MMA1 of the previous tile completed before its bar_h was observed
+#pragma unroll
+        for (int c = 0; c < C / 8; ++c)
+          st_shared_v4(arow + ((c << 4) ^ sw), pack_bf16x2(x[8 * c] * inv, x[8 * c + 1] * inv),
+                       pack_bf16x2(x[8 * c + 2] * inv, x[8 * c + 3] * inv), pack_bf16x2(x[8 * c + 4] * inv, x[8 * c + 5] * inv),
+                       pack_bf16x2(x[8 * c + 6] * inv, x[8 * c + 7] * inv));
+        fence_proxy_async_smem();
+        tc_fence_before();  // this thread's TMEM reads of the previous tile are ordered before the next MMAs
+        mbar_arrive_a(bar_a);
+      }
+      for (int h = 0; h < NH; ++h, ++idx) {
+        mbar_wait_a(bar_h, idx & 1);
         tc_fence_after();
-      }
+        if (h >= 1) {  // the single H tile is free once MMA2_{h-1} has completed (h == 0: waited at the end of the last tile)
+          mbar_wait_a(bar_o, (idx - 1) & 1);
+          tc_fence_after();
+        }
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_base + c4 * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {  // 4 chunks of 8 hidden units
+            const float4 ba = ld_shared_v4_f32(sB + 4 * (h * 128 + c4 * 32 + 8 * c));
+            const float4 bb = ld_shared_v4_f32(sB + 4 * (h * 128 + c4 * 32 + 8 * c + 4));
+            const float bq[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+            float g[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = gelu_tanh_fast(__uint_as_float(r[8 * c + i]) + bq[i]);
+            const int cc = c4 * 4 + c;  // 16-byte chunk index inside the 128-wide row: atom = cc >> 3
+            st_shared_v4(hrow + (cc >> 3) * 16384 + (((cc & 7) << 4) ^ hsw), pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
+                         pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive_a(bar_h2);
+      }
+      mbar_wait_a(bar_o, (idx - 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c4 = 0; c4 < C / 32; ++c4) {
         uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_base + c4 * 32, r);
+        tmem_ld_32x32b_x32(tmem_base + lane_base + Cfg::OUT_COL + c4 * 32, r);
         tmem_ld_wait();
+        if (valid) {
+          float v[32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {  // 4 chunks of 8 hidden units
-          const float4 ba = ld_shared_v4_f32(sB + 4 * (h * 128 + c4 * 32 + 8 * c));
-          const float4 bb = ld_shared_v4_f32(sB + 4 * (h * 128 + c4 * 32 + 8 * c + 4));
-          const float bq[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-          float g[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = gelu_tanh_fast(__uint_as_float(r[8 * c + i]) + bq[i]);
-          const int cc = c4 * 4 + c;  // 16-byte chunk index inside the 128-wide row: atom = cc >> 3
-          st_shared_v4(hrow + (cc >> 3) * 16384 + (((cc & 7) << 4) ^ hsw), pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
-                       pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+          for (int i = 0; i < 8; ++i) {
+            const float4 bq = ld_shared_v4_f32(sB + 4 * (4 * C + c4 * 32 + 4 * i));
+            v[4 * i] = __uint_as_float(r[4 * i]) + bq.x + x[c4 * 32 + 4 * i];
+            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bq.y + x[c4 * 32 + 4 * i + 1];
+            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bq.z + x[c4 * 32 + 4 * i + 2];
+            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bq.w + x[c4 * 32 + 4 * i + 3];
+          }
+          store_act<float, 32>(X + m * C + c4 * 32, v);
+          if (xb_out) store_act<bf16, 32>(xb_out + m * C + c4 * 32, v);
         }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive_a(bar_h2);
-    }
-    mbar_wait_a(bar_o, (NH - 1) & 1);
-    tc_fence_after();
-#pragma unroll
-    for (int c4 = 0; c4 < C / 32; ++c4) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_base + 128 + c4 * 32, r);
-      tmem_ld_wait();
-      if (valid) {
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 bq = ld_shared_v4_f32(sB + 4 * (4 * C + c4 * 32 + 4 * i));
-          v[4 * i] = __uint_as_float(r[4 * i]) + bq.x + x[c4 * 32 + 4 * i];
-          v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bq.y + x[c4 * 32 + 4 * i + 1];
-          v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bq.z + x[c4 * 32 + 4 * i + 2];
-          v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bq.w + x[c4 * 32 + 4 * i + 3];
-        }
-        store_act<float, 32>(X + m * C + c4 * 32, v);
-        if (xb_out) store_act<bf16, 32>(xb_out + m * C + c4 * 32, v);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<256>(tmem_base);
+  if (warp == 4) tmem_dealloc<Cfg::TCOLS>(tmem_base);
 }
 
 struct TcFfPlan {
@@ -1445,7 +1464,9 @@ TcFfPlan* tc_ff_plan_create(const void* w1_bf16, const void* w2_bf16, int C, int
 void tc_ff_plan_destroy(TcFfPlan* p) { delete p; }
 
 int launch_fused_ff(const TcFfPlan* p, float* X, const float* b1, const float* b2, void* xb_out, cudaStream_t st) {
-  const unsigned grid = static_cast<unsigned>((p->M + 127) / 128);
+  const unsigned ntiles = static_cast<unsigned>((p->M + 127) / 128);
+  const unsigned slots = static_cast<unsigned>(g_num_sms) * (p->C == 32 ? FfCfg<32>::CTAS : FfCfg<64>::CTAS);
+  const unsigned grid = ntiles < slots ? ntiles : slots;  // persistent CTAs
   bf16* xb = reinterpret_cast<bf16*>(xb_out);
   if (p->C == 32)
     fused_ff_kernel<32><<<grid, FF_THREADS, FfCfg<32>::SMEM, st>>>(p->tmW1, p->tmW2, X, b1, b2, xb, p->M);
@@ -1484,7 +1505,7 @@ fused_qkv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
   const uint32_t bar_d = bar_a + 8;
   const uint32_t tmem_slot = bar_d + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * 128;
+  const int ntiles = static_cast<int>((M + 127) / 128);  // PERSISTENT: tiles blockIdx.x, +gridDim.x, ... (W fetched once)
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmW);
@@ -1509,19 +1530,24 @@ fused_qkv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
     constexpr uint32_t idesc = make_idesc_bf16(128, 3 * C);
     mbar_expect_tx_p(on, bar_w, Cfg::W_BYTES);
     tma_load_2d_p(on, sW, &tmW, bar_w, 0, 0);
-    mbar_wait_a(bar_a, 0);
     mbar_wait_a(bar_w, 0);
-    tc_fence_after();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      mbar_wait_a(bar_a, it & 1);  // normalised tile in smem, previous accumulator read by every thread
+      tc_fence_after();
 #pragma unroll
-    for (int k = 0; k < C / 16; ++k)
-      umma_bf16_p(on, tmem_base, make_kmajor_desc<Cfg::SWZ>(sA + k * 32), make_kmajor_desc<Cfg::SWZ>(sW + k * 32), idesc,
-                  k != 0 ? 1u : 0u);
-    umma_commit_p(on, bar_d);
+      for (int k = 0; k < C / 16; ++k)
+        umma_bf16_p(on, tmem_base, make_kmajor_desc<Cfg::SWZ>(sA + k * 32), make_kmajor_desc<Cfg::SWZ>(sW + k * 32), idesc,
+                    k != 0 ? 1u : 0u);
+      umma_commit_p(on, bar_d);
+    }
   } else {
     const int row = warp * 32 + lane;
-    const int64_t m = m0 + row;
-    const bool valid = m < M;
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int64_t m = static_cast<int64_t>(tile) * 128 + row;
+    const bool valid = m < M;
     {
       float x[C];
       const float4* xr = reinterpret_cast<const float4*>(X + (valid ? m : 0) * C);
@@ -1555,6 +1581,7 @@ fused_qkv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
         st_shared_v4(arow + ((c << 4) ^ sw), pack_bf16x2(x[8 * c], x[8 * c + 1]), pack_bf16x2(x[8 * c + 2], x[8 * c + 3]),
                      pack_bf16x2(x[8 * c + 4], x[8 * c + 5]), pack_bf16x2(x[8 * c + 6], x[8 * c + 7]));
       fence_proxy_async_smem();
+      tc_fence_before();  // TMEM reads of the previous tile are ordered before the next MMA
       mbar_arrive_a(bar_a);
     }
     // RoPE row of this token (interleaved pairs, rotary_embedding_torch semantics)
@@ -1570,7 +1597,7 @@ fused_qkv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
         sn[4 * i] = b.x; sn[4 * i + 1] = b.y; sn[4 * i + 2] = b.z; sn[4 * i + 3] = b.w;
       }
     }
-    mbar_wait_a(bar_d, 0);
+    mbar_wait_a(bar_d, it & 1);
     tc_fence_after();
 #pragma unroll
     for (int c = 0; c < 3 * C / 32; ++c) {
@@ -1592,6 +1619,7 @@ fused_qkv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
       }
       if (valid) store_act<bf16, 32>(qkv + m * (3 * C) + c * 32, v);
     }
+    }  // tile loop
   }
   tc_fence_before();
   __syncthreads();
@@ -1617,7 +1645,9 @@ void tc_qkv_plan_destroy(TcQkvPlan* p) { delete p; }
 int launch_fused_qkv(const TcQkvPlan* p, const float* X, const float* wg, const float* bg, const float* rope_cos,
                      const float* rope_sin, void* qkv, float* gates, int L, int F, int posmode, float qscale,
                      cudaStream_t st) {
-  const unsigned grid = static_cast<unsigned>((p->M + 127) / 128);
+  const unsigned ntiles = static_cast<unsigned>((p->M + 127) / 128);
+  const unsigned slots = static_cast<unsigned>(g_num_sms) * (p->C == 32 ? 3u : 2u);
+  const unsigned grid = ntiles < slots ? ntiles : slots;  // persistent CTAs
   bf16* q = reinterpret_cast<bf16*>(qkv);
   if (p->C == 32)
     fused_qkv_kernel<32><<<grid, FF_THREADS, QkvCfg<32>::SMEM, st>>>(p->tmW, X, wg, bg, rope_cos, rope_sin, q, gates, p->M, L, F, posmode, qscale);
