@@ -348,7 +348,9 @@ int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool f
       return fail(c, BT_ERR_CUDA, "fused qkv launch failed");
     BT_LAUNCHED(c, "qkv_fused", st);
   } else {
-    const bool gates_in_norm = heads <= 4;  // 1/2/4 heads
+    // heads 1/2 (unfused fallback of blocks 0/1): gates inside the norm kernel; heads >= 4: padded gates GEMM
+    static const int gin_max = getenv("BT_GATES_IN_NORM_MAX") ? atoi(getenv("BT_GATES_IN_NORM_MAX")) : 2;
+    const bool gates_in_norm = heads <= gin_max;
     launch_norm(X, c->XN, M, C, tc, st, gates_in_norm ? c->GATES : nullptr, w.wg->f32, w.bg->f32, heads);
     BT_LAUNCHED(c, gates_in_norm ? "norm_gates" : "norm", st);
     if (!gates_in_norm) {  // gates = sigmoid(to_gates(x_normed)): a [heads -> 32 padded] x C GEMM on the same rows

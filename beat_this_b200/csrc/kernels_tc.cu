@@ -988,6 +988,7 @@ constexpr int A6_SMEM = AT_SQ + A6_NST * (A6_SK + A6_SV) + 1024 + 128;
 constexpr int A6_THREADS = 160;
 constexpr uint32_t A6_TM_O = 64, A6_TM_P = 96;
 
+template <int POLY>  // every POLY-th exponential on the FMA pipe (0: all on MUFU)
 __global__ void __launch_bounds__(A6_THREADS, 4)
 attn_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const float* __restrict__ gates, bf16* __restrict__ out, int L, int heads) {
@@ -1129,7 +1130,10 @@ attn_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int c = 0; c < 8; ++c) {
         float p[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) p[i] = ex2_approx(s[c * 8 + i] - m_ref);
+        for (int i = 0; i < 8; ++i) {
+          const float x = s[c * 8 + i] - m_ref;
+          p[i] = (POLY > 0 && i % (POLY > 0 ? POLY : 1) == (POLY > 0 ? POLY : 1) - 1) ? ex2_poly(x) : ex2_approx(x);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           pk[c * 4 + i] = pack_bf16x2(p[2 * i], p[2 * i + 1]);
@@ -1211,8 +1215,13 @@ int launch_attn_time_tc(const TcAttnPlan* p, const float* gates, void* out, cuda
   // default: 4 CTAs/SM kernel (64-key tiles); BT_ATTN_VARIANT=128 selects the 2-CTAs/SM kernel (128-key tiles)
   static const int variant = getenv("BT_ATTN_VARIANT") ? atoi(getenv("BT_ATTN_VARIANT")) : 64;
   if (variant == 64) {
-    attn_tc64_kernel<<<grid, A6_THREADS, A6_SMEM, st>>>(p->tmQK, p->tmKV64, gates, reinterpret_cast<bf16*>(out), p->L,
-                                                        p->heads);
+    static const int poly64 = getenv("BT_ATTN_POLY") ? atoi(getenv("BT_ATTN_POLY")) : 0;
+    if (poly64 == 8)
+      attn_tc64_kernel<8><<<grid, A6_THREADS, A6_SMEM, st>>>(p->tmQK, p->tmKV64, gates, reinterpret_cast<bf16*>(out), p->L, p->heads);
+    else if (poly64 == 4)
+      attn_tc64_kernel<4><<<grid, A6_THREADS, A6_SMEM, st>>>(p->tmQK, p->tmKV64, gates, reinterpret_cast<bf16*>(out), p->L, p->heads);
+    else
+      attn_tc64_kernel<0><<<grid, A6_THREADS, A6_SMEM, st>>>(p->tmQK, p->tmKV64, gates, reinterpret_cast<bf16*>(out), p->L, p->heads);
     return 0;
   }
   static const int poly = getenv("BT_ATTN_POLY") ? atoi(getenv("BT_ATTN_POLY")) : AT_POLY_MOD;
@@ -1352,17 +1361,34 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
     const uint32_t hrow = sH + row * 128;
     const uint32_t hsw = static_cast<uint32_t>(row & 7) << 4;
     int idx = 0;
+    constexpr bool PREFETCH = C == 32;  // next tile's row requested while this tile is in the MMAs (register budget: C = 32 only)
+    float4 xn[PREFETCH ? C / 4 : 1];
+    auto load_x = [&](int tile, float4* dst) {
+      const int64_t mm = static_cast<int64_t>(tile) * 128 + row;
+      const float4* xr = reinterpret_cast<const float4*>(X + (mm < M ? mm : 0) * C);
+#pragma unroll
+      for (int i = 0; i < C / 4; ++i) dst[i] = mm < M ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if constexpr (PREFETCH) {
+      if (static_cast<int>(blockIdx.x) < ntiles) load_x(blockIdx.x, xn);
+    }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t m = static_cast<int64_t>(tile) * 128 + row;
       const bool valid = m < M;
       // ---- RMSNorm of this token (x stays in registers for the residual) ----
       float x[C];
       {
-        const float4* xr = reinterpret_cast<const float4*>(X + (valid ? m : 0) * C);
+        float4 xq[C / 4];
+        if constexpr (PREFETCH) {
+#pragma unroll
+          for (int i = 0; i < C / 4; ++i) xq[i] = xn[i];
+        } else {
+          load_x(tile, xq);
+        }
         float ss = 0.f;
 #pragma unroll
         for (int i = 0; i < C / 4; ++i) {
-          const float4 q = valid ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 q = xq[i];
           x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
           ss = fmaf(q.x, q.x, ss); ss = fmaf(q.y, q.y, ss); ss = fmaf(q.z, q.z, ss); ss = fmaf(q.w, q.w, ss);
         }
@@ -1379,6 +1405,9 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
         fence_proxy_async_smem();
         tc_fence_before();  // this thread's TMEM reads of the previous tile are ordered before the next MMAs
         mbar_arrive_a(bar_a);
+        if constexpr (PREFETCH) {
+          if (tile + static_cast<int>(gridDim.x) < ntiles) load_x(tile + gridDim.x, xn);
+        }
       }
       for (int h = 0; h < NH; ++h, ++idx) {
         mbar_wait_a(bar_h, idx & 1);
@@ -1545,16 +1574,23 @@ fused_qkv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
     const int row = warp * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
     int it = 0;
+    float4 xn[C / 4];  // next tile's row, requested while this tile is in the MMA / epilogue
+    auto load_x = [&](int tile) {
+      const int64_t mm = static_cast<int64_t>(tile) * 128 + row;
+      const float4* xr = reinterpret_cast<const float4*>(X + (mm < M ? mm : 0) * C);
+#pragma unroll
+      for (int i = 0; i < C / 4; ++i) xn[i] = mm < M ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if (static_cast<int>(blockIdx.x) < ntiles) load_x(blockIdx.x);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int64_t m = static_cast<int64_t>(tile) * 128 + row;
     const bool valid = m < M;
     {
       float x[C];
-      const float4* xr = reinterpret_cast<const float4*>(X + (valid ? m : 0) * C);
       float ss = 0.f;
 #pragma unroll
       for (int i = 0; i < C / 4; ++i) {
-        const float4 q = valid ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 q = xn[i];
         x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
         ss = fmaf(q.x, q.x, ss); ss = fmaf(q.y, q.y, ss); ss = fmaf(q.z, q.z, ss); ss = fmaf(q.w, q.w, ss);
       }
@@ -1583,6 +1619,7 @@ fused_qkv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
       fence_proxy_async_smem();
       tc_fence_before();  // TMEM reads of the previous tile are ordered before the next MMA
       mbar_arrive_a(bar_a);
+      if (tile + static_cast<int>(gridDim.x) < ntiles) load_x(tile + gridDim.x);
     }
     // RoPE row of this token (interleaved pairs, rotary_embedding_torch semantics)
     float cs[16], sn[16];
@@ -1672,7 +1709,9 @@ int tc_init(char* err, int errlen) {
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   cudaFuncSetAttribute(attn_tc_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
   cudaFuncSetAttribute(attn_tc_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-  cudaFuncSetAttribute(attn_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM);
+  cudaFuncSetAttribute(attn_tc64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM);
+  cudaFuncSetAttribute(attn_tc64_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM);
+  cudaFuncSetAttribute(attn_tc64_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM);
   cudaError_t r = cudaFuncSetAttribute(attn_tc_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
   if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<32>::SMEM);
   if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<64>::SMEM);
