@@ -1,6 +1,7 @@
 // HBM-bound kernels of the path: log-mel frontend, stem conv, RMSNorm(+gates),
 // frequency-direction attention, head + aggregation scatter, peak picking.
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #include "bt_kernels.h"
 #include "common.cuh"
@@ -391,6 +392,140 @@ attn_freq_kernel(const TAct* __restrict__ qkv, const float* __restrict__ gates, 
   }
 }
 
+// bf16 path: the same attention on warp-level tensor-core MMAs (mma.sync m16n8k16, fp32 accumulate).
+// A warp stages 32 rows (32/F groups: q | k | v, 64 bytes each) in shared memory with the coalesced
+// row-per-lane loads of the SIMT kernel, then works on two 16-row query tiles: S = Q K^T from
+// ldmatrix fragments, softmax in the accumulator layout (row reductions over the 4 lanes of a quad),
+// P re-packed in registers as the A operand of P V (V through ldmatrix.trans).  F = 32: a tile sees
+// all 32 keys; F = 16: a tile is one group; F = 8: a tile holds two groups, the cross blocks are
+// masked.  ~40 tensor instructions per warp instead of ~4000 FMAs per lane.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int F>
+__global__ void __launch_bounds__(128)
+attn_freq_mma_kernel(const bf16* __restrict__ qkv, const float* __restrict__ gates, bf16* __restrict__ out,
+                     int B, int L, int heads, float scale_log2) {
+  constexpr int GPW = 32 / F;
+  constexpr int RS = 80;  // staged row stride in bytes (64 + 16 pad: conflict-free ldmatrix)
+  constexpr int NT = F == 32 ? 4 : 2;  // 8-key tiles a query tile attends to
+  __shared__ __align__(16) uint8_t stage[4][3][32 * RS];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ngrp = static_cast<int64_t>(B) * L * heads;
+  const int64_t grp0 = (static_cast<int64_t>(blockIdx.x) * 4 + wib) * GPW;
+  if (grp0 >= ngrp) return;  // warp-uniform
+  const int C = heads * 32;
+  auto row_token = [&](int r, int64_t& m, int& h) -> bool {  // staged row r -> token row, head; false: padding group
+    const int64_t grp = grp0 + r / F;
+    const bool act = grp < ngrp;
+    const int64_t gg = act ? grp : grp0;
+    h = static_cast<int>(gg % heads);
+    const int64_t bt_ = gg / heads;
+    const int t = static_cast<int>(bt_ % L);
+    const int b = static_cast<int>(bt_ / L);
+    m = (static_cast<int64_t>(b) * F + (r % F)) * L + t;
+    return act;
+  };
+  const uint32_t sQ = smem_u32(&stage[wib][0][0]), sK = smem_u32(&stage[wib][1][0]), sV = smem_u32(&stage[wib][2][0]);
+  {
+    int64_t m; int h;
+    row_token(lane, m, h);
+    const uint4* rp = reinterpret_cast<const uint4*>(qkv + m * 3 * C + h * 32);
+#pragma unroll
+    for (int part = 0; part < 3; ++part) {
+      const uint4* src = rp + part * (C / 8);
+      uint4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = src[i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        st_shared_v4(sQ + part * (32 * RS) + lane * RS + 16 * i, v[i].x, v[i].y, v[i].z, v[i].w);
+    }
+  }
+  __syncwarp();
+  const int g = lane >> 2, c = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int key_base = F == 32 ? 0 : 16 * mt;
+    uint32_t qa[2][4];
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk)
+      ldsm_x4(sQ + (16 * mt + (lane & 7) + ((lane >> 3) & 1) * 8) * RS + (kk * 16 + (lane >> 4) * 8) * 2, qa[kk]);
+    float sc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+      uint32_t kb[4];
+      ldsm_x4(sK + (key_base + 8 * j + (lane & 7)) * RS + ((lane >> 3) * 8) * 2, kb);
+      mma_bf16_16816(sc[j], qa[0], kb[0], kb[1]);
+      mma_bf16_16816(sc[j], qa[1], kb[2], kb[3]);
+    }
+    if (F == 8) {  // rows 0-7 belong to the tile's first group (keys of tile 0), rows 8-15 to the second
+      sc[1][0] = sc[1][1] = -INFINITY;
+      sc[0][2] = sc[0][3] = -INFINITY;
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      mx0 = fmaxf(mx0, fmaxf(sc[j][0], sc[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(sc[j][2], sc[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      sc[j][0] = exp2f((sc[j][0] - mx0) * scale_log2); sc[j][1] = exp2f((sc[j][1] - mx0) * scale_log2);
+      sc[j][2] = exp2f((sc[j][2] - mx1) * scale_log2); sc[j][3] = exp2f((sc[j][3] - mx1) * scale_log2);
+      l0 += sc[j][0] + sc[j][1];
+      l1 += sc[j][2] + sc[j][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    float o[4][4];
+#pragma unroll
+    for (int jd = 0; jd < 4; ++jd) o[jd][0] = o[jd][1] = o[jd][2] = o[jd][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NT / 2; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(sc[2 * kk][0], sc[2 * kk][1]);
+      pa[1] = pack_bf16x2(sc[2 * kk][2], sc[2 * kk][3]);
+      pa[2] = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+      pa[3] = pack_bf16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+#pragma unroll
+      for (int jd = 0; jd < 4; jd += 2) {
+        uint32_t vb[4];
+        const int q4 = lane >> 3;
+        ldsm_x4_trans(sV + (key_base + 16 * kk + (q4 & 1) * 8 + (lane & 7)) * RS + (8 * (jd + (q4 >> 1))) * 2, vb);
+        mma_bf16_16816(o[jd], pa, vb[0], vb[1]);
+        mma_bf16_16816(o[jd + 1], pa, vb[2], vb[3]);
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      int64_t m; int h;
+      if (row_token(16 * mt + g + 8 * half, m, h)) {
+        const float gsc = gates[m * heads + h] / (half == 0 ? l0 : l1);
+        uint32_t* op = reinterpret_cast<uint32_t*>(out + m * C + h * 32);
+#pragma unroll
+        for (int jd = 0; jd < 4; ++jd)
+          op[4 * jd + c] = pack_bf16x2(o[jd][2 * half] * gsc, o[jd][2 * half + 1] * gsc);
+      }
+    }
+  }
+}
+
 template <typename TAct>
 static void attn_freq_dispatch(const void* qkv, const float* gates, void* out, int B, int F, int L, int heads,
                                float scale, cudaStream_t st) {
@@ -405,6 +540,18 @@ static void attn_freq_dispatch(const void* qkv, const float* gates, void* out, i
 
 void launch_attn_freq(const void* qkv, const float* gates, void* out, int B, int F, int L, int heads,
                       float scale, int act_bf16, cudaStream_t st) {
+  static const bool simt = getenv("BT_ATTN_FREQ_SIMT") && atoi(getenv("BT_ATTN_FREQ_SIMT")) != 0;
+  if (act_bf16 && !simt && (F == 32 || F == 16 || F == 8)) {
+    const int64_t ngrp = static_cast<int64_t>(B) * L * heads;
+    const unsigned grid = static_cast<unsigned>(ceil_div64(ngrp, 4 * (32 / F)));
+    const bf16* q = reinterpret_cast<const bf16*>(qkv);
+    bf16* o = reinterpret_cast<bf16*>(out);
+    const float sl2 = scale * 1.4426950408889634f;
+    if (F == 32) attn_freq_mma_kernel<32><<<grid, 128, 0, st>>>(q, gates, o, B, L, heads, sl2);
+    else if (F == 16) attn_freq_mma_kernel<16><<<grid, 128, 0, st>>>(q, gates, o, B, L, heads, sl2);
+    else attn_freq_mma_kernel<8><<<grid, 128, 0, st>>>(q, gates, o, B, L, heads, sl2);
+    return;
+  }
   if (act_bf16) attn_freq_dispatch<bf16>(qkv, gates, out, B, F, L, heads, scale, st);
   else attn_freq_dispatch<float>(qkv, gates, out, B, F, L, heads, scale, st);
 }
