@@ -33,7 +33,7 @@ struct FfW { const Param *w1, *b1, *w2, *b2; };
 
 // tensor-core plans for one (wave size, chunk length) geometry
 struct AttnPlans { TcGemmPlan *qkv = nullptr, *out = nullptr, *gates = nullptr; TcAttnPlan* attn = nullptr; TcQkvPlan* fqkv = nullptr; };
-struct FfPlans { TcGemmPlan *ff1 = nullptr, *ff2 = nullptr; TcFfPlan* fused = nullptr; };
+struct FfPlans { TcGemmPlan *ff1 = nullptr, *ff2 = nullptr; TcFfPlan *fused = nullptr, *fused_op = nullptr; };
 struct WavePlans {
   AttnPlans fa[3], ta[3];
   FfPlans ff_f[3], ff_t[3];
@@ -57,6 +57,7 @@ struct bt_ctx {
   int64_t launches = 0;
   bool sync_debug = false;
   bool fuse_ff = true;  // BT_FUSE_FF=0 falls back to norm + two GEMMs for the narrow frontend FFNs
+  bool fuse_outproj = true;  // BT_FUSE_OUTPROJ=0: separate attention out-projection GEMM in front of the fused FFN
 
   // workspace: sized for ws_wave chunks of BT_CHUNK frames; grows on demand up to `wave`
   int wave = 128;
@@ -237,6 +238,7 @@ void free_plans(bt_ctx* c) {
     };
     auto ff = [](FfPlans& f) {
       if (f.fused) tc_ff_plan_destroy(f.fused);
+      if (f.fused_op) tc_ff_plan_destroy(f.fused_op);
       if (f.ff1) tc_gemm_plan_destroy(f.ff1);
       if (f.ff2) tc_gemm_plan_destroy(f.ff2);
     };
@@ -333,8 +335,9 @@ EpiParams epi_generic(const Param* bias, int gelu, const float* resid, int ldr, 
 
 // x += attention(x) over `planes` planes of L tokens with dim C (reference roformer.py:114-132).
 // freq == true: sequences run over the F planes of each chunk (PartialFTTransformer attnF).
+// skip_out: the out-projection + residual are done by the following fused FFN kernel (fused_ff_kernel<C, true>).
 int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool freq, const AttnW& w,
-                    AttnPlans* tp, int nb, cudaStream_t st) {
+                    AttnPlans* tp, int nb, cudaStream_t st, bool skip_out = false) {
   const bool tc = c->dtype == BT_DTYPE_BF16;
   const int heads = C / kHeadDim;
   const int64_t M = static_cast<int64_t>(planes) * L;
@@ -385,6 +388,7 @@ int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool f
                           planes, L, heads, st);
     BT_LAUNCHED(c, "attn_time_simt", st);
   }
+  if (skip_out) return BT_OK;
   GemmShape go = plain_shape(planes, L, C, C, C);
   EpiParams eo = epi_generic(nullptr, 0, X, C, X, C, nullptr, 0);
   return run_gemm(c, c->O, w.wout, tp ? tp->out : nullptr, go, eo, "gemm_attn_out", st);
@@ -392,11 +396,13 @@ int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool f
 
 // x += ff(x) (reference roformer.py:38-61); optionally also writes a bf16 copy of the result.
 int ff_block(bt_ctx* c, float* X, int planes, int L, int C, int mult, const FfW& w, FfPlans* tp, void* copy_act,
-             cudaStream_t st) {
+             cudaStream_t st, bool with_outproj = false) {
   const bool tc = c->dtype == BT_DTYPE_BF16;
   const int64_t M = static_cast<int64_t>(planes) * L;
+  if (with_outproj && !(tc && tp && tp->fused_op)) return fail(c, BT_ERR_ARG, "fused out-projection requested without a plan");
   if (tc && tp && tp->fused) {
-    if (launch_fused_ff(tp->fused, X, w.b1->f32, w.b2->f32, copy_act, st) != 0) return fail(c, BT_ERR_CUDA, "fused ff launch failed");
+    if (launch_fused_ff(with_outproj ? tp->fused_op : tp->fused, X, w.b1->f32, w.b2->f32, copy_act, st) != 0)
+      return fail(c, BT_ERR_CUDA, "fused ff launch failed");
     BT_LAUNCHED(c, "ff_fused", st);
     return BT_OK;
   }
@@ -463,10 +469,12 @@ int build_plans(bt_ctx* c, int nb, int L, WavePlans** out) {
     }
     return true;
   };
-  auto mk_ff = [&](FfPlans& f, const FfW& fw, int planes, int C, int mult) -> bool {
+  auto mk_ff = [&](FfPlans& f, const FfW& fw, int planes, int C, int mult, const Param* wout = nullptr) -> bool {
     if (c->fuse_ff && mult == 4 && (C == 32 || C == 64)) {  // narrow frontend FFNs: one fused kernel
-      f.fused = tc_ff_plan_create(fw.w1->b16, fw.w2->b16, C, static_cast<int64_t>(planes) * L, err, sizeof(err));
-      return f.fused != nullptr;
+      f.fused = tc_ff_plan_create(fw.w1->b16, fw.w2->b16, C, static_cast<int64_t>(planes) * L, nullptr, nullptr, err, sizeof(err));
+      if (f.fused && wout && c->fuse_outproj)  // ... and one with the preceding attention's out-projection in front
+        f.fused_op = tc_ff_plan_create(fw.w1->b16, fw.w2->b16, C, static_cast<int64_t>(planes) * L, c->O, wout->b16, err, sizeof(err));
+      return f.fused != nullptr && (!(wout && c->fuse_outproj) || f.fused_op != nullptr);
     }
     f.ff1 = mk(c->XN, fw.w1, plain_shape(planes, L, mult * C, C, C), planes);
     f.ff2 = mk(c->H, fw.w2, plain_shape(planes, L, C, mult * C, mult * C), planes);
@@ -478,9 +486,9 @@ int build_plans(bt_ctx* c, int nb, int L, WavePlans** out) {
     const std::string p = "b" + std::to_string(i);
     if (c->hp.partial_transformers) {
       ok = ok && mk_attn(w->fa[i], attn_w(c, p + ".attnF"), nb * F, C, true);
-      ok = ok && mk_ff(w->ff_f[i], ff_w(c, p + ".ffF"), nb * F, C, 4);
+      ok = ok && mk_ff(w->ff_f[i], ff_w(c, p + ".ffF"), nb * F, C, 4, attn_w(c, p + ".attnF").wout);
       ok = ok && mk_attn(w->ta[i], attn_w(c, p + ".attnT"), nb * F, C, false);
-      ok = ok && mk_ff(w->ff_t[i], ff_w(c, p + ".ffT"), nb * F, C, 4);
+      ok = ok && mk_ff(w->ff_t[i], ff_w(c, p + ".ffT"), nb * F, C, 4, attn_w(c, p + ".attnT").wout);
     }
     if (ok) {
       w->conv[i] = mk(c->XB, find_param(c, p + ".conv.w"), conv_shape(nb, F, L, C), nb * F);
@@ -529,13 +537,17 @@ int run_wave(bt_ctx* c, const float* spect, const Wave& wv, float* beat, float* 
     const int64_t elems = static_cast<int64_t>(planes) * L * C;
     void* copy_for_conv = tc ? c->XB : nullptr;
     if (c->hp.partial_transformers) {
-      if ((r = attention_block(c, X, planes, L, C, F, true, attn_w(c, p + ".attnF"), wp ? &wp->fa[i] : nullptr, nb, st)) != BT_OK) return r;
+      // out-projection + residual of an attention move into the following fused FFN kernel when there is a plan
+      // for it (C = 32 / 64) and nobody asked to see the intermediate residual stream (debug tap)
+      const bool op_f = wp && wp->ff_f[i].fused_op && c->tap_name != p + ".attnF";
+      const bool op_t = wp && wp->ff_t[i].fused_op && c->tap_name != p + ".attnT";
+      if ((r = attention_block(c, X, planes, L, C, F, true, attn_w(c, p + ".attnF"), wp ? &wp->fa[i] : nullptr, nb, st, op_f)) != BT_OK) return r;
       if ((r = do_tap(c, (p + ".attnF").c_str(), X, elems, false, st)) != BT_OK) return r;
-      if ((r = ff_block(c, X, planes, L, C, 4, ff_w(c, p + ".ffF"), wp ? &wp->ff_f[i] : nullptr, nullptr, st)) != BT_OK) return r;
+      if ((r = ff_block(c, X, planes, L, C, 4, ff_w(c, p + ".ffF"), wp ? &wp->ff_f[i] : nullptr, nullptr, st, op_f)) != BT_OK) return r;
       if ((r = do_tap(c, (p + ".ffF").c_str(), X, elems, false, st)) != BT_OK) return r;
-      if ((r = attention_block(c, X, planes, L, C, F, false, attn_w(c, p + ".attnT"), wp ? &wp->ta[i] : nullptr, nb, st)) != BT_OK) return r;
+      if ((r = attention_block(c, X, planes, L, C, F, false, attn_w(c, p + ".attnT"), wp ? &wp->ta[i] : nullptr, nb, st, op_t)) != BT_OK) return r;
       if ((r = do_tap(c, (p + ".attnT").c_str(), X, elems, false, st)) != BT_OK) return r;
-      if ((r = ff_block(c, X, planes, L, C, 4, ff_w(c, p + ".ffT"), wp ? &wp->ff_t[i] : nullptr, copy_for_conv, st)) != BT_OK) return r;
+      if ((r = ff_block(c, X, planes, L, C, 4, ff_w(c, p + ".ffT"), wp ? &wp->ff_t[i] : nullptr, copy_for_conv, st, op_t)) != BT_OK) return r;
       if ((r = do_tap(c, (p + ".ffT").c_str(), X, elems, false, st)) != BT_OK) return r;
     } else if (tc) {
       launch_f32_to_bf16(X, c->XB, elems, st);
@@ -641,6 +653,8 @@ int bt_create(bt_ctx** out, int device_ordinal, const bt_hparams* hp, int comput
   c->sync_debug = dbg && dbg[0] == '1';
   const char* ffe = getenv("BT_FUSE_FF");
   c->fuse_ff = !(ffe && ffe[0] == '0');
+  const char* foe = getenv("BT_FUSE_OUTPROJ");
+  c->fuse_outproj = !(foe && foe[0] == '0');
 
   if (cudaEventCreateWithFlags(&c->stage_ev, cudaEventDisableTiming) != cudaSuccess) {
     delete c;

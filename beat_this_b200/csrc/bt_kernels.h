@@ -104,7 +104,8 @@ int launch_attn_time_tc(const TcAttnPlan* plan, const float* gates, void* out_bf
 
 // fused RMSNorm + FFN + residual for C in {32, 64} (frontend), x updated in place (+ optional bf16 copy)
 struct TcFfPlan;
-TcFfPlan* tc_ff_plan_create(const void* w1_bf16, const void* w2_bf16, int C, int64_t M, char* err, int errlen);
+TcFfPlan* tc_ff_plan_create(const void* w1_bf16, const void* w2_bf16, int C, int64_t M, const void* o_bf16,
+                            const void* wout_bf16, char* err, int errlen);
 void tc_ff_plan_destroy(TcFfPlan*);
 int launch_fused_ff(const TcFfPlan* plan, float* X, const float* b1, const float* b2, void* xb_out, cudaStream_t st);
 

@@ -1253,18 +1253,26 @@ struct FfCfg {
   static constexpr int W1_BYTES = 4 * C * C * 2;    // all chunks resident
   static constexpr int W2C_BYTES = C * 128 * 2;     // one K-chunk of W2
   static constexpr int H_BYTES = 128 * 128 * 2;
-  static constexpr int SMEM = A_BYTES + W1_BYTES + W2C_BYTES + H_BYTES + 5 * C * 4 + 1024 + 128;
+  static constexpr int WO_BYTES = C * C * 2;       // attention out-projection weight (fused_ff_kernel<C, true>)
+  static constexpr int SMEM = A_BYTES + W1_BYTES + W2C_BYTES + H_BYTES + WO_BYTES + 5 * C * 4 + 1024 + 128;
   static constexpr int SWZ_A = C * 2 < 128 ? C * 2 : 128;  // 64-byte rows for C=32, 128 for C=64
   // TMEM: H accumulator [0,128) and OUT accumulator.  With a single hidden chunk (C = 32) OUT reuses the H
   // columns (every thread has read H before MMA2 is issued) -> 128 columns, 3 CTAs/SM instead of 2.
   static constexpr int OUT_COL = NH == 1 ? 0 : 128;
   static constexpr int TCOLS = NH == 1 ? 128 : 256;
   static constexpr int CTAS = NH == 1 ? 3 : 2;
+  // accumulator of the optional out-projection prologue (O Wo^T): columns that are dead at that point
+  static constexpr int D0_COL = NH == 1 ? 64 : 0;
 };
 
-template <int C>
+// OP = true: the attention out-projection is fused in front (reference roformer.py:134-140 followed by
+// roformer.py:38-61): x' = x + O Wo^T is computed per tile by one more MMA (the gated attention output O is
+// TMA-loaded into the A-tile buffer, which the normalised x' overwrites afterwards), then the FFN runs on x'.
+// Saves the separate out-projection GEMM: one fp32 read + write of the residual stream per element.
+template <int C, bool OP>
 __global__ void __launch_bounds__(FF_THREADS, FfCfg<C>::CTAS)
 fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWo,
                 float* __restrict__ X, const float* __restrict__ b1, const float* __restrict__ b2,
                 bf16* __restrict__ xb_out, int64_t M) {
   // PERSISTENT: each CTA walks over token tiles (stride gridDim.x); W1 (and W2 when it is a single chunk) are
@@ -1278,14 +1286,17 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
   const uint32_t sW1 = sA + Cfg::A_BYTES;
   const uint32_t sW2 = sW1 + Cfg::W1_BYTES;
   const uint32_t sH = sW2 + Cfg::W2C_BYTES;
-  const uint32_t sB = sH + Cfg::H_BYTES;          // b1[4C] | b2[C] fp32
+  const uint32_t sWo = sH + Cfg::H_BYTES;
+  const uint32_t sB = sWo + Cfg::WO_BYTES;        // b1[4C] | b2[C] fp32
   const uint32_t bar_w1 = sB + 5 * C * 4;
   const uint32_t bar_w2 = bar_w1 + 8;
   const uint32_t bar_a = bar_w2 + 8;
   const uint32_t bar_h = bar_a + 8;
   const uint32_t bar_h2 = bar_h + 8;
   const uint32_t bar_o = bar_h2 + 8;
-  const uint32_t tmem_slot = bar_o + 8;
+  const uint32_t bar_of = bar_o + 8;              // O tile landed in the A buffer (OP)
+  const uint32_t bar_d0 = bar_of + 8;             // O Wo^T accumulated (OP)
+  const uint32_t tmem_slot = bar_d0 + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = static_cast<int>((M + 127) / 128);
 
@@ -1296,6 +1307,7 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
     };
     init(bar_w1, 1); init(bar_w2, 1); init(bar_a, 128); init(bar_h, 1); init(bar_h2, 128); init(bar_o, 1);
+    init(bar_of, 1); init(bar_d0, 1);
     fence_barrier_init();
   }
   if (warp == 4) {
@@ -1315,8 +1327,16 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
     constexpr uint32_t idesc1 = make_idesc_bf16(128, 128);
     constexpr uint32_t idesc2 = make_idesc_bf16(128, C);
     // weights: W1 [4C, C] all chunks (boxes of 128 rows), W2 [C, 4C] one K-chunk at a time (two 64-wide boxes)
-    mbar_expect_tx_p(on, bar_w1, Cfg::W1_BYTES);
+    mbar_expect_tx_p(on, bar_w1, Cfg::W1_BYTES + (OP ? Cfg::WO_BYTES : 0));
     for (int h = 0; h < NH; ++h) tma_load_2d_p(on, sW1 + h * (128 * C * 2), &tmW1, bar_w1, 0, h * 128);
+    if constexpr (OP) tma_load_2d_p(on, sWo, &tmWo, bar_w1, 0, 0);
+    auto load_o = [&](int tile) {  // gated attention output rows of a tile -> the A buffer (same box / swizzle)
+      mbar_expect_tx_p(on, bar_of, Cfg::A_BYTES);
+      tma_load_2d_p(on, sA, &tmO, bar_of, 0, tile * 128);
+    };
+    if constexpr (OP) {
+      if (static_cast<int>(blockIdx.x) < ntiles) load_o(blockIdx.x);
+    }
     auto load_w2 = [&](int h) {
       mbar_expect_tx_p(on, bar_w2, Cfg::W2C_BYTES);
       for (int a = 0; a < 2; ++a) tma_load_2d_p(on, sW2 + a * (C * 128), &tmW2, bar_w2, h * 128 + a * 64, 0);
@@ -1334,6 +1354,16 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
     int w2_loads = 0; // completed-or-in-flight W2 chunk loads minus one: parity of bar_w2
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      if constexpr (OP) {  // D0 = O Wo^T into columns that nobody reads at this point
+        constexpr uint32_t idesc0 = make_idesc_bf16(128, C);
+        mbar_wait_a(bar_of, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < C / 16; ++k)
+          umma_bf16_p(on, tmem_base + Cfg::D0_COL, make_kmajor_desc<Cfg::SWZ_A>(sA + k * 32),
+                      make_kmajor_desc<Cfg::SWZ_A>(sWo + k * 32), idesc0, k != 0 ? 1u : 0u);
+        umma_commit_p(on, bar_d0);
+      }
       mbar_wait_a(bar_a, it & 1);  // normalised tile in smem (and every thread is done with the previous tile's TMEM)
       tc_fence_after();
       issue_mma1(0);
@@ -1341,6 +1371,9 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
         mbar_wait_a(bar_h2, idx & 1);  // bf16 H_h tile written, accumulator H consumed
         tc_fence_after();
         if (h + 1 < NH) issue_mma1(h + 1);
+        if constexpr (OP) {  // the last MMA1 of this tile has completed (its H was read): the A buffer is free
+          if (h == NH - 1 && tile + static_cast<int>(gridDim.x) < ntiles) load_o(tile + gridDim.x);
+        }
         if (NH > 1 || idx == 0) mbar_wait_a(bar_w2, w2_loads & 1);
         tc_fence_after();
 #pragma unroll
@@ -1360,7 +1393,7 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
     const uint32_t hrow = sH + row * 128;
     const uint32_t hsw = static_cast<uint32_t>(row & 7) << 4;
-    int idx = 0;
+    int idx = 0, it = 0;
     constexpr bool PREFETCH = C == 32;  // next tile's row requested while this tile is in the MMAs (register budget: C = 32 only)
     float4 xn[PREFETCH ? C / 4 : 1];
     auto load_x = [&](int tile, float4* dst) {
@@ -1372,7 +1405,7 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
     if constexpr (PREFETCH) {
       if (static_cast<int>(blockIdx.x) < ntiles) load_x(blockIdx.x, xn);
     }
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int64_t m = static_cast<int64_t>(tile) * 128 + row;
       const bool valid = m < M;
       // ---- RMSNorm of this token (x stays in registers for the residual) ----
@@ -1385,13 +1418,26 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
         } else {
           load_x(tile, xq);
         }
-        float ss = 0.f;
 #pragma unroll
         for (int i = 0; i < C / 4; ++i) {
           const float4 q = xq[i];
           x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
-          ss = fmaf(q.x, q.x, ss); ss = fmaf(q.y, q.y, ss); ss = fmaf(q.z, q.z, ss); ss = fmaf(q.w, q.w, ss);
         }
+        if constexpr (OP) {  // x' = x + O Wo^T (attention residual)
+          mbar_wait_a(bar_d0, it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c4 = 0; c4 < C / 32; ++c4) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_base + Cfg::D0_COL + c4 * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[c4 * 32 + i] += __uint_as_float(r[i]);
+          }
+        }
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < C; ++i) ss = fmaf(x[i], x[i], ss);
         const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
         constexpr int RB = C * 2;  // bytes per A row
         const uint32_t arow = sA + row * RB;
@@ -1467,26 +1513,48 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
 }
 
 struct TcFfPlan {
-  CUtensorMap tmW1, tmW2;
+  CUtensorMap tmW1, tmW2, tmO, tmWo;
   int C;
   int64_t M;
+  bool outproj;
 };
 
-TcFfPlan* tc_ff_plan_create(const void* w1_bf16, const void* w2_bf16, int C, int64_t M, char* err, int errlen) {
+// o_bf16 / wout_bf16 != nullptr: plan for the variant with the attention out-projection fused in front
+// (o_bf16: gated attention output [M, C], wout_bf16: [C, C]).
+TcFfPlan* tc_ff_plan_create(const void* w1_bf16, const void* w2_bf16, int C, int64_t M, const void* o_bf16,
+                            const void* wout_bf16, char* err, int errlen) {
   if (C != 32 && C != 64) { snprintf(err, errlen, "fused ff: C must be 32 or 64"); return nullptr; }
   TcFfPlan* p = new TcFfPlan();
-  p->C = C; p->M = M;
+  p->C = C; p->M = M; p->outproj = o_bf16 != nullptr && wout_bf16 != nullptr;
+  const uint32_t swz_a = C * 2 < 128 ? C * 2 : 128;
   {  // W1 [4C, C] row-major: box = {C, 128 rows}
     const uint64_t dims[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(4 * C)};
     const uint64_t strides[1] = {static_cast<uint64_t>(C) * 2};
     const uint32_t box[2] = {static_cast<uint32_t>(C), 128};
-    if (!make_tmap(&p->tmW1, w1_bf16, 2, dims, strides, box, C * 2 < 128 ? C * 2 : 128, err, errlen)) { delete p; return nullptr; }
+    if (!make_tmap(&p->tmW1, w1_bf16, 2, dims, strides, box, swz_a, err, errlen)) { delete p; return nullptr; }
   }
   {  // W2 [C, 4C] row-major: box = {64 K, C rows}
     const uint64_t dims[2] = {static_cast<uint64_t>(4 * C), static_cast<uint64_t>(C)};
     const uint64_t strides[1] = {static_cast<uint64_t>(4 * C) * 2};
     const uint32_t box[2] = {64, static_cast<uint32_t>(C)};
     if (!make_tmap(&p->tmW2, w2_bf16, 2, dims, strides, box, 128, err, errlen)) { delete p; return nullptr; }
+  }
+  if (p->outproj) {
+    {  // O [M, C] row-major: box = {C, 128 tokens}, same swizzle as the hand-written A tile
+      const uint64_t dims[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(M)};
+      const uint64_t strides[1] = {static_cast<uint64_t>(C) * 2};
+      const uint32_t box[2] = {static_cast<uint32_t>(C), 128};
+      if (!make_tmap(&p->tmO, o_bf16, 2, dims, strides, box, swz_a, err, errlen)) { delete p; return nullptr; }
+    }
+    {  // Wo [C, C] row-major
+      const uint64_t dims[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(C)};
+      const uint64_t strides[1] = {static_cast<uint64_t>(C) * 2};
+      const uint32_t box[2] = {static_cast<uint32_t>(C), static_cast<uint32_t>(C)};
+      if (!make_tmap(&p->tmWo, wout_bf16, 2, dims, strides, box, swz_a, err, errlen)) { delete p; return nullptr; }
+    }
+  } else {
+    p->tmO = p->tmW1;  // never dereferenced
+    p->tmWo = p->tmW1;
   }
   return p;
 }
@@ -1497,10 +1565,12 @@ int launch_fused_ff(const TcFfPlan* p, float* X, const float* b1, const float* b
   const unsigned slots = static_cast<unsigned>(g_num_sms) * (p->C == 32 ? FfCfg<32>::CTAS : FfCfg<64>::CTAS);
   const unsigned grid = ntiles < slots ? ntiles : slots;  // persistent CTAs
   bf16* xb = reinterpret_cast<bf16*>(xb_out);
-  if (p->C == 32)
-    fused_ff_kernel<32><<<grid, FF_THREADS, FfCfg<32>::SMEM, st>>>(p->tmW1, p->tmW2, X, b1, b2, xb, p->M);
-  else
-    fused_ff_kernel<64><<<grid, FF_THREADS, FfCfg<64>::SMEM, st>>>(p->tmW1, p->tmW2, X, b1, b2, xb, p->M);
+#define BT_FF_L(CC, OPP)                                                                                          \
+  fused_ff_kernel<CC, OPP><<<grid, FF_THREADS, FfCfg<CC>::SMEM, st>>>(p->tmW1, p->tmW2, p->tmO, p->tmWo, X, b1, b2, xb, \
+                                                                      p->M)
+  if (p->C == 32) { if (p->outproj) BT_FF_L(32, true); else BT_FF_L(32, false); }
+  else { if (p->outproj) BT_FF_L(64, true); else BT_FF_L(64, false); }
+#undef BT_FF_L
   return 0;
 }
 
@@ -1713,8 +1783,10 @@ int tc_init(char* err, int errlen) {
   cudaFuncSetAttribute(attn_tc64_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM);
   cudaFuncSetAttribute(attn_tc64_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM);
   cudaError_t r = cudaFuncSetAttribute(attn_tc_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-  if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<32>::SMEM);
-  if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<64>::SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<32>::SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<64>::SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<32>::SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<64>::SMEM);
   if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_qkv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, QkvCfg<32>::SMEM);
   if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_qkv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, QkvCfg<64>::SMEM);
   if (r != cudaSuccess) {

@@ -113,6 +113,28 @@ def test_ragged_batch_vs_oracle(small0_ckpt, lib_built, float16):
     assert worst < (BF16_TOL if float16 else F32_TOL)
 
 
+@pytest.mark.parametrize("float16", [False, True])
+def test_wave_size_does_not_change_results(small0_ckpt, lib_built, float16):
+    """Chunks are processed in waves of equal-length chunks (bt_set_wave_chunks): 1-, 2- and 128-chunk waves
+    over a ragged batch (9 chunks of two lengths) must give bit-identical logits -- every chunk is independent
+    and the persistent kernels walk the tiles in a fixed order."""
+    from beat_this_b200 import synthetic
+    from beat_this_b200.inference import Audio2Frames
+
+    secs = [61.3, 5.0, 30.0, 95.0, 12.34]
+    clips = [synthetic.synth_clip(30 + i, s) for i, s in enumerate(secs)]
+    a2f = Audio2Frames(small0_ckpt, "cuda:0", float16)
+    ref = None
+    for wave in (128, 2, 1):
+        a2f.model.engine.set_wave_chunks(wave)
+        out = [(b.cpu().clone(), d.cpu().clone()) for b, d in a2f.batch(clips, 22050)]
+        if ref is None:
+            ref = out
+            continue
+        for (b, d), (rb, rd) in zip(out, ref):
+            assert torch.equal(b, rb) and torch.equal(d, rd), wave
+
+
 def test_no_cpu_fallback(small0_ckpt, lib_built):
     from beat_this_b200.inference import Spect2Frames
 

@@ -17,6 +17,7 @@ VARIANTS = [
     {"BT_ATTN_POLY": "8"},                            # default kernel with polynomial exp2 share
     {"BT_ATTN_FREQ_SIMT": "1"},                       # CUDA-core frequency attention
     {"BT_FUSE_FF": "0"},                              # unfused frontend blocks (norm + GEMMs)
+    {"BT_FUSE_OUTPROJ": "0"},                         # separate attention out-projection GEMM in front of the fused FFN
     {"BT_GATES_IN_NORM_MAX": "4"},                    # gates of the 4-head block inside the norm kernel
 ]
 
