@@ -45,6 +45,10 @@ PROTOTYPES = {
     "bt_num_frames": (c_int64, [c_int64]),
     "bt_plan_chunks": (c_int64, [c_int64, POINTER(c_int64), POINTER(c_int64), c_int64]),
     "bt_logmel": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, POINTER(c_int64), c_void_p]),
+    "bt_resample": (
+        c_int,
+        [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, POINTER(c_int64), c_void_p],
+    ),
     "bt_spect2frames": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_void_p, c_void_p]),
     "bt_audio2frames": (
         c_int,

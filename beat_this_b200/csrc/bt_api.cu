@@ -579,7 +579,7 @@ int run_wave(bt_ctx* c, const float* spect, const Wave& wv, float* beat, float* 
     if ((r = ff_block(c, X, nb, L, D, c->hp.ff_mult, ff_w(c, p + ".ff"), wp ? &wp->lf[l] : nullptr, nullptr, st)) != BT_OK) return r;
     if ((r = do_tap(c, (p + ".ff").c_str(), X, static_cast<int64_t>(nb) * L * D, false, st)) != BT_OK) return r;
   }
-  launch_head(X, D, find_param(c, "head.w")->f32, find_param(c, "head.b")->f32, wv.chunks_dev, nb, L, beat, down, st);
+  launch_head(X, D, find_param(c, "head.w")->f32, find_param(c, "head.b")->f32, wv.chunks_dev, nb, L, beat, down, c->hp.sum_head ? 1 : 0, st);
   BT_LAUNCHED(c, "head", st);
   return BT_OK;
 }
@@ -627,10 +627,10 @@ int bt_create(bt_ctx** out, int device_ordinal, const bt_hparams* hp, int comput
     return fail(nullptr, BT_ERR_ARG, "bt_create: compute_dtype must be BT_DTYPE_F32 or BT_DTYPE_BF16");
   if (hp->spect_dim != 128 || hp->head_dim != 32 || hp->stem_dim != 32 || hp->transformer_dim % 64 != 0 ||
       hp->transformer_dim < 64 || hp->transformer_dim > 1024 || hp->n_layers < 1 || hp->ff_mult < 1 ||
-      hp->ff_mult > 4 || !hp->sum_head)
+      hp->ff_mult > 4)
     return fail(nullptr, BT_ERR_ARG,
                 "bt_create: unsupported hyper-parameters (need spect_dim 128, head_dim 32, stem_dim 32, "
-                "transformer_dim multiple of 64 in [64,1024], sum_head)");
+                "transformer_dim multiple of 64 in [64,1024], ff_mult <= 4)");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -870,6 +870,37 @@ int bt_logmel(bt_ctx* c, const float* audio_dev, const int64_t* sample_offsets_h
                 find_param(c, "mel.twiddle")->f32, find_param(c, "mel.fb_start")->i32,
                 find_param(c, "mel.fb_ptr")->i32, find_param(c, "mel.fb_w")->f32, spect_dev, st);
   BT_LAUNCHED(c, "logmel", st);
+  return BT_OK;
+}
+
+int bt_resample(bt_ctx* c, const float* audio_in_dev, const int64_t* in_offsets_host, int32_t n_clips,
+                const float* coef_dev, int32_t L, int32_t M, int32_t K, float* audio_out_dev,
+                const int64_t* out_offsets_host, void* stream) {
+  if (!c) return BT_ERR_ARG;
+  if (n_clips <= 0) return BT_OK;
+  if (!audio_in_dev || !in_offsets_host || !coef_dev || !audio_out_dev || !out_offsets_host)
+    return fail(c, BT_ERR_ARG, "bt_resample: null argument");
+  if (L <= 0 || M <= 0 || K <= 0 || (K & 1)) return fail(c, BT_ERR_ARG, "bt_resample: need L, M > 0 and an even K > 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BT_CUDA(c, cudaSetDevice(c->device));
+  prof_mark(c, st);
+  int64_t max_out = 0;
+  for (int i = 0; i < n_clips; ++i) {
+    if (in_offsets_host[i + 1] < in_offsets_host[i] || out_offsets_host[i + 1] < out_offsets_host[i])
+      return fail(c, BT_ERR_ARG, "bt_resample: offsets must be non-decreasing");
+    max_out = std::max(max_out, out_offsets_host[i + 1] - out_offsets_host[i]);
+  }
+  const size_t bytes = static_cast<size_t>(n_clips + 1) * 8 * 2;
+  int r = ensure_stage(c, bytes);
+  if (r != BT_OK) return r;
+  int64_t* h = static_cast<int64_t*>(c->stage_host);
+  memcpy(h, in_offsets_host, (n_clips + 1) * 8);
+  memcpy(h + n_clips + 1, out_offsets_host, (n_clips + 1) * 8);
+  if ((r = upload_stage(c, bytes, st)) != BT_OK) return r;
+  const int64_t* d = static_cast<const int64_t*>(c->stage_dev);
+  if (launch_resample(audio_in_dev, d, audio_out_dev, d + n_clips + 1, n_clips, max_out, coef_dev, L, M, K, st) != 0)
+    return fail(c, BT_ERR_ARG, "bt_resample: ratio %d/%d with %d taps needs too much shared memory", L, M, K);
+  BT_LAUNCHED(c, "resample", st);
   return BT_OK;
 }
 

@@ -75,7 +75,9 @@ void launch_stem(const float* spect, const ChunkSrc* chunks, int nchunks, int L,
                  const float* bn1_shift, const float* w, const float* bias, float* out,
                  cudaStream_t st);
 void launch_head(const float* x, int D, const float* w, const float* b, const ChunkSrc* chunks,
-                 int nchunks, int L, float* beat, float* down, cudaStream_t st);
+                 int nchunks, int L, float* beat, float* down, int sum_head, cudaStream_t st);
+int launch_resample(const float* in, const int64_t* in_off_dev, float* out, const int64_t* out_off_dev, int n_clips,
+                    int64_t max_out, const float* coef, int L, int M, int K, cudaStream_t st);
 void launch_logmel(const float* audio, const int64_t* sample_off_dev, const int64_t* frame_off_dev,
                    int n_clips, int64_t max_frames, const float* window, const float* twiddle,
                    const int32_t* fb_start, const int32_t* fb_ptr, const float* fb_w, float* spect,

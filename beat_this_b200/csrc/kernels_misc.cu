@@ -115,6 +115,61 @@ void launch_logmel(const float* audio, const int64_t* sample_off_dev, const int6
 }
 
 // ------------------------------------------------------------------------------------------
+// Polyphase resampler to 22.05 kHz: device stand-in for soxr.resample (reference inference.py:274-275; method and
+// filter design in beat_this_b200/preprocessing.py, parity with soxr unpinned).
+//   y[n] = sum_k coef[(n M) mod L][k] * x[floor(n M / L) - K/2 + 1 + k],  zeros outside the clip.
+// One CTA = 256 consecutive output samples of one clip; the input span they read is staged in shared memory.
+// Algorithmic HBM bytes: 4 B per input sample + 4 B per output sample (the L x K bank stays in L1/L2).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+resample_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_off, float* __restrict__ out,
+                const int64_t* __restrict__ out_off, const float* __restrict__ coef, int L, int M, int K) {
+  extern __shared__ float xs[];
+  const int clip = blockIdx.y;
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * 256;
+  const int64_t s0 = in_off[clip], len = in_off[clip + 1] - s0;
+  const int64_t o0 = out_off[clip], nout = out_off[clip + 1] - o0;
+  if (n0 >= nout) return;
+  const int64_t n_last = min(n0 + 255, nout - 1);
+  const int64_t j_lo = (n0 * M) / L - K / 2 + 1;
+  const int span = static_cast<int>((n_last * M) / L - K / 2 + K - j_lo + 1);
+  for (int i = threadIdx.x; i < span; i += 256) {
+    const int64_t j = j_lo + i;
+    xs[i] = (j >= 0 && j < len) ? in[s0 + j] : 0.f;
+  }
+  __syncthreads();
+  const int64_t n = n0 + threadIdx.x;
+  if (n >= nout) return;
+  const int64_t nm = n * M;
+  const int base = static_cast<int>(nm / L - K / 2 + 1 - j_lo);
+  const float* c = coef + static_cast<int64_t>(nm % L) * K;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+  for (; k + 4 <= K; k += 4) {
+    a0 = fmaf(__ldg(c + k), xs[base + k], a0);
+    a1 = fmaf(__ldg(c + k + 1), xs[base + k + 1], a1);
+    a2 = fmaf(__ldg(c + k + 2), xs[base + k + 2], a2);
+    a3 = fmaf(__ldg(c + k + 3), xs[base + k + 3], a3);
+  }
+  for (; k < K; ++k) a0 = fmaf(__ldg(c + k), xs[base + k], a0);
+  out[o0 + n] = (a0 + a1) + (a2 + a3);
+}
+
+int launch_resample(const float* in, const int64_t* in_off_dev, float* out, const int64_t* out_off_dev, int n_clips,
+                    int64_t max_out, const float* coef, int L, int M, int K, cudaStream_t st) {
+  if (n_clips <= 0 || max_out <= 0) return 0;
+  const int64_t span = (255ll * M) / L + K + 2;
+  if (span * 4 > 200 * 1024) return -1;  // absurd ratio: the staged input span does not fit in shared memory
+  const int smem = static_cast<int>(span * 4);
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return -1;
+  dim3 grid(static_cast<unsigned>((max_out + 255) / 256), static_cast<unsigned>(n_clips));
+  resample_kernel<<<grid, 256, smem, st>>>(in, in_off_dev, out, out_off_dev, coef, L, M, K);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // stem: BN1d(128) -> Conv2d(1->32, k(4,3), s(4,1), p(0,1), no bias) -> BN2d -> GELU
 // (reference beat_tracker.py:108-126).  BN2d is folded into w/bias on the host; BN1d cannot
 // be folded (the conv's time padding is zero *after* BN1d) and is applied to each tap.
@@ -566,7 +621,7 @@ void launch_attn_freq(const void* qkv, const float* gates, void* out, int B, int
 __global__ void __launch_bounds__(256)
 head_kernel(const float* __restrict__ x, int D, const float* __restrict__ w, const float* __restrict__ bias,
             const ChunkSrc* __restrict__ chunks, int nchunks, int L, float* __restrict__ beat,
-            float* __restrict__ down) {
+            float* __restrict__ down, int sum_head) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= static_cast<int64_t>(nchunks) * L) return;
@@ -586,16 +641,16 @@ head_kernel(const float* __restrict__ x, int D, const float* __restrict__ w, con
     const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
     const float o0 = a0 * inv + bias[0], o1 = a1 * inv + bias[1];
     const int64_t fr = cs.out_base + cs.start + t;
-    beat[fr] = o0 + o1;
+    beat[fr] = sum_head ? o0 + o1 : o0;  // SumHead (beat_tracker.py:315-330) / Head (beat_tracker.py:333-346)
     down[fr] = o1;
   }
 }
 
 void launch_head(const float* x, int D, const float* w, const float* b, const ChunkSrc* chunks,
-                 int nchunks, int L, float* beat, float* down, cudaStream_t st) {
+                 int nchunks, int L, float* beat, float* down, int sum_head, cudaStream_t st) {
   const int64_t rows = static_cast<int64_t>(nchunks) * L;
   head_kernel<<<static_cast<unsigned>(ceil_div64(rows, 8)), 256, 0, st>>>(x, D, w, b, chunks, nchunks, L,
-                                                                           beat, down);
+                                                                           beat, down, sum_head);
 }
 
 // ------------------------------------------------------------------------------------------

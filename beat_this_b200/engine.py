@@ -63,6 +63,7 @@ class Engine:
         _lib.check(self.lib, None, code)
         self.ctx = ctx
         self._model_ready = False
+        self._resample_banks = {}  # (sr_in, sr_out) -> (coef device tensor, L, M, K)
         if packed is not None:
             self.set_params(packed)
         if wave_chunks:
@@ -117,6 +118,27 @@ class Engine:
         for a, b in zip(sample_offsets[:-1], sample_offsets[1:]):
             fo.append(fo[-1] + 1 + (int(b) - int(a)) // 441)
         return fo
+
+    def resample_cat(self, audio: torch.Tensor, sample_offsets, sr: int, sr_out: int = 22050):
+        """Concatenated fp32 device audio at `sr` Hz -> (audio at `sr_out` Hz, new sample offsets): the device
+        stand-in for soxr.resample (reference inference.py:274-275), see preprocessing.resample_filter_bank."""
+        from . import preprocessing as P
+
+        assert audio.is_cuda and audio.dtype == torch.float32 and audio.is_contiguous()
+        key = (int(sr), int(sr_out))
+        if key not in self._resample_banks:
+            coef, L, M, K = P.resample_filter_bank(*key)
+            self._resample_banks[key] = (torch.from_numpy(coef).to(self.device).contiguous(), L, M, K)
+        coef, L, M, K = self._resample_banks[key]
+        so = [int(v) for v in sample_offsets]
+        oo = [0]
+        for i in range(len(so) - 1):
+            oo.append(oo[-1] + P.resampled_length(so[i + 1] - so[i], L, M))
+        out = torch.empty(max(oo[-1], 1), dtype=torch.float32, device=self.device)[: oo[-1]]
+        code = self.lib.bt_resample(self.ctx, c_void_p(audio.data_ptr()), i64_array(so), len(so) - 1, c_void_p(coef.data_ptr()),
+                                    L, M, K, c_void_p(out.data_ptr()), i64_array(oo), self._stream())
+        _lib.check(self.lib, self.ctx, code)
+        return out, oo
 
     def logmel_cat(self, audio: torch.Tensor, sample_offsets):
         """audio: flat fp32 device tensor; returns (spect [total_frames,128], frame_offsets)."""

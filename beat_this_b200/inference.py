@@ -154,8 +154,8 @@ class Spect2Frames:
         return self.spect2frames(spect)
 
 
-def _mono_22k(signal, sr):
-    """Channel mix + resample front door of Audio2Frames.signal2spect (inference.py:269-275)."""
+def _mono(signal):
+    """Channel mix of Audio2Frames.signal2spect (inference.py:269-273): float64 mean over axis 1."""
     signal = np.asarray(signal) if not isinstance(signal, (np.ndarray, torch.Tensor)) else signal
     if isinstance(signal, torch.Tensor):
         signal = signal.detach().cpu().numpy()
@@ -163,27 +163,37 @@ def _mono_22k(signal, sr):
         signal = signal.mean(1)
     elif signal.ndim != 1:
         raise ValueError(f"Expected 1D or 2D signal, got shape {signal.shape}")
-    if sr != 22050:
-        try:
-            import soxr
-        except ImportError as e:  # the reference hard-depends on soxr (inference.py:4)
-            raise RuntimeError("resampling needs the `soxr` package (as in the reference); input must be 22050 Hz without it") from e
-        signal = soxr.resample(signal, in_rate=sr, out_rate=22050)
     return signal
 
 
-class Audio2Frames(Spect2Frames):
-    """Framewise logits from an audio signal (reference inference.py:260-281)."""
+def _soxr_resample(signal, sr):
+    """The reference's own host resampler (inference.py:274-275), when the package is installed."""
+    try:
+        import soxr
+    except ImportError as e:
+        raise RuntimeError("resampler='soxr' needs the `soxr` package; the default resampler='device' does not") from e
+    return soxr.resample(signal, in_rate=sr, out_rate=22050)
 
-    def __init__(self, checkpoint_path="final0", device="cuda", float16=False):
+
+class Audio2Frames(Spect2Frames):
+    """Framewise logits from an audio signal (reference inference.py:260-281).
+
+    Audio that is not at 22.05 kHz is resampled on the device (`resampler="device"`, a Kaiser-windowed-sinc
+    polyphase FIR designed to soxr-HQ-like targets, see preprocessing.resample_filter_bank) or, with
+    `resampler="soxr"`, by the reference's own host library when it is installed."""
+
+    def __init__(self, checkpoint_path="final0", device="cuda", float16=False, resampler="device"):
         super().__init__(checkpoint_path, device, float16)
+        if resampler not in ("device", "soxr"):
+            raise ValueError("resampler must be 'device' or 'soxr'")
+        self.resampler = resampler
         self.spect = LogMelSpect(device=self.device, _engine=self.model.engine)
         self._pinned = None
 
     def signal2spect(self, signal, sr):
-        signal = _mono_22k(signal, sr)
-        signal = torch.tensor(signal, dtype=torch.float32, device=self.device)
-        return self.spect(signal)
+        audio, so = self._stage([signal], sr)
+        spect, _ = self.model.engine.logmel_cat(audio, so)
+        return spect
 
     def __call__(self, signal, sr):
         beat, down, _ = self._frames_batch([signal], sr)
@@ -191,8 +201,13 @@ class Audio2Frames(Spect2Frames):
 
     # ---- batched path ----------------------------------------------------------------------
     def _stage(self, signals, sr):
-        """mono/22.05 kHz fp32 signals -> one pinned host buffer -> device (async)."""
-        mono = [np.ascontiguousarray(_mono_22k(s, sr), dtype=np.float32) for s in signals]
+        """mono fp32 signals -> one pinned host buffer -> device (async) -> 22.05 kHz on the device."""
+        sr = int(sr)
+        host_resample = sr != 22050 and self.resampler == "soxr"
+        mono = [_mono(s) for s in signals]
+        if host_resample:
+            mono = [_soxr_resample(m, sr) for m in mono]
+        mono = [np.ascontiguousarray(m, dtype=np.float32) for m in mono]
         so = [0]
         for m in mono:
             so.append(so[-1] + m.shape[0])
@@ -202,7 +217,10 @@ class Audio2Frames(Spect2Frames):
         hn = host.numpy()
         for i, m in enumerate(mono):
             hn[so[i] : so[i + 1]] = m
-        return host.to(self.device, non_blocking=True), so
+        audio = host.to(self.device, non_blocking=True)
+        if sr != 22050 and not host_resample:
+            audio, so = self.model.engine.resample_cat(audio, so, sr)
+        return audio, so
 
     def _frames_batch(self, signals, sr):
         audio, so = self._stage(signals, sr)
@@ -222,8 +240,8 @@ class Audio2Beats(Audio2Frames):
     """Beat / downbeat positions in seconds from an audio signal (reference
     inference.py:284-303)."""
 
-    def __init__(self, checkpoint_path="final0", device="cuda", float16=False, dbn=False):
-        super().__init__(checkpoint_path, device, float16)
+    def __init__(self, checkpoint_path="final0", device="cuda", float16=False, dbn=False, resampler="device"):
+        super().__init__(checkpoint_path, device, float16, resampler)
         self.frames2beats = Postprocessor(type="dbn" if dbn else "minimal", engine=self.model.engine)
 
     def __call__(self, signal, sr):

@@ -120,6 +120,58 @@ def mel_constants() -> dict:
     }
 
 
+# ------------------------------------------------------------------------------------------------
+# Resampler constants (device stand-in for ``soxr.resample(signal, in_rate=sr, out_rate=22050)``,
+# reference inference.py:274-275).  soxr is a third-party C library that is absent offline, so this
+# is a *restated published method* (band-limited interpolation with a Kaiser-windowed sinc, J. O.
+# Smith, "Digital Audio Resampling"), designed to soxr's documented HQ targets: flat (+-1e-5 dB) to
+# 0.93 of the output Nyquist, <= -124 dB from the Nyquist on.  Parity with soxr itself is UNPINNED
+# (DESIGN.md section 2); the CUDA kernel is checked against a float64 direct-form evaluation.
+#   y[n] = sum_j x[j] * g * h(s * (n*M/L - j)),  h(t) = rho * sinc(rho t) * kaiser_beta(t / Z), |t| <= Z
+#   L/M = sr_out/sr_in in lowest terms, s = g = min(1, L/M)
+RESAMPLE_ZERO_CROSSINGS = 94
+RESAMPLE_BETA = 12.8
+RESAMPLE_ROLLOFF = 0.9565
+
+
+def resample_ratio(sr_in: int, sr_out: int = SAMPLE_RATE):
+    """(L, M) with sr_out / sr_in = L / M in lowest terms."""
+    sr_in, sr_out = int(sr_in), int(sr_out)
+    if sr_in <= 0 or sr_out <= 0:
+        raise ValueError("sample rates must be positive integers")
+    g = math.gcd(sr_in, sr_out)
+    return sr_out // g, sr_in // g
+
+
+def resampled_length(n: int, L: int, M: int) -> int:
+    """Number of output samples for n input samples: round-half-up of n * L / M."""
+    return (2 * n * L + M) // (2 * M)
+
+
+def resample_kernel(t):
+    """h(t) of the header comment, float64, t in units of output-band zero crossings."""
+    t = np.asarray(t, dtype=np.float64)
+    u = np.clip(1.0 - (t / RESAMPLE_ZERO_CROSSINGS) ** 2, 0.0, None)
+    w = np.i0(RESAMPLE_BETA * np.sqrt(u)) / np.i0(RESAMPLE_BETA)
+    h = RESAMPLE_ROLLOFF * np.sinc(RESAMPLE_ROLLOFF * t) * w
+    return np.where(np.abs(t) <= RESAMPLE_ZERO_CROSSINGS, h, 0.0)
+
+
+def resample_filter_bank(sr_in: int, sr_out: int = SAMPLE_RATE):
+    """Polyphase bank for the device kernel: (coef float32 [L, K], L, M, K).  Output n reads the K input
+    samples q - K/2 + 1 + k (k = 0..K-1, q = floor(n M / L)) with the row phase = (n M) mod L."""
+    L, M = resample_ratio(sr_in, sr_out)
+    s = min(1.0, L / M)
+    K = 2 * int(math.ceil(RESAMPLE_ZERO_CROSSINGS / s))
+    if L * K > (1 << 26):
+        raise ValueError(f"resampling {sr_in} -> {sr_out} Hz needs a {L} x {K} polyphase bank; use a rate with a "
+                         "larger common divisor with the target rate")
+    phase = np.arange(L, dtype=np.float64)[:, None] / L
+    k = np.arange(K, dtype=np.float64)[None, :]
+    coef = s * resample_kernel(s * (phase + (K // 2 - 1) - k))
+    return coef.astype(np.float32), L, M, K
+
+
 class LogMelSpect(torch.nn.Module):
     """Drop-in for the reference class (preprocessing.py:27-59).  Only the reference's
     default analysis parameters are implemented in the kernel; anything else raises."""

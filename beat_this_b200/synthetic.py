@@ -26,7 +26,10 @@ SAMPLE_RATE = 22050
 
 def model_hparams(name: str = "final0") -> dict:
     """BeatThis constructor arguments as stored in ``hyper_parameters`` (pl_module.py:22-44)."""
-    dim = {"final0": 512, "small0": 128}[name] if name in ("final0", "small0") else int(name)
+    # "<base>-nosum" / "<base>-nopartial": the ablation families of the reference README (sum_head=False ->
+    # Head, beat_tracker.py:333-346; partial_transformers=False -> nn.Identity, beat_tracker.py:151-152)
+    base, _, variant = name.partition("-")
+    dim = {"final0": 512, "small0": 128}[base] if base in ("final0", "small0") else int(base)
     return dict(
         spect_dim=128,
         fps=50,
@@ -44,8 +47,8 @@ def model_hparams(name: str = "final0") -> dict:
         max_epochs=100,
         use_dbn=False,
         eval_trim_beats=5,
-        sum_head=True,
-        partial_transformers=True,
+        sum_head=variant != "nosum",
+        partial_transformers=variant != "nopartial",
     )
 
 
@@ -102,10 +105,11 @@ def make_state_dict(hp: dict, seed: int = 0) -> "OrderedDict[str, torch.Tensor]"
     c = stem
     for i in range(3):
         p = f"frontend.blocks.{i}"
-        _attention(sd, p + ".partial.attnF", c, g)
-        _feedforward(sd, p + ".partial.ffF", c, 4, g)
-        _attention(sd, p + ".partial.attnT", c, g)
-        _feedforward(sd, p + ".partial.ffT", c, 4, g)
+        if hp.get("partial_transformers", True):
+            _attention(sd, p + ".partial.attnF", c, g)
+            _feedforward(sd, p + ".partial.ffF", c, 4, g)
+            _attention(sd, p + ".partial.attnT", c, g)
+            _feedforward(sd, p + ".partial.ffT", c, 4, g)
         _conv(sd, p + ".conv2d.weight", 2 * c, c, 2, 3, g)
         _bn(sd, p + ".norm", 2 * c, g)
         c *= 2

@@ -108,6 +108,17 @@ int bt_logmel(bt_ctx* ctx, const float* audio_dev, const int64_t* sample_offsets
               int32_t n_clips, float* spect_dev, const int64_t* frame_offsets_host,
               void* stream);
 
+/* Resample front door of Audio2Frames.signal2spect (inference.py:274-275:
+ * `soxr.resample(signal, in_rate=sr, out_rate=22050)`), as a device polyphase FIR:
+ *   out[n] = sum_k coef[(n*M) mod L][k] * in[floor(n*M/L) - K/2 + 1 + k]   (zeros outside a clip)
+ * with sr_out/sr_in = L/M in lowest terms.  coef_dev: [L][K] fp32 bank (the host side designs it,
+ * beat_this_b200/preprocessing.py: Kaiser-windowed sinc to soxr-HQ-like targets; parity with
+ * soxr itself is unpinned).  in/out: concatenated fp32 clips with host offset arrays
+ * [n_clips+1]; out lengths are the caller's (normally round(len*L/M)). */
+int bt_resample(bt_ctx* ctx, const float* audio_in_dev, const int64_t* in_offsets_host,
+                int32_t n_clips, const float* coef_dev, int32_t L, int32_t M, int32_t K,
+                float* audio_out_dev, const int64_t* out_offsets_host, void* stream);
+
 /* Spect2Frames.spect2frames (inference.py:244-254): split_piece -> BeatThis.forward on
  * every chunk -> aggregate_prediction(keep_first).  spect_dev as produced by bt_logmel.
  * beat_dev / downbeat_dev: out, fp32 logits, concatenated with the same frame offsets. */

@@ -194,7 +194,7 @@ def batchnorm(x, sd, p, dim):
     return x * scale.view(shape) + shift.view(shape)
 
 
-def forward(sd: dict, x: torch.Tensor, taps: dict | None = None, explicit=False):
+def forward(sd: dict, x: torch.Tensor, taps: dict | None = None, explicit=False, sum_head=True):
     """BeatThis.forward (beat_tracker.py:188-192) on x [B, L, 128] -> (beat[B,L], downbeat[B,L]).
     `taps`, when given, collects intermediates in [B, F, L, C] (frontend) / [B, L, D] layout."""
     B, L, _ = x.shape
@@ -244,9 +244,9 @@ def forward(sd: dict, x: torch.Tensor, taps: dict | None = None, explicit=False)
         h = feedforward(h, sd, p + ".1") + h
         tap(f"l{l}.ff", h)
     h = rmsnorm(h, sd["transformer_blocks.norm.gamma"])
-    # SumHead: beat_tracker.py:315-330
+    # SumHead: beat_tracker.py:315-330 (beat = beat + downbeat in fp32); Head: beat_tracker.py:333-346
     o = h @ sd["task_heads.beat_downbeat_lin.weight"].T + sd["task_heads.beat_downbeat_lin.bias"]
-    beat = o[..., 0] + o[..., 1]
+    beat = o[..., 0] + o[..., 1] if sum_head else o[..., 0]
     down = o[..., 1]
     return beat, down
 
@@ -257,16 +257,16 @@ def strip_prefix(state_dict: dict) -> dict:
 
 
 @torch.inference_mode()
-def spect2frames(sd: dict, spect: torch.Tensor, batch_chunks: bool = True):
+def spect2frames(sd: dict, spect: torch.Tensor, batch_chunks: bool = True, sum_head: bool = True):
     """Spect2Frames.spect2frames (inference.py:244-254): chunk 1500 / border 6 / keep_first."""
     chunks, starts = split_piece(spect)
     if batch_chunks and len({len(c) for c in chunks}) == 1:
-        b, d = forward(sd, torch.stack(chunks))
+        b, d = forward(sd, torch.stack(chunks), sum_head=sum_head)
         preds = list(zip(b, d))
     else:
         preds = []
         for c in chunks:
-            b, d = forward(sd, c[None])
+            b, d = forward(sd, c[None], sum_head=sum_head)
             preds.append((b[0], d[0]))
     return aggregate(preds, starts, len(spect))
 
@@ -316,3 +316,31 @@ def audio2beats(sd: dict, signal: np.ndarray, sr: int = SR):
     """Audio2Beats.__call__ (inference.py:301-303) with the minimal postprocessor."""
     b, d = spect2frames(sd, signal2spect(signal, sr))
     return postp_minimal(b, d)
+
+
+def resample_direct(x, sr_in: int, sr_out: int = 22050):
+    """Float64 direct-form evaluation of the resampler DEFINITION in beat_this_b200/preprocessing.py
+    (stand-in for soxr.resample, reference inference.py:274-275; parity with soxr unpinned): every output
+    sample sums the continuous Kaiser-windowed sinc over the input samples in its support -- no polyphase
+    bank, so the bank construction and the kernel indexing are checked independently."""
+    import math
+
+    import numpy as np
+
+    from beat_this_b200 import preprocessing as P
+
+    x = np.asarray(x, dtype=np.float64)
+    g = math.gcd(int(sr_in), int(sr_out))
+    L, M = sr_out // g, sr_in // g
+    s = min(1.0, L / M)
+    n_out = (2 * len(x) * L + M) // (2 * M)
+    half = int(math.ceil(P.RESAMPLE_ZERO_CROSSINGS / s)) + 1
+    y = np.zeros(n_out)
+    for n0 in range(0, n_out, 4096):
+        n = np.arange(n0, min(n_out, n0 + 4096))
+        pos = n * (M / L)
+        j = np.floor(pos)[:, None].astype(np.int64) + np.arange(-half, half + 1)[None, :]
+        ok = (j >= 0) & (j < len(x))
+        xv = np.where(ok, x[np.clip(j, 0, len(x) - 1)], 0.0)
+        y[n0 : n0 + len(n)] = (xv * (s * P.resample_kernel(s * (pos[:, None] - j)))).sum(1)
+    return y

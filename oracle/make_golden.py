@@ -144,6 +144,20 @@ def main():
     report["small0 explicit-softmax vs sdpa"] = float((e_b - b2).abs().max())
     report["small0 frontend tap vs ref"] = float((ref_front - taps["frontend"]).abs().max())
 
+    # 4a'. ablation families (reference README.md:86-101): Head instead of SumHead, no partial transformers
+    for variant in ("small0-nosum", "small0-nopartial"):
+        vpath, vmodel, vsd = ref_model_from(variant, 0)
+        vhp = synthetic.model_hparams(variant)
+        torch.manual_seed(5)
+        vspect = torch.rand(1700, 128) * 7  # 2 chunks
+        vb, vd = ref_inf.Spect2Frames(vpath, "cpu", False)(vspect)
+        vob, vod = O.spect2frames(vsd, vspect, sum_head=vhp["sum_head"])
+        report[f"{variant} spect2frames oracle-vs-ref"] = float(max((vb - vob).abs().max(), (vd - vod).abs().max()))
+        key = variant.replace("-", "_")
+        gold[f"{key}_ckpt_sum"] = np.float64(synthetic.tensor_checksum(vsd))
+        gold[f"{key}_spect1700_beat"] = vb.numpy()
+        gold[f"{key}_spect1700_down"] = vd.numpy()
+
     # 4b. final0-shaped: Audio2Frames / Audio2Beats on a 10 s clip (1 short chunk) and a 30 s clip (2 chunks)
     path, model, sd = ref_model_from("final0", 0)
     a2b = ref_inf.Audio2Beats(path, "cpu", False, False)

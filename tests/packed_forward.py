@@ -102,4 +102,4 @@ def forward(packed, hp, x, taps=None):
         x_ = _ff(x_, packed, f"l{l}.ff", D, hp["ff_mult"])
         if taps is not None: taps[f"l{l}.ff"] = x_[:, 0].clone()
     o = _norm(x_[:, 0]) @ _p(packed, "head.w", 2, D).T + _p(packed, "head.b", 2)
-    return o[..., 0] + o[..., 1], o[..., 1]
+    return (o[..., 0] + o[..., 1] if hp.get("sum_head", True) else o[..., 0]), o[..., 1]

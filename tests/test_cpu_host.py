@@ -61,7 +61,7 @@ def test_no_gpu_fails_loudly(lib_built):
         Spect2Frames("whatever.ckpt", "cpu")
 
 
-@pytest.mark.parametrize("name", ["small0"])
+@pytest.mark.parametrize("name", ["small0", "small0-nosum", "small0-nopartial"])
 def test_packed_parameters_reproduce_the_oracle(name):
     """Fold/layout logic of weights.py: the kernel schedule emulated in torch with the packed
     parameters (tests/packed_forward.py) must equal the oracle forward, stage by stage."""
@@ -75,7 +75,7 @@ def test_packed_parameters_reproduce_the_oracle(name):
     x = torch.rand(2, 90, 128) * 7
     t1, t2 = {}, {}
     with torch.inference_mode():
-        b, d = O.forward(sd, x, t1)
+        b, d = O.forward(sd, x, t1, sum_head=hp["sum_head"])
         b2, d2 = PF.forward(packed, weights.filter_hparams(hp), x, t2)
     for k in t1:
         assert (t1[k] - t2[k]).abs().max() < 1e-4, k

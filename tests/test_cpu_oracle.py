@@ -63,6 +63,24 @@ def test_model_golden_small0(small0_ckpt):
     assert np.abs(d.numpy() - g["small0_spect1500_down"]).max() < 2e-4
 
 
+@pytest.mark.parametrize("variant", ["small0-nosum", "small0-nopartial"])
+def test_model_golden_ablation_families(variant):
+    """sum_head=False (Head, beat_tracker.py:333-346) and partial_transformers=False (nn.Identity,
+    beat_tracker.py:151-152): fixtures written by the reference's own Spect2Frames (oracle/make_golden.py)."""
+    from conftest import ckpt_path
+
+    g = np.load(os.path.join(GOLDEN, "model.npz"))
+    key = variant.replace("-", "_")
+    ck = torch.load(ckpt_path(variant), weights_only=True)
+    sd = O.strip_prefix(ck["state_dict"])
+    assert abs(synthetic.tensor_checksum(sd) - float(g[f"{key}_ckpt_sum"])) < 1e-6 * abs(float(g[f"{key}_ckpt_sum"]))
+    torch.manual_seed(5)
+    spect = torch.rand(1700, 128) * 7
+    b, d = O.spect2frames(sd, spect, sum_head=ck["hyper_parameters"]["sum_head"])
+    assert np.abs(b.numpy() - g[f"{key}_spect1700_beat"]).max() < 2e-4
+    assert np.abs(d.numpy() - g[f"{key}_spect1700_down"]).max() < 2e-4
+
+
 def test_model_golden_final0_short_clip(final0_ckpt):
     g = np.load(os.path.join(GOLDEN, "model.npz"))
     sd = O.strip_prefix(torch.load(final0_ckpt, weights_only=True)["state_dict"])
@@ -94,3 +112,36 @@ def test_oracle_against_live_reference(small0_ckpt):
     for T in (1, 1488, 1489, 3001):
         _, starts = ref_inf.split_piece(torch.zeros(T, 1), 1500, 6, True)
         assert np.array_equal(starts, O.split_starts(T))
+
+
+# ------------------------------------------------------------------------------------ resampler
+@pytest.mark.parametrize("sr", [44100, 48000, 16000, 8000, 96000, 11025, 32000])
+def test_resample_bank_equals_direct_form(sr):
+    """The polyphase bank the CUDA kernel consumes (preprocessing.resample_filter_bank) reproduces the float64
+    direct-form definition (oracle.resample_direct) -- bank construction and tap indexing are independent code."""
+    from beat_this_b200 import preprocessing as P
+
+    rng = np.random.default_rng(sr)
+    x = rng.standard_normal(2500)
+    coef, L, M, K = P.resample_filter_bank(sr)
+    assert coef.shape == (L, K) and K % 2 == 0 and abs(coef.astype(np.float64).sum(1).mean() - 1.0) < 1e-6
+    n_out = P.resampled_length(len(x), L, M)
+    n = np.arange(n_out)
+    j = ((n * M) // L)[:, None] - K // 2 + 1 + np.arange(K)[None, :]
+    xv = np.where((j >= 0) & (j < len(x)), x[np.clip(j, 0, len(x) - 1)], 0.0)
+    y_bank = (xv * coef[(n * M) % L].astype(np.float64)).sum(1)
+    y = O.resample_direct(x, sr)
+    assert y.shape == y_bank.shape and np.abs(y - y_bank).max() < 1e-6
+
+
+def test_resample_filter_meets_its_design_targets():
+    """Design targets stated in preprocessing.py (soxr-HQ-like): a 1 kHz and a 10 kHz tone pass 44.1 -> 22.05 kHz
+    unchanged, a 12 kHz tone (above the new Nyquist) is rejected by more than 120 dB."""
+    sr = 44100
+    t = np.arange(sr // 2) / sr
+    t2 = np.arange(len(t) // 2) / 22050
+    for f, tol in ((1000.0, 1e-7), (10000.0, 1e-5)):
+        y = O.resample_direct(np.sin(2 * np.pi * f * t), sr)
+        assert len(y) == len(t2) and np.abs(y[400:-400] - np.sin(2 * np.pi * f * t2)[400:-400]).max() < tol
+    y = O.resample_direct(np.sin(2 * np.pi * 12000.0 * t), sr)
+    assert 20 * np.log10(np.abs(y[400:-400]).max()) < -120.0

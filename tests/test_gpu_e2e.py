@@ -49,6 +49,27 @@ def test_config1_spect2frames_small0(small0_ckpt, lib_built, float16):
 
 
 @pytest.mark.parametrize("float16", [False, True])
+@pytest.mark.parametrize("variant", ["small0-nosum", "small0-nopartial"])
+def test_ablation_checkpoint_families_golden(variant, lib_built, float16):
+    """Checkpoints trained without the SumHead / without the partial transformers (reference README.md:86-101)
+    load and match the reference's Spect2Frames output (fixture from oracle/make_golden.py)."""
+    from conftest import ckpt_path
+    from beat_this_b200.inference import Spect2Frames
+
+    path = ckpt_path(variant)
+    key = variant.replace("-", "_")
+    _check_ckpt(path, f"{key}_ckpt_sum")
+    g = _gold()
+    torch.manual_seed(5)
+    spect = torch.rand(1700, 128) * 7
+    beat, down = Spect2Frames(path, "cuda:0", float16)(spect.cuda())
+    eb = np.abs(beat.cpu().numpy() - g[f"{key}_spect1700_beat"]).max()
+    ed = np.abs(down.cpu().numpy() - g[f"{key}_spect1700_down"]).max()
+    print(f"{variant} spect1700 float16={float16}: max abs err beat {eb:.3e} downbeat {ed:.3e}")
+    assert max(eb, ed) < (BF16_TOL if float16 else F32_TOL)
+
+
+@pytest.mark.parametrize("float16", [False, True])
 def test_final0_audio2beats_golden(final0_ckpt, lib_built, float16):
     """Audio2Frames / Audio2Beats, final0-shaped checkpoint, 10 s (one short chunk) and 30 s
     (two 1500-frame chunks) clips, against the reference's own logits and timestamps."""
@@ -133,6 +154,30 @@ def test_wave_size_does_not_change_results(small0_ckpt, lib_built, float16):
             continue
         for (b, d), (rb, rd) in zip(out, ref):
             assert torch.equal(b, rb) and torch.equal(d, rd), wave
+
+
+def test_audio_at_44k1_goes_through_the_device_resampler(small0_ckpt, lib_built):
+    """Audio2Beats with sr != 22050 (reference inference.py:274-275): device resampler + the usual path must equal
+    the oracle pipeline run on the float64 direct-form resampling of the same signal."""
+    from beat_this_b200 import synthetic
+    from beat_this_b200.inference import Audio2Beats
+    from oracle import beat_this_oracle as O
+
+    sd = O.strip_prefix(torch.load(small0_ckpt, weights_only=True)["state_dict"])
+    x = synthetic.synth_clip(77, 12.0, sr=44100)
+    stereo = np.stack([x, 0.25 * x[::-1]], axis=1)
+    a2b = Audio2Beats(small0_ckpt, "cuda:0", False)
+    for sig in (x, stereo):
+        beat, down = super(Audio2Beats, a2b).__call__(sig, 44100)
+        mono = sig if sig.ndim == 1 else sig.mean(1)
+        ob, od = O.spect2frames(sd, O.signal2spect(O.resample_direct(mono, 44100), 22050))
+        assert beat.shape == ob.shape
+        e = max((beat.cpu() - ob).abs().max().item(), (down.cpu() - od).abs().max().item())
+        print(f"44.1 kHz clip ndim={sig.ndim}: max abs logit err vs oracle pipeline {e:.3e}")
+        assert e < F32_TOL
+        bt, dt = a2b(sig, 44100)
+        obt, odt = O.postp_minimal(beat.cpu(), down.cpu())
+        assert np.array_equal(bt, obt) and np.array_equal(dt, odt)
 
 
 def test_no_cpu_fallback(small0_ckpt, lib_built):

@@ -155,6 +155,32 @@ def test_debug_attention(small_f32, small_bf16, bf16):
         assert err < (3e-2 if bf16 else 1e-4), (seqs, L, heads)
 
 
+@pytest.mark.parametrize("sr", [44100, 48000, 16000, 96000])
+def test_resample_matches_direct_form(lib_built, dev, sr):
+    """bt_resample (device polyphase FIR, stand-in for soxr.resample, inference.py:274-275) against the float64
+    direct-form definition, ragged clips incl. one shorter than the filter."""
+    from beat_this_b200.engine import Engine
+    from oracle import beat_this_oracle as O
+
+    eng = Engine(None, None, dev)  # no model parameters needed
+    rng = np.random.default_rng(sr)
+    clips = [rng.uniform(-1, 1, n) for n in (sr // 3 + 17, 50, 3 * sr // 4, 1)]
+    so = [0]
+    for c in clips:
+        so.append(so[-1] + len(c))
+    audio = torch.tensor(np.concatenate(clips), dtype=torch.float32, device=dev)
+    out, oo = eng.resample_cat(audio, so, sr)
+    worst = 0.0
+    for i, c in enumerate(clips):
+        ref = O.resample_direct(c.astype(np.float32).astype(np.float64), sr)
+        got = out[oo[i] : oo[i + 1]].cpu().numpy()
+        assert got.shape == ref.shape, (i, got.shape, ref.shape)
+        if len(ref):
+            worst = max(worst, float(np.abs(got - ref).max()))
+    print(f"resample {sr} -> 22050: max abs err vs float64 direct form {worst:.3e}")
+    assert worst < 2e-5
+
+
 # ------------------------------------------------------------------------------ per-stage parity
 TAPS = ["stem"] + [f"b{i}.{s}" for i in range(3) for s in ("attnF", "ffF", "attnT", "ffT", "conv")] + ["frontend"] + [
     f"l{l}.{s}" for l in range(6) for s in ("attn", "ff")
