@@ -2,8 +2,10 @@
 
 ``type="minimal"``: peak picking (max-pool 7 equality and logit > 0), adjacent-peak merging,
 downbeat snapping and ``np.unique`` all run in one device kernel (``bt_peakpick``); only the
-final timestamp arrays come back to the host.  ``type="dbn"``: the madmom DBN stays on the
-host exactly as in the reference (postprocessor.py:138-173) and needs ``madmom`` installed.
+final timestamp arrays come back to the host.  ``type="dbn"``: the DBN stays on the host as in the
+reference (postprocessor.py:138-173): madmom's ``DBNDownBeatTrackingProcessor`` when madmom is
+installed (exactly the reference's object), otherwise the restatement of its published algorithm in
+``beat_this_b200/dbn.py`` (parity with madmom unpinned); ``dbn_impl`` forces one of the two.
 """
 from __future__ import annotations
 
@@ -14,18 +16,28 @@ import torch
 
 
 class Postprocessor:
-    def __init__(self, type: str = "minimal", fps: int = 50, engine=None, device="cuda"):
+    def __init__(self, type: str = "minimal", fps: int = 50, engine=None, device="cuda", dbn_impl: str = "auto"):
         assert type in ["minimal", "dbn"]
+        assert dbn_impl in ["auto", "madmom", "native"]
         self.type = type
         self.fps = fps
         if fps != 50:
             raise NotImplementedError("the device peak picker is built for the reference's 50 fps")
         if type == "dbn":
-            from madmom.features.downbeats import DBNDownBeatTrackingProcessor
+            kw = dict(beats_per_bar=[3, 4], min_bpm=55.0, max_bpm=215.0, fps=self.fps, transition_lambda=100)
+            self.dbn = None
+            if dbn_impl in ("auto", "madmom"):
+                try:
+                    from madmom.features.downbeats import DBNDownBeatTrackingProcessor
 
-            self.dbn = DBNDownBeatTrackingProcessor(
-                beats_per_bar=[3, 4], min_bpm=55.0, max_bpm=215.0, fps=self.fps, transition_lambda=100
-            )
+                    self.dbn = DBNDownBeatTrackingProcessor(**kw)
+                except ImportError:
+                    if dbn_impl == "madmom":
+                        raise
+            if self.dbn is None:
+                from .dbn import DBNDownBeatTracker
+
+                self.dbn = DBNDownBeatTracker(**kw)
         if engine is None:
             from .engine import Engine
 

@@ -191,3 +191,108 @@ def test_world_size_2_gloo_broadcast_and_sharding(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
     assert res.returncode == 0, res.stderr[-2000:]
     assert "GLOO_OK 128" in res.stdout
+
+
+def test_cli_output_naming_and_task_collection(tmp_path):
+    """Output naming of the command line tool (reference cli.py:94-112,150-168): suffix replace / append, output
+    directory keeps the path relative to the directory named on the command line, existing outputs and files that
+    already carry the suffix are skipped."""
+    from pathlib import Path
+
+    from beat_this_b200 import cli
+
+    f = Path("/music/a/song.wav")
+    assert cli.output_path_for(f, ".beats", False) == Path("/music/a/song.beats")
+    assert cli.output_path_for(f, ".beats", True) == Path("/music/a/song.wav.beats")
+    assert cli.output_path_for(f, ".beats", False, Path("/out")) == Path("/out/song.beats")
+    assert cli.output_path_for(f, ".beats", False, Path("/out"), root=Path("/music")) == Path("/out/a/song.beats")
+    assert cli.output_path_for(f, ".txt", True, Path("/out"), root=Path("/music")) == Path("/out/a/song.wav.txt")
+
+    (tmp_path / "in" / "sub").mkdir(parents=True)
+    for name in ("x.wav", "sub/y.wav", "sub/y.beats", "z.flac"):
+        (tmp_path / "in" / name).write_bytes(b"")
+    tasks, single = cli.collect_tasks([str(tmp_path / "in")], str(tmp_path / "out"), ".beats", False, False)
+    assert not single
+    assert sorted(str(d.relative_to(tmp_path / "out")) for _, d in tasks) == ["sub/y.beats", "x.beats", "z.beats"]
+    (tmp_path / "out").mkdir()
+    (tmp_path / "out" / "x.beats").write_text("")
+    tasks, _ = cli.collect_tasks([str(tmp_path / "in")], str(tmp_path / "out"), ".beats", False, True)
+    assert sorted(s.name for s, _ in tasks) == ["y.wav", "z.flac"]
+    tasks, single = cli.collect_tasks([str(tmp_path / "in" / "x.wav")], None, ".beats", False, False)
+    assert single and tasks == [(tmp_path / "in" / "x.wav", tmp_path / "in" / "x.beats")]
+    tasks, single = cli.collect_tasks([str(tmp_path / "in" / "x.wav")], str(tmp_path / "named.tsv"), ".beats", False, False)
+    assert single and tasks[0][1] == tmp_path / "named.tsv"
+    args = cli.build_parser().parse_args(["a.wav", "--float16", "--no-dbn", "-o", "o", "--touch-first"])
+    assert args.float16 and not args.dbn and args.output == "o" and args.touch_first and args.suffix == ".beats"
+    assert cli._claim(tmp_path / "lock" / "t.beats", True, True) and not cli._claim(tmp_path / "lock" / "t.beats", True, True)
+
+
+def test_native_dbn_viterbi_equals_dense_bruteforce():
+    """The vectorised Viterbi of beat_this_b200/dbn.py (position shift + a small tempo matrix at beat boundaries)
+    against a textbook dense O(T S^2) decoder built independently from the model's published definition."""
+    from beat_this_b200.dbn import _BarModel
+
+    rng = np.random.default_rng(0)
+    for beats in (3, 4):
+        m = _BarModel(beats, 60.0 * 10 / 215.0, 60.0 * 10 / 55.0, None, 100, 16)  # fps 10: 63 states per beat
+        S = m.num_states
+        per_beat = S // beats
+        # dense log transition matrix A[prev, next]
+        A = np.full((S, S), -np.inf)
+        first = set(int(v) for v in m.first_states.ravel())
+        for s_ in range(S):
+            if s_ not in first:
+                A[s_ - 1, s_] = 0.0
+        starts = np.cumsum(np.r_[0, m.intervals[:-1]])
+        for b in range(beats):
+            for k_to, i_to in enumerate(m.intervals):
+                for k_from, i_from in enumerate(m.intervals):
+                    p = np.exp(-100 * abs(i_to / i_from - 1.0))
+                    row = np.exp(-100 * np.abs(m.intervals / i_from - 1.0))
+                    row[row <= np.spacing(1.0)] = 0.0
+                    if p > np.spacing(1.0):
+                        prev = ((b - 1) % beats) * per_beat + starts[k_from] + i_from - 1
+                        A[prev, b * per_beat + starts[k_to]] = np.log(p / row.sum())
+        act = rng.uniform(0.01, 0.3, (40, 2))  # rows sum to < 1 like (beat - downbeat, downbeat) probabilities
+        act[::7] = (0.7, 0.05)
+        act[::21] = (0.05, 0.8)
+        dens = m.log_densities(act)[:, m.pointers]
+        v = np.full(S, -np.log(S))
+        bp = np.zeros((len(act), S), dtype=int)
+        for t in range(len(act)):
+            cand = v[:, None] + A
+            bp[t] = cand.argmax(0)
+            v = cand.max(0) + dens[t]
+        st = int(v.argmax())
+        ref_logp, ref_path = float(v[st]), []
+        for t in range(len(act) - 1, -1, -1):
+            ref_path.append(st)
+            st = bp[t, st]
+        path, logp = m.viterbi(act)
+        assert abs(logp - ref_logp) < 1e-9 and np.array_equal(path, ref_path[::-1])
+
+
+def test_native_dbn_tracks_synthetic_meters():
+    """4/4 at 120 BPM and 3/4 at 90 BPM impulse trains: beats on the impulses (after the `correct` step), bar
+    positions counted 1..4 / 1..3, the right bar-length model wins, leading/trailing silence is trimmed, silence
+    gives no beats; and Postprocessor(type='dbn') reaches it when madmom is not installed."""
+    from beat_this_b200.dbn import DBNDownBeatTracker
+
+    trk = DBNDownBeatTracker()
+    assert [(m.beats, m.intervals[0], m.intervals[-1]) for m in trk.models] == [(3, 14, 55), (4, 14, 55)]
+    T = 1000
+    act = np.full((T, 2), 0.01)
+    frames = list(range(110, 900, 25))
+    for k, f in enumerate(frames):
+        act[f, 1 if k % 4 == 0 else 0] = 0.9
+    out = trk(act)
+    assert np.array_equal(np.round(out[:, 0] * 50).astype(int), frames)
+    assert np.array_equal(out[:, 1].astype(int), [k % 4 + 1 for k in range(len(frames))])
+    act = np.full((T, 2), 0.01)
+    frames = [int(round(7 + k * 100 / 3)) for k in range(29)]
+    for k, f in enumerate(frames):
+        act[f, 1 if k % 3 == 0 else 0] = 0.8
+    out = trk(act)
+    assert np.array_equal(np.round(out[:, 0] * 50).astype(int), frames)
+    assert np.array_equal(out[:, 1].astype(int), [k % 3 + 1 for k in range(len(frames))])
+    assert trk(np.full((200, 2), 0.001)).shape == (0, 2)

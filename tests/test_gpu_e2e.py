@@ -239,3 +239,58 @@ def test_file2beats_and_file2file(small0_ckpt, lib_built, tmp_path):
     assert len(lines) == len(batch[0][0]) and all("\t" in ln for ln in lines)
     with pytest.raises(RuntimeError):
         f2b(tmp_path / "missing.wav")
+
+
+def test_cli_directory_tree(small0_ckpt, lib_built, tmp_path):
+    """`python -m beat_this_b200.cli <dir> -o <out> --activations` (reference cli.py semantics on the batched engine):
+    mixed sample rates / channel counts in one tree, .beats identical to File2Beats, .npy = vstack([beat, downbeat]),
+    --skip-existing leaves present outputs alone."""
+    from scipy.io import wavfile
+
+    from beat_this_b200 import cli, synthetic
+    from beat_this_b200.inference import File2Beats
+
+    src = tmp_path / "in"
+    (src / "sub").mkdir(parents=True)
+    specs = [("a.wav", 22050, 6.0, 1), ("sub/b.wav", 44100, 7.5, 2), ("sub/c.wav", 22050, 3.2, 1)]
+    for name, sr, secs, ch in specs:
+        x = synthetic.synth_clip(60 + len(name), secs, sr=sr)
+        data = np.round(x * 32767).astype(np.int16)
+        wavfile.write(src / name, sr, data if ch == 1 else np.stack([data, data // 2], axis=1))
+    out = tmp_path / "out"
+    assert cli.main([str(src), "-o", str(out), "--model", small0_ckpt, "--activations", "--batch", "2"]) == 0
+    f2b = File2Beats(small0_ckpt, "cuda:0", float16=False)
+    for name, sr, secs, ch in specs:
+        dst = (out / name).with_suffix(".beats")
+        beats, downbeats = f2b(src / name)
+        lines = dst.read_text().splitlines()
+        assert [float(ln.split("\t")[0]) for ln in lines] == [float(f"{b}") for b in beats]
+        assert sum(ln.endswith("\t1") for ln in lines) == len(downbeats)
+        act = np.load(dst.with_suffix(".npy"))
+        assert act.shape[0] == 2 and act.shape[1] == 1 + int(round(secs * sr)) * 22050 // sr // 441
+    stamp = (out / "a.beats").stat().st_mtime_ns
+    (out / "sub" / "b.beats").unlink()
+    assert cli.main([str(src), "-o", str(out), "--model", small0_ckpt, "--skip-existing"]) == 0
+    assert (out / "a.beats").stat().st_mtime_ns == stamp and (out / "sub" / "b.beats").exists()
+
+
+def test_config4_audio2beats_dbn_on_host(small0_ckpt, lib_built):
+    """BASELINE config 4 shape (Audio2Beats --dbn, DBN on the host): frames from the device, post-processing by the
+    host DBN (madmom if installed, else beat_this_b200/dbn.py).  The host side must equal running the same tracker
+    on the oracle-style activations of OUR logits (postprocessor.py:138-173 arithmetic)."""
+    from beat_this_b200 import synthetic
+    from beat_this_b200.inference import Audio2Beats
+
+    a2b = Audio2Beats(small0_ckpt, "cuda:0", False, True)
+    clips = [synthetic.synth_clip(90 + i, s) for i, s in enumerate((20.0, 8.0))]
+    res = a2b.batch(clips, 22050)
+    frames = super(Audio2Beats, a2b).batch(clips, 22050)
+    for (beats, downbeats), (bl, dl) in zip(res, frames):
+        eps = 1e-5
+        bp = bl.double().sigmoid().cpu().numpy() * (1 - eps) + eps / 2
+        dp = dl.double().sigmoid().cpu().numpy() * (1 - eps) + eps / 2
+        out = a2b.frames2beats.dbn(np.vstack((np.maximum(bp - dp, eps / 2), dp)).T)
+        assert np.array_equal(beats, out[:, 0]) and np.array_equal(downbeats, out[out[:, 1] == 1][:, 0])
+        assert np.all(np.diff(beats) > 0) and np.all(np.isin(downbeats, beats))
+    single = a2b(clips[1], 22050)
+    assert np.array_equal(single[0], res[1][0]) and np.array_equal(single[1], res[1][1])
