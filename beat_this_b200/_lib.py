@@ -14,7 +14,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libbeatthis_sm100.so")
-SOURCES = ["bt_api.cu", "kernels_simt.cu", "kernels_misc.cu", "kernels_tc.cu"]
+SOURCES = ["bt_api.cu", "kernels_simt.cu", "kernels_misc.cu", "kernels_tc.cu", "dbn_host.cpp"]
 HEADERS = ["common.cuh", "epilogue.cuh", "bt_kernels.h", os.path.join("..", "..", "include", "beatthis.h")]
 
 BT_DTYPE_F32 = 0
@@ -48,6 +48,10 @@ PROTOTYPES = {
     "bt_resample": (
         c_int,
         [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, POINTER(c_int64), c_void_p],
+    ),
+    "bt_dbn_viterbi": (
+        c_int,
+        [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "bt_spect2frames": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_void_p, c_void_p]),
     "bt_audio2frames": (

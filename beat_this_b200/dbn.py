@@ -20,6 +20,22 @@ from __future__ import annotations
 import numpy as np
 
 
+_LIB = False
+
+
+def _native():
+    """The shared library if it is built (the decoder itself needs no GPU)."""
+    global _LIB
+    if _LIB is False:
+        try:
+            from . import _lib
+
+            _LIB = _lib.load() if hasattr(_lib, "load") else None
+        except Exception:
+            _LIB = None
+    return _LIB
+
+
 class _BarModel:
     """State space + transition + observation model for one bar length (vectorised for Viterbi)."""
 
@@ -68,7 +84,28 @@ class _BarModel:
         return d
 
     def viterbi(self, act):
-        """Most probable state path and its log-probability (uniform initial distribution)."""
+        """Most probable state path and its log-probability (uniform initial distribution): the C++ decoder of the
+        shared library (bt_dbn_viterbi, csrc/dbn_host.cpp -- madmom's is Cython), or `viterbi_numpy` when the
+        library has not been built (both are host code and are tested against each other)."""
+        lib = _native()
+        if lib is None:
+            return self.viterbi_numpy(act)
+        import ctypes
+
+        dens = np.ascontiguousarray(self.log_densities(act))
+        T = len(act)
+        path = np.empty(T, dtype=np.int64)
+        logp = ctypes.c_double()
+        iv = np.ascontiguousarray(self.intervals, dtype=np.int32)
+        lt = np.ascontiguousarray(self.log_tempo, dtype=np.float64)
+        pt = np.ascontiguousarray(self.pointers, dtype=np.int32)
+        code = lib.bt_dbn_viterbi(dens.ctypes.data, T, self.beats, len(iv), iv.ctypes.data, lt.ctypes.data, pt.ctypes.data,
+                                  path.ctypes.data, ctypes.byref(logp))
+        if code != 0:
+            raise RuntimeError(f"bt_dbn_viterbi failed ({code})")
+        return path, float(logp.value)
+
+    def viterbi_numpy(self, act):
         T, S = len(act), self.num_states
         dens = self.log_densities(act)
         v = np.full(S, -np.log(S))

@@ -119,6 +119,16 @@ int bt_resample(bt_ctx* ctx, const float* audio_in_dev, const int64_t* in_offset
                 int32_t n_clips, const float* coef_dev, int32_t L, int32_t M, int32_t K,
                 float* audio_out_dev, const int64_t* out_offsets_host, void* stream);
 
+/* Host-side Viterbi of the bar-pointer HMM behind Postprocessor(type="dbn") (model/postprocessor.py:29-37,170:
+ * madmom DBNDownBeatTrackingProcessor; restated in beat_this_b200/dbn.py, parity with madmom unpinned).
+ * No CUDA, no ctx: thread-safe.  log_dens [T][3] = log densities of (no beat, beat, downbeat); the state space is
+ * `beats` beats x the positions of every tempo `intervals[n_int]` (frames per beat); log_tempo [n_int][n_int] =
+ * log P(tempo f -> tempo k) at a beat boundary; pointers [S] = density column of every state.
+ * path_out [T] receives the most probable state sequence, *logp_out its log-probability. */
+int bt_dbn_viterbi(const double* log_dens, int64_t T, int32_t beats, int32_t n_int,
+                   const int32_t* intervals, const double* log_tempo, const int32_t* pointers,
+                   int64_t* path_out, double* logp_out);
+
 /* Spect2Frames.spect2frames (inference.py:244-254): split_piece -> BeatThis.forward on
  * every chunk -> aggregate_prediction(keep_first).  spect_dev as produced by bt_logmel.
  * beat_dev / downbeat_dev: out, fp32 logits, concatenated with the same frame offsets. */

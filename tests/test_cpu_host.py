@@ -227,7 +227,7 @@ def test_cli_output_naming_and_task_collection(tmp_path):
     assert cli._claim(tmp_path / "lock" / "t.beats", True, True) and not cli._claim(tmp_path / "lock" / "t.beats", True, True)
 
 
-def test_native_dbn_viterbi_equals_dense_bruteforce():
+def test_native_dbn_viterbi_equals_dense_bruteforce(lib_built):
     """The vectorised Viterbi of beat_this_b200/dbn.py (position shift + a small tempo matrix at beat boundaries)
     against a textbook dense O(T S^2) decoder built independently from the model's published definition."""
     from beat_this_b200.dbn import _BarModel
@@ -268,11 +268,12 @@ def test_native_dbn_viterbi_equals_dense_bruteforce():
         for t in range(len(act) - 1, -1, -1):
             ref_path.append(st)
             st = bp[t, st]
-        path, logp = m.viterbi(act)
-        assert abs(logp - ref_logp) < 1e-9 and np.array_equal(path, ref_path[::-1])
+        for decode in (m.viterbi_numpy, m.viterbi):  # numpy form and the C++ decoder of the shared library
+            path, logp = decode(act)
+            assert abs(logp - ref_logp) < 1e-9 and np.array_equal(path, ref_path[::-1])
 
 
-def test_native_dbn_tracks_synthetic_meters():
+def test_native_dbn_tracks_synthetic_meters(lib_built):
     """4/4 at 120 BPM and 3/4 at 90 BPM impulse trains: beats on the impulses (after the `correct` step), bar
     positions counted 1..4 / 1..3, the right bar-length model wins, leading/trailing silence is trimmed, silence
     gives no beats; and Postprocessor(type='dbn') reaches it when madmom is not installed."""
