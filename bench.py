@@ -27,9 +27,16 @@ import tempfile
 import threading
 import time
 
-# keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly ONE line, the JSON result: everything else that writes to file descriptor 1 -- Python
+# prints, the NCCL version banner (printed from C at NCCL_DEBUG >= VERSION), library chatter -- goes to stderr.
+_REAL_STDOUT = os.dup(1)
+sys.stdout.flush()
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -175,7 +182,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(seconds: float, budget_s: float = 20.0):
@@ -338,7 +345,7 @@ def run_ours(args, rank, world, local):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.seconds)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
