@@ -1,11 +1,17 @@
 // bf16 tensor-core path (BT_DTYPE_BF16) for sm_100a: tcgen05.mma with TMEM accumulators,
 // TMA (cp.async.bulk.tensor) operand staging through an mbarrier ring, warp-specialised
-// roles.  Two kernels:
-//   gemm_tc_kernel  -- D = A * W^T over "planes" with shifted slabs (linear layers, the
-//                      k(2,3) frontend convolutions as implicit GEMM, frontend.linear),
-//                      persistent over output tiles, fused epilogues (epilogue.cuh).
-//   attn_tc_kernel  -- flash attention for head_dim 32 over sequences of up to 1500 frames
-//                      (time-direction attention of the frontend and the 6 main layers).
+// roles.  Kernels:
+//   gemm_tc_kernel   -- D = A * W^T over "planes" with shifted slabs (linear layers, the
+//                       k(2,3) frontend convolutions as implicit GEMM, frontend.linear),
+//                       persistent over output tiles, fused epilogues (epilogue.cuh);
+//                       gemm_tc2_kernel = opt-in cta_group::2 variant.
+//   attn_tc64_kernel -- flash attention for head_dim 32 over sequences of up to 1500 frames
+//                       (time-direction attention of the frontend and the 6 main layers),
+//                       P and O in tensor memory, 4 CTAs/SM; attn_tc_kernel<KS,POLY> = the
+//                       earlier 2-CTAs/SM form (BT_ATTN_VARIANT=128).
+//   fused_ff_kernel  -- persistent [out-projection +] RMSNorm + FFN + residual for C = 32/64.
+//   fused_qkv_kernel -- persistent RMSNorm + gates + QKV + RoPE for C = 32/64.
+// Every TMA / MMA issuing warp runs converged with predicated single-lane instructions (umma_bf16_p ...).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -632,7 +638,7 @@ int launch_gemm_tc(const TcGemmPlan* p, const EpiParams& e, cudaStream_t st) {
 // ========================================================================== attention
 // One CTA per (sequence, head, 128-query tile), 2 CTAs/SM.  Warps 0-7: softmax, two threads per
 // query row (warps w and w+4 share TMEM lane quarter w%4; keys [0,64) / [64,128) of each tile);
-// warp 8 lane 0: TMA producer + MMA issuer.  TMEM (256 columns): S [0,128) | O [128,192) | P [192,256).
+// warp 8 (converged, one elected lane issues): TMA producer + MMA issuer.  TMEM (256 columns): S [0,128) | O [128,192) | P [192,256).
 //   S_j = Q K_j^T  : A = Q  [128 x 32] bf16 (K-major, SW64), B = K tile [128 keys x 32] (K-major, SW64)
 //   O  += P_j [V_j | 1] : A = P_j [128 x 128] bf16 **in tensor memory** (written by the softmax
 //                    threads with tcgen05.st, two keys per 32-bit column), B = V tile exactly as the
@@ -1242,7 +1248,7 @@ int launch_attn_time_tc(const TcAttnPlan* p, const float* gates, void* out, cuda
 // kernel (reference roformer.py:38-61): the hidden activations never leave the SM.  Unfused, this
 // block streams 32 bytes per element through HBM (norm 6 + ff1 10 + ff2 16); fused it is 8.
 // CTA = 128 tokens; warps 0-3: one token row per thread (RMSNorm, bias+GELU, residual), warp 4
-// lane 0: TMA (weights) + tcgen05.mma issue.  Hidden units are processed in chunks of 128:
+// (converged, one elected lane issues): TMA (weights) + tcgen05.mma.  Hidden units are processed in chunks of 128:
 //   H_h = Xn W1_h^T (N=128, K=C) -> TMEM cols [0,128) -> bias+GELU -> bf16 tile in smem ->
 //   OUT (+)= H_h W2_h^T (N=C, K=128) -> TMEM cols [128,128+C).
 constexpr int FF_THREADS = 160;
@@ -1578,7 +1584,7 @@ int launch_fused_ff(const TcFfPlan* p, float* X, const float* b1, const float* b
 // RMSNorm -> gates -> to_qkv GEMM -> RoPE (+ q scaling) for the narrow frontend attentions (C = 32 /
 // 64) in one kernel (reference roformer.py:114-123,127-128): replaces norm_kernel + the QKV GEMM
 // (16 bytes/element through HBM) by 4 in + 6 out.  CTA = 128 tokens; warps 0-3 one token row per
-// thread, warp 4 lane 0 TMA (weights) + tcgen05.mma.  N = 3C fits one MMA and 128/256 TMEM columns.
+// thread, warp 4 (converged) TMA (weights) + tcgen05.mma.  N = 3C fits one MMA and 128/256 TMEM columns.
 template <int C>
 struct QkvCfg {
   static constexpr int A_BYTES = 128 * C * 2;
