@@ -49,6 +49,11 @@ PROTOTYPES = {
         c_int,
         [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, POINTER(c_int64), c_void_p],
     ),
+    "bt_dbn_track": (
+        c_int,
+        [c_void_p, c_void_p, c_int32, c_void_p, c_int32, ctypes.c_double, ctypes.c_double, c_int32, ctypes.c_double,
+         ctypes.c_double, ctypes.c_double, c_int32, ctypes.c_double, c_int32, c_void_p, c_void_p, c_void_p],
+    ),
     "bt_dbn_viterbi": (
         c_int,
         [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],

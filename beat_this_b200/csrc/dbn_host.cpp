@@ -1,20 +1,25 @@
-// Host Viterbi decoder of the bar-pointer HMM used by the DBN post-processor (beat_this_b200/dbn.py; stand-in
-// for madmom's Cython HMM.viterbi behind DBNDownBeatTrackingProcessor, reference model/postprocessor.py:29-37,170).
+// Host DBN post-processor: bar-pointer HMM + Viterbi, the stand-in for madmom's DBNDownBeatTrackingProcessor
+// (Cython in madmom) that the reference configures in model/postprocessor.py:29-37 and calls per piece in
+// postprocessor.py:138-173.  Restated from the published algorithm (see beat_this_b200/dbn.py, which holds the
+// numpy twin of everything here); parity with madmom is unpinned.  Plain C++ threads, no CUDA.
+//
 // The state space is never materialised as a transition matrix: inside a beat a state can only be reached from
 // the previous position of the same tempo, and the first position of a beat from the LAST position of every
-// tempo of the previous beat (n_int x n_int log-probabilities).  Plain C++, no CUDA: called per clip from a
-// Python thread pool (ctypes releases the GIL).
+// tempo of the previous beat (n_int x n_int log-probabilities).
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <limits>
+#include <thread>
 #include <vector>
 
 #include "../../include/beatthis.h"
 
-extern "C" int bt_dbn_viterbi(const double* log_dens, int64_t T, int32_t beats, int32_t n_int, const int32_t* intervals,
-                              const double* log_tempo, const int32_t* pointers, int64_t* path_out, double* logp_out) {
-  if (!log_dens || !intervals || !log_tempo || !pointers || !path_out || !logp_out || T <= 0 || beats <= 0 || n_int <= 0)
-    return BT_ERR_ARG;
+namespace {
+
+int viterbi(const double* log_dens, int64_t T, int32_t beats, int32_t n_int, const int32_t* intervals,
+            const double* log_tempo, const int32_t* pointers, int64_t* path_out, double* logp_out) {
   int64_t per_beat = 0;
   std::vector<int64_t> first(n_int), last(n_int);
   for (int k = 0; k < n_int; ++k) {
@@ -64,5 +69,160 @@ extern "C" int bt_dbn_viterbi(const double* log_dens, int64_t T, int32_t beats, 
       state -= 1;
     }
   }
+  return BT_OK;
+}
+
+struct BarModel {
+  int32_t beats = 0, n_int = 0;
+  int64_t per_beat = 0;
+  std::vector<int32_t> intervals, pointers;  // pointers: 0 no beat, 1 beat, 2 downbeat
+  std::vector<double> log_tempo;
+
+  // beat_this_b200/dbn.py::_BarModel.__init__
+  void build(int32_t beats_, double min_interval, double max_interval, int32_t num_tempi, double transition_lambda,
+             double observation_lambda) {
+    beats = beats_;
+    std::vector<double> iv;
+    for (double i = std::nearbyint(min_interval); i <= std::nearbyint(max_interval); i += 1.0) iv.push_back(i);
+    if (num_tempi > 0 && num_tempi < static_cast<int32_t>(iv.size())) {  // log-spaced tempi, as few as requested
+      int n_log = num_tempi;
+      std::vector<double> u;
+      while (static_cast<int32_t>(u.size()) < num_tempi) {
+        u.clear();
+        const double lo = std::log2(min_interval), hi = std::log2(max_interval);
+        for (int i = 0; i < n_log; ++i) {
+          const double e = n_log > 1 ? lo + (hi - lo) * i / (n_log - 1) : lo;
+          u.push_back(std::nearbyint(std::exp2(e)));
+        }
+        std::sort(u.begin(), u.end());
+        u.erase(std::unique(u.begin(), u.end()), u.end());
+        ++n_log;
+      }
+      iv = u;
+    }
+    n_int = static_cast<int32_t>(iv.size());
+    intervals.resize(n_int);
+    per_beat = 0;
+    for (int k = 0; k < n_int; ++k) { intervals[k] = static_cast<int32_t>(iv[k]); per_beat += intervals[k]; }
+    log_tempo.assign(static_cast<size_t>(n_int) * n_int, 0.0);
+    const double eps = std::nextafter(1.0, 2.0) - 1.0;  // np.spacing(1)
+    for (int f = 0; f < n_int; ++f) {
+      double sum = 0.0;
+      for (int k = 0; k < n_int; ++k) {
+        double p = std::exp(-transition_lambda * std::fabs(iv[k] / iv[f] - 1.0));
+        if (p <= eps) p = 0.0;
+        log_tempo[f * n_int + k] = p;
+        sum += p;
+      }
+      for (int k = 0; k < n_int; ++k) log_tempo[f * n_int + k] = std::log(log_tempo[f * n_int + k] / sum);
+    }
+    const double border = 1.0 / observation_lambda;
+    pointers.assign(per_beat * beats, 0);
+    for (int b = 0; b < beats; ++b) {
+      int64_t s = b * per_beat;
+      for (int k = 0; k < n_int; ++k)
+        for (int32_t j = 0; j < intervals[k]; ++j, ++s)
+          if (static_cast<double>(j) / intervals[k] < border) pointers[s] = b == 0 ? 2 : 1;
+    }
+  }
+};
+
+struct Tracker {
+  std::vector<BarModel> models;
+  double fps = 50.0, threshold = 0.05, observation_lambda = 16.0;
+  bool correct = true;
+
+  // beat_this_b200/dbn.py::DBNDownBeatTracker.__call__; returns the number of beats written
+  int64_t track(const double* act_in, int64_t T_in, double* times, int32_t* numbers) const {
+    int64_t first = 0, T = T_in;
+    const double* act = act_in;
+    if (threshold > 0) {  // decode between the first and the last frame with an activation above the threshold
+      int64_t lo = -1, hi = -1;
+      for (int64_t t = 0; t < T_in; ++t)
+        if (act_in[2 * t] >= threshold || act_in[2 * t + 1] >= threshold) { if (lo < 0) lo = t; hi = t; }
+      // np.nonzero(...)[0].any(): false when nothing passes, and (numpy quirk kept) when only frame 0 does
+      if (hi > 0) { first = lo; act = act_in + 2 * lo; T = hi + 1 - lo; }
+      else T = 0;
+    }
+    bool any = false;
+    for (int64_t t = 0; t < 2 * T && !any; ++t) any = act[t] != 0.0;
+    if (!any) return 0;
+    std::vector<double> dens(3 * T);
+    for (int64_t t = 0; t < T; ++t) {
+      dens[3 * t] = std::log((1.0 - (act[2 * t] + act[2 * t + 1])) / (observation_lambda - 1.0));
+      dens[3 * t + 1] = std::log(act[2 * t]);
+      dens[3 * t + 2] = std::log(act[2 * t + 1]);
+    }
+    std::vector<int64_t> best_path, path(T);
+    double best_logp = -std::numeric_limits<double>::infinity();
+    const BarModel* best = nullptr;
+    for (const BarModel& m : models) {
+      double logp = 0;
+      viterbi(dens.data(), T, m.beats, m.n_int, m.intervals.data(), m.log_tempo.data(), m.pointers.data(), path.data(), &logp);
+      if (best == nullptr || logp > best_logp) { best_logp = logp; best = &m; best_path = path; }
+    }
+    int64_t n = 0;
+    auto number_of = [&](int64_t t) { return static_cast<int32_t>(best_path[t] / best->per_beat) + 1; };
+    if (correct) {  // every beat moves to the strongest activation inside its beat region
+      int64_t t = 0;
+      while (t < T) {
+        if (best->pointers[best_path[t]] >= 1) {
+          const int64_t left = t;
+          while (t < T && best->pointers[best_path[t]] >= 1) ++t;
+          int64_t arg = 0;  // np.argmax over the flattened [frames, 2] block
+          for (int64_t i = 1; i < 2 * (t - left); ++i)
+            if (act[2 * left + i] > act[2 * left + arg]) arg = i;
+          const int64_t peak = arg / 2 + left;
+          times[n] = static_cast<double>(peak + first) / fps;
+          numbers[n++] = number_of(peak);
+        } else {
+          ++t;
+        }
+      }
+    } else {
+      for (int64_t t = 1; t < T; ++t)
+        if (number_of(t) != number_of(t - 1)) { times[n] = static_cast<double>(t + first) / fps; numbers[n++] = number_of(t); }
+    }
+    return n;
+  }
+};
+
+}  // namespace
+
+extern "C" int bt_dbn_viterbi(const double* log_dens, int64_t T, int32_t beats, int32_t n_int, const int32_t* intervals,
+                              const double* log_tempo, const int32_t* pointers, int64_t* path_out, double* logp_out) {
+  if (!log_dens || !intervals || !log_tempo || !pointers || !path_out || !logp_out || T <= 0 || beats <= 0 || n_int <= 0)
+    return BT_ERR_ARG;
+  return viterbi(log_dens, T, beats, n_int, intervals, log_tempo, pointers, path_out, logp_out);
+}
+
+extern "C" int bt_dbn_track(const double* activations, const int64_t* frame_offsets, int32_t n_clips,
+                            const int32_t* beats_per_bar, int32_t n_bar_lengths, double min_bpm, double max_bpm,
+                            int32_t num_tempi, double transition_lambda, double observation_lambda, double threshold,
+                            int32_t correct, double fps, int32_t n_threads, double* times_out, int32_t* numbers_out,
+                            int64_t* counts_out) {
+  if (!activations || !frame_offsets || !beats_per_bar || !times_out || !numbers_out || !counts_out || n_clips < 0 ||
+      n_bar_lengths <= 0 || min_bpm <= 0 || max_bpm <= min_bpm || fps <= 0 || observation_lambda <= 1)
+    return BT_ERR_ARG;
+  Tracker trk;
+  trk.fps = fps; trk.threshold = threshold; trk.observation_lambda = observation_lambda; trk.correct = correct != 0;
+  trk.models.resize(n_bar_lengths);
+  for (int i = 0; i < n_bar_lengths; ++i) {
+    if (beats_per_bar[i] <= 0) return BT_ERR_ARG;
+    trk.models[i].build(beats_per_bar[i], 60.0 * fps / max_bpm, 60.0 * fps / min_bpm, num_tempi, transition_lambda, observation_lambda);
+  }
+  std::atomic<int32_t> next{0};
+  auto work = [&]() {
+    for (int32_t i = next.fetch_add(1); i < n_clips; i = next.fetch_add(1)) {
+      const int64_t f0 = frame_offsets[i], T = frame_offsets[i + 1] - f0;
+      counts_out[i] = T > 0 ? trk.track(activations + 2 * f0, T, times_out + f0, numbers_out + f0) : 0;
+    }
+  };
+  int nt = n_threads > 0 ? n_threads : static_cast<int>(std::thread::hardware_concurrency());
+  nt = std::max(1, std::min(nt, static_cast<int>(n_clips)));
+  std::vector<std::thread> pool;
+  for (int i = 1; i < nt; ++i) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
   return BT_OK;
 }

@@ -142,6 +142,9 @@ class DBNDownBeatTracker:
         self.fps = float(fps)
         self.threshold = threshold
         self.correct = correct
+        self.params = dict(beats_per_bar=[int(b) for b in np.atleast_1d(beats_per_bar)], min_bpm=float(min_bpm),
+                           max_bpm=float(max_bpm), num_tempi=int(num_tempi or 0), transition_lambda=float(transition_lambda),
+                           observation_lambda=float(observation_lambda))
         min_interval = 60.0 * fps / max_bpm
         max_interval = 60.0 * fps / min_bpm
         self.models = [_BarModel(b, min_interval, max_interval, num_tempi, transition_lambda, observation_lambda)
@@ -149,6 +152,41 @@ class DBNDownBeatTracker:
 
     def __call__(self, activations):
         """activations [T, 2] = (beat-but-not-downbeat, downbeat) probabilities -> [[time_s, beat_number], ...]."""
+        if _native() is not None:
+            return self.batch([activations])[0]
+        return self.track_numpy(activations)
+
+    def batch(self, activations_list, n_threads: int = 0):
+        """Many pieces at once on the C++ tracker of the shared library (bt_dbn_track: model construction, Viterbi
+        and peak correction in C++, one host thread per piece); `track_numpy` is its numpy twin."""
+        lib = _native()
+        if lib is None:
+            return [self.track_numpy(a) for a in activations_list]
+        acts = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1, 2) for a in activations_list]
+        fo = np.zeros(len(acts) + 1, dtype=np.int64)
+        for i, a in enumerate(acts):
+            fo[i + 1] = fo[i] + len(a)
+        cat = np.concatenate(acts) if acts else np.zeros((0, 2))
+        cat = np.ascontiguousarray(cat)
+        total = max(int(fo[-1]), 1)
+        times = np.empty(total, dtype=np.float64)
+        numbers = np.empty(total, dtype=np.int32)
+        counts = np.zeros(max(len(acts), 1), dtype=np.int64)
+        bpb = np.asarray(self.params["beats_per_bar"], dtype=np.int32)
+        p = self.params
+        code = lib.bt_dbn_track(cat.ctypes.data, fo.ctypes.data, len(acts), bpb.ctypes.data, len(bpb), p["min_bpm"], p["max_bpm"],
+                                p["num_tempi"], p["transition_lambda"], p["observation_lambda"], float(self.threshold or 0.0),
+                                int(bool(self.correct)), self.fps, int(n_threads), times.ctypes.data, numbers.ctypes.data,
+                                counts.ctypes.data)
+        if code != 0:
+            raise RuntimeError(f"bt_dbn_track failed ({code})")
+        out = []
+        for i in range(len(acts)):
+            a, n = int(fo[i]), int(counts[i])
+            out.append(np.vstack((times[a : a + n], numbers[a : a + n].astype(np.float64))).T if n else np.empty((0, 2)))
+        return out
+
+    def track_numpy(self, activations):
         act = np.asarray(activations, dtype=np.float64)
         first = 0
         if self.threshold:  # only decode between the first and the last frame that exceeds the threshold

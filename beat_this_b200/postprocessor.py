@@ -85,12 +85,16 @@ class Postprocessor:
         bp = bp * (1 - eps) + eps / 2
         dp = dp * (1 - eps) + eps / 2
 
-        def item(i):
+        def activation(i):  # the artificial multiclass prediction of postprocessor.py:159-167
             b = bp[frame_offsets[i] : frame_offsets[i + 1]]
             d = dp[frame_offsets[i] : frame_offsets[i + 1]]
-            act = np.vstack((np.maximum(b - d, eps / 2), d)).T
-            out = self.dbn(act)
+            return np.vstack((np.maximum(b - d, eps / 2), d)).T
+
+        def split(out):
             return out[:, 0], out[out[:, 1] == 1][:, 0]
 
-        with ThreadPoolExecutor() as ex:
-            return list(ex.map(item, range(len(frame_offsets) - 1)))
+        n = len(frame_offsets) - 1
+        if hasattr(self.dbn, "batch"):  # native tracker: all pieces in one multi-threaded C++ call
+            return [split(o) for o in self.dbn.batch([activation(i) for i in range(n)])]
+        with ThreadPoolExecutor() as ex:  # madmom: one piece per thread, as in the reference
+            return list(ex.map(lambda i: split(self.dbn(activation(i))), range(n)))

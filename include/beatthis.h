@@ -129,6 +129,19 @@ int bt_dbn_viterbi(const double* log_dens, int64_t T, int32_t beats, int32_t n_i
                    const int32_t* intervals, const double* log_tempo, const int32_t* pointers,
                    int64_t* path_out, double* logp_out);
 
+/* The whole DBN post-processing step of Postprocessor.postp_dbn (model/postprocessor.py:138-173) for many pieces
+ * at once, multi-threaded on the host: activations [total_frames][2] = (beat-but-not-downbeat, downbeat)
+ * probabilities as the reference builds them (:159-167), pieces at frame_offsets[n_clips+1].  Model parameters as
+ * in madmom's DBNDownBeatTrackingProcessor (reference values: beats_per_bar {3,4}, 55..215 BPM, num_tempi 60,
+ * transition_lambda 100, observation_lambda 16, threshold 0.05, correct 1, fps 50).  Piece i writes
+ * counts_out[i] (time [s], beat number) pairs at times_out / numbers_out + frame_offsets[i]; downbeats are the
+ * entries with number 1.  n_threads <= 0: hardware concurrency. */
+int bt_dbn_track(const double* activations, const int64_t* frame_offsets, int32_t n_clips,
+                 const int32_t* beats_per_bar, int32_t n_bar_lengths, double min_bpm, double max_bpm,
+                 int32_t num_tempi, double transition_lambda, double observation_lambda,
+                 double threshold, int32_t correct, double fps, int32_t n_threads,
+                 double* times_out, int32_t* numbers_out, int64_t* counts_out);
+
 /* Spect2Frames.spect2frames (inference.py:244-254): split_piece -> BeatThis.forward on
  * every chunk -> aggregate_prediction(keep_first).  spect_dev as produced by bt_logmel.
  * beat_dev / downbeat_dev: out, fp32 logits, concatenated with the same frame offsets. */

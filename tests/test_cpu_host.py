@@ -297,3 +297,32 @@ def test_native_dbn_tracks_synthetic_meters(lib_built):
     assert np.array_equal(np.round(out[:, 0] * 50).astype(int), frames)
     assert np.array_equal(out[:, 1].astype(int), [k % 3 + 1 for k in range(len(frames))])
     assert trk(np.full((200, 2), 0.001)).shape == (0, 2)
+
+
+def test_native_dbn_cxx_tracker_equals_numpy_twin(lib_built):
+    """bt_dbn_track (C++: model construction, Viterbi, peak correction, one thread per piece) against the numpy
+    implementation of the same definition, on noisy pulse trains incl. silent / one-frame / frame-0-only pieces,
+    and with log-spaced tempi (num_tempi smaller than the linear tempo grid)."""
+    from beat_this_b200.dbn import DBNDownBeatTracker
+
+    rng = np.random.default_rng(4)
+    pieces = []
+    for period, meter, T in ((23.7, 4, 900), (31.2, 3, 700), (17.0, 4, 400)):
+        act = rng.uniform(0.001, 0.08, (T, 2))
+        f, k = rng.uniform(0, period), 0
+        while f < T:
+            act[int(f)] = (0.05, 0.7) if k % meter == 0 else (0.75, 0.03)
+            f += period * (1 + 0.02 * rng.standard_normal())
+            k += 1
+        pieces.append(act)
+    only0 = np.full((50, 2), 0.001)
+    only0[0, 0] = 0.9
+    pieces += [np.full((120, 2), 0.001), np.full((1, 2), 0.4), only0]
+    for kw in ({}, {"num_tempi": 20}, {"correct": False}):
+        trk = DBNDownBeatTracker(**kw)
+        got = trk.batch(pieces, n_threads=3)
+        for act, g in zip(pieces, got):
+            ref = trk.track_numpy(act)
+            assert g.shape == ref.shape and np.array_equal(g, ref), kw
+        assert np.array_equal(trk(pieces[0]), got[0])
+    assert len(got[0]) > 20 and got[3].shape == (0, 2) and got[5].shape == (0, 2)
