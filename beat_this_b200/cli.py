@@ -22,23 +22,21 @@ from .utils import save_beat_tsv
 
 
 def build_parser() -> argparse.ArgumentParser:
-    ap = argparse.ArgumentParser(description="Detects beats in given audio files with a Beat This! model (B200 engine).")
-    ap.add_argument("inputs", type=str, nargs="+", help="An audio file to process, or a directory of such files. Can be given multiple times.")
-    ap.add_argument("--model", type=str, default="final0", help="Name or path of the checkpoint to use (default: %(default)s).")
-    ap.add_argument("--output", "-o", type=str, default=None,
-                    help="Output file name for a single input file, or output directory for multiple input files. If omitted, "
-                         "outputs are saved next to each input file (see --suffix and --append).")
-    ap.add_argument("--suffix", "-s", type=str, default=".beats",
-                    help="Suffix for output file names (default: %(default)s). Ignored if an explicit output file name is given.")
-    ap.add_argument("--append", action="store_true", help="Append the suffix to the file name instead of replacing the existing suffix.")
-    ap.add_argument("--skip-existing", action="store_true", help="Do not overwrite existing output files, skip them.")
-    ap.add_argument("--touch-first", action="store_true",
-                    help="Create the empty output file before processing. With --skip-existing several processes can share one file set.")
-    ap.add_argument("--dbn", default=False, action=argparse.BooleanOptionalAction, help="Use madmom's DBN postprocessing (needs madmom on the host).")
-    ap.add_argument("--gpu", type=int, default=None, help="Which GPU to use (default: LOCAL_RANK under torchrun, else 0). There is no CPU path.")
-    ap.add_argument("--float16", action="store_true", help="bf16 tensor-core path (the fast one) instead of the fp32 CUDA-core path.")
-    ap.add_argument("--activations", action="store_true", help="Also save the raw activations with a .npy suffix.")
-    ap.add_argument("--batch", type=int, default=32, help="Files per device batch (default: %(default)s).")
+    ap = argparse.ArgumentParser(prog="beat_this_b200", description="Beat and downbeat times for audio files (Beat This! model on the B200 engine).")
+    add = ap.add_argument
+    add("inputs", nargs="+", help="audio files and/or directories that are searched recursively")
+    add("--model", default="final0", help="checkpoint name or path [%(default)s]")
+    add("--output", "-o", default=None, help="result file (one input file) or result directory; default: next to each input")
+    add("--suffix", "-s", default=".beats", help="extension of the result files [%(default)s]")
+    add("--append", action="store_true", help="keep the audio extension and add the suffix after it")
+    add("--skip-existing", action="store_true", help="leave results that already exist untouched")
+    add("--touch-first", action="store_true", help="create the (empty) result file before working on it: with --skip-existing, "
+                                                   "several processes can split one directory between them")
+    add("--dbn", default=False, action=argparse.BooleanOptionalAction, help="DBN post-processing on the host instead of peak picking")
+    add("--gpu", type=int, default=None, help="CUDA device index [LOCAL_RANK or 0]; a GPU is required")
+    add("--float16", action="store_true", help="bf16 tensor-core kernels (fast path) instead of fp32")
+    add("--activations", action="store_true", help="also write the frame activations as <result>.npy (2 x frames)")
+    add("--batch", type=int, default=32, help="files per device batch [%(default)s]")
     return ap
 
 
