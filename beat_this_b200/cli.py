@@ -1,9 +1,10 @@
 #!/usr/bin/env python3
 """``beat_this`` command line tool on the B200 engine (reference beat_this/cli.py:22-191: same options, same
 output naming, same ``.beats`` / ``.npy`` files), re-organised around the batched device path: the work list is
-built first, files are decoded and pushed through ``Audio2Frames`` / the device peak picker ``--batch`` files at
-a time (files of one sample rate share a launch), and under ``torchrun`` every rank takes every WORLD_SIZE-th
-task (tasks are independent: no collective).
+built first, then ``--batch`` files at a time are claimed and handed to ``File2Beats.batch`` (native WAV decode on
+host threads -> pinned ring -> device, groups of one sample rate share launches, decode of the next group overlaps
+the kernels of the current one); under ``torchrun`` every rank takes every WORLD_SIZE-th task (tasks are
+independent: no collective).  A file that fails costs only itself, and its --touch-first placeholder is removed.
 
     python -m beat_this_b200.cli song.wav                     # -> song.beats
     python -m beat_this_b200.cli music_dir -o out --float16    # directory tree -> out/.../*.beats
@@ -34,9 +35,9 @@ def build_parser() -> argparse.ArgumentParser:
                                                    "several processes can split one directory between them")
     add("--dbn", default=False, action=argparse.BooleanOptionalAction, help="DBN post-processing on the host instead of peak picking")
     add("--gpu", type=int, default=None, help="CUDA device index [LOCAL_RANK or 0]; a GPU is required")
-    add("--float16", action="store_true", help="bf16 tensor-core kernels (fast path) instead of fp32")
+    add("--float16", action="store_true", help="fp16 tensor-core kernels (fast path) instead of fp32")
     add("--activations", action="store_true", help="also write the frame activations as <result>.npy (2 x frames)")
-    add("--batch", type=int, default=32, help="files per device batch [%(default)s]")
+    add("--batch", type=int, default=256, help="files claimed and queued at a time [%(default)s]; the device works on groups of up to 64 clips")
     return ap
 
 
@@ -85,9 +86,20 @@ def _claim(dst: Path, skip_existing: bool, touch_first: bool) -> bool:
     return not (skip_existing and dst.exists())
 
 
+def _release(dst: Path, touch_first: bool) -> None:
+    """A file we claimed with --touch-first but could not process: remove the empty placeholder again, otherwise a
+    rerun with --skip-existing would silently skip it."""
+    if touch_first:
+        try:
+            if dst.exists() and dst.stat().st_size == 0:
+                dst.unlink()
+        except OSError:
+            pass
+
+
 def run(inputs, model="final0", output=None, suffix=".beats", append=False, skip_existing=False, touch_first=False,
-        dbn=False, gpu=None, float16=False, activations=False, batch=32) -> int:
-    from .inference import Audio2Beats
+        dbn=False, gpu=None, float16=False, activations=False, batch=256) -> int:
+    from .inference import File2Beats
     from .preprocessing import load_audio
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -97,39 +109,55 @@ def run(inputs, model="final0", output=None, suffix=".beats", append=False, skip
         raise SystemExit("beat_this_b200 has no CPU path: --gpu must name a CUDA device")
     tasks, single = collect_tasks(inputs, output, suffix, append, skip_existing)
     tasks = tasks[rank::world]
-    a2b = Audio2Beats(model, f"cuda:{gpu}", float16, dbn)
+    f2b = File2Beats(model, f"cuda:{gpu}", float16, dbn)
     failed = 0
-    for b0 in range(0, len(tasks), max(1, batch)):
-        group = []
-        for src, dst in tasks[b0 : b0 + max(1, batch)]:
-            if not single and not _claim(dst, skip_existing, touch_first):
-                continue
-            try:
+
+    def fail(src, dst, why=""):
+        nonlocal failed
+        failed += 1
+        _release(dst, touch_first)
+        print(f'Could not process "{src}"{why}. Rerun with this file alone for details.', file=sys.stderr)
+
+    step = max(1, batch)
+    for b0 in range(0, len(tasks), step):
+        # claim right before working on a slice, so that several processes can share one directory (cli.py:178-184)
+        group = [(src, dst) for src, dst in tasks[b0 : b0 + step] if single or _claim(dst, skip_existing, touch_first)]
+        if not group:
+            continue
+        if single:  # one file: let errors surface, as the reference does for its single-file case
+            src, dst = group[0]
+            if activations:
                 wav, sr = load_audio(src)
-                group.append((src, dst, wav, sr))
-            except Exception as e:
-                if single:
-                    raise
-                failed += 1
-                print(f'Could not load "{src}": {e}', file=sys.stderr)
-        for sr in sorted({g[3] for g in group}):
-            same = [g for g in group if g[3] == sr]
-            try:
-                beat, down, fo = a2b._frames_batch([g[2] for g in same], sr)
-                times = a2b.frames2beats.batch_cat(beat, down, fo)
-            except Exception as e:
-                if single:
-                    raise
-                failed += len(same)
-                print(f"Could not process a batch of {len(same)} file(s) at {sr} Hz ({e}); rerun them one by one for details.", file=sys.stderr)
-                continue
-            beat_h, down_h = beat.cpu().numpy(), down.cpu().numpy()
-            for i, (src, dst, _, _) in enumerate(same):
-                beats, downbeats = times[i]
-                if activations:  # reference cli.py:139-147: vstack([beat, downbeat]) next to the .beats file
+                beat, down = f2b.spect2frames(f2b.signal2spect(wav, sr))
+                dst.parent.mkdir(parents=True, exist_ok=True)
+                np.save(dst.with_suffix(".npy"), np.vstack([beat.cpu().numpy(), down.cpu().numpy()]))
+                beats, downbeats = f2b.frames2beats(beat, down)
+            else:
+                beats, downbeats = f2b(src)
+            save_beat_tsv(beats, downbeats, dst)
+            continue
+        if activations:  # logits wanted on the host as well: one file at a time through the three public stages
+            for src, dst in group:
+                try:
+                    wav, sr = load_audio(src)
+                    beat, down = f2b.spect2frames(f2b.signal2spect(wav, sr))
                     dst.parent.mkdir(parents=True, exist_ok=True)
-                    np.save(dst.with_suffix(".npy"), np.vstack([beat_h[fo[i] : fo[i + 1]], down_h[fo[i] : fo[i + 1]]]))
-                save_beat_tsv(beats, downbeats, dst)
+                    np.save(dst.with_suffix(".npy"), np.vstack([beat.cpu().numpy(), down.cpu().numpy()]))
+                    save_beat_tsv(*f2b.frames2beats(beat, down), dst)
+                except Exception:
+                    fail(src, dst)
+            continue
+        # a failure inside a device batch costs only the file that caused it: File2Beats.batch(on_error="skip")
+        # retries the files of a failed batch one by one and reports None for the ones that really fail
+        results = f2b.batch([src for src, _ in group], on_error="skip")
+        for (src, dst), res in zip(group, results):
+            if res is None:
+                fail(src, dst)
+                continue
+            try:
+                save_beat_tsv(res[0], res[1], dst)
+            except Exception:
+                fail(src, dst, " (writing the result failed)")
     return 1 if failed else 0
 
 

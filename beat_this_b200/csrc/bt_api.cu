@@ -2,6 +2,7 @@
 // and the per-wave schedule of the BeatThis forward pass (reference
 // beat_this/model/beat_tracker.py:188-192, math restated in SURVEY.md App. A.3).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -30,6 +31,26 @@ struct Param {
 
 struct AttnW { const Param *wqkv, *wg, *bg, *wout; };
 struct FfW { const Param *w1, *b1, *w2, *b2; };
+// every parameter the forward pass touches, resolved once in bt_finalize (no name lookups per launch)
+struct ModelW {
+  const Param *rope_cos = nullptr, *rope_sin = nullptr, *bn1_scale = nullptr, *bn1_shift = nullptr, *stem_w = nullptr,
+              *stem_b = nullptr, *lin_w = nullptr, *lin_b = nullptr, *head_w = nullptr, *head_b = nullptr;
+  AttnW fa[3]{}, ta[3]{};
+  FfW ff_f[3]{}, ff_t[3]{};
+  const Param *conv_w[3] = {nullptr, nullptr, nullptr}, *conv_b[3] = {nullptr, nullptr, nullptr};
+  std::vector<AttnW> la;
+  std::vector<FfW> lf;
+};
+// small host -> device tables (offsets, chunk descriptors) travel through a ring of pinned slots: a slot is only
+// waited for when it comes round again, kStageSlots uploads later, so no API call blocks on earlier GPU work
+constexpr int kStageSlots = 16;
+struct StageSlot {
+  void* host = nullptr;
+  void* dev = nullptr;
+  size_t cap = 0;
+  cudaEvent_t ev = nullptr;
+  bool pending = false;
+};
 
 // tensor-core plans for one (wave size, chunk length) geometry
 struct AttnPlans { TcGemmPlan *qkv = nullptr, *out = nullptr, *gates = nullptr; TcAttnPlan* attn = nullptr; TcQkvPlan* fqkv = nullptr; };
@@ -68,14 +89,12 @@ struct bt_ctx {
   float* spect_ws = nullptr;
   int64_t spect_cap = 0;
   // pinned staging + device tables
-  void* stage_host = nullptr;
-  size_t stage_cap = 0;
-  void* stage_dev = nullptr;
-  size_t stage_dev_cap = 0;
-  cudaEvent_t stage_ev = nullptr;
-  bool stage_pending = false;
+  StageSlot stage[kStageSlots];
+  int stage_next = 0;
+  ModelW mw;
 
   std::map<std::pair<int, int>, WavePlans*> plans;
+  std::vector<std::pair<int, int>> plan_order;  // insertion order: oldest geometry is evicted first
 
   // per-kernel-class device timing (bt_profile_*): one event after every launch; the
   // duration of a launch is the gap to the previous event on the same stream
@@ -187,32 +206,32 @@ int64_t chunks_for(int64_t T, int64_t* starts, int64_t* lens, int64_t cap) {
   return n;
 }
 
-int ensure_stage(bt_ctx* c, size_t bytes) {
-  if (c->stage_pending) {
-    BT_CUDA(c, cudaEventSynchronize(c->stage_ev));
-    c->stage_pending = false;
+int acquire_stage(bt_ctx* c, size_t bytes, StageSlot** out) {
+  StageSlot* sl = &c->stage[c->stage_next];
+  c->stage_next = (c->stage_next + 1) % kStageSlots;
+  if (sl->pending) {  // kStageSlots uploads ago: long finished unless the caller is that far ahead of the GPU
+    BT_CUDA(c, cudaEventSynchronize(sl->ev));
+    sl->pending = false;
   }
-  if (bytes > c->stage_cap) {
-    if (c->stage_host) cudaFreeHost(c->stage_host);
-    c->stage_host = nullptr;
-    size_t cap = std::max<size_t>(bytes * 2, 1 << 16);
-    BT_CUDA(c, cudaMallocHost(&c->stage_host, cap));
-    c->stage_cap = cap;
+  if (!sl->ev) BT_CUDA(c, cudaEventCreateWithFlags(&sl->ev, cudaEventDisableTiming));
+  if (bytes > sl->cap) {
+    if (sl->host) cudaFreeHost(sl->host);
+    if (sl->dev) cudaFree(sl->dev);
+    sl->host = sl->dev = nullptr;
+    sl->cap = 0;
+    const size_t cap = std::max<size_t>(bytes * 2, 1 << 16);
+    BT_CUDA(c, cudaMallocHost(&sl->host, cap));
+    BT_CUDA(c, cudaMalloc(&sl->dev, cap));
+    sl->cap = cap;
   }
-  if (bytes > c->stage_dev_cap) {
-    if (c->stage_dev) cudaFree(c->stage_dev);
-    c->stage_dev = nullptr;
-    size_t cap = std::max<size_t>(bytes * 2, 1 << 16);
-    BT_CUDA(c, cudaMalloc(&c->stage_dev, cap));
-    c->stage_dev_cap = cap;
-  }
+  *out = sl;
   return BT_OK;
 }
 
-int upload_stage(bt_ctx* c, size_t bytes, cudaStream_t st) {
-  BT_CUDA(c, cudaMemcpyAsync(c->stage_dev, c->stage_host, bytes, cudaMemcpyHostToDevice, st));
-  BT_CUDA(c, cudaEventRecord(c->stage_ev, st));
-  c->stage_pending = true;
+int upload_stage(bt_ctx* c, StageSlot* sl, size_t bytes, cudaStream_t st) {
+  BT_CUDA(c, cudaMemcpyAsync(sl->dev, sl->host, bytes, cudaMemcpyHostToDevice, st));
+  BT_CUDA(c, cudaEventRecord(sl->ev, st));
+  sl->pending = true;
   return BT_OK;
 }
 
@@ -226,32 +245,34 @@ void free_ws(bt_ctx* c) {
   c->ws_wave = 0;
 }
 
-void free_plans(bt_ctx* c) {
-  for (auto& kv : c->plans) {
-    WavePlans* w = kv.second;
-    auto fa = [](AttnPlans& a) {
-      if (a.qkv) tc_gemm_plan_destroy(a.qkv);
-      if (a.out) tc_gemm_plan_destroy(a.out);
-      if (a.gates) tc_gemm_plan_destroy(a.gates);
-      if (a.fqkv) tc_qkv_plan_destroy(a.fqkv);
-      if (a.attn) tc_attn_plan_destroy(a.attn);
-    };
-    auto ff = [](FfPlans& f) {
-      if (f.fused) tc_ff_plan_destroy(f.fused);
-      if (f.fused_op) tc_ff_plan_destroy(f.fused_op);
-      if (f.ff1) tc_gemm_plan_destroy(f.ff1);
-      if (f.ff2) tc_gemm_plan_destroy(f.ff2);
-    };
-    for (int i = 0; i < 3; ++i) {
-      fa(w->fa[i]); fa(w->ta[i]); ff(w->ff_f[i]); ff(w->ff_t[i]);
-      if (w->conv[i]) tc_gemm_plan_destroy(w->conv[i]);
-    }
-    if (w->lin) tc_gemm_plan_destroy(w->lin);
-    for (auto& a : w->la) fa(a);
-    for (auto& f : w->lf) ff(f);
-    delete w;
+void destroy_wave_plans(WavePlans* w) {
+  auto fa = [](AttnPlans& a) {
+    if (a.qkv) tc_gemm_plan_destroy(a.qkv);
+    if (a.out) tc_gemm_plan_destroy(a.out);
+    if (a.gates) tc_gemm_plan_destroy(a.gates);
+    if (a.fqkv) tc_qkv_plan_destroy(a.fqkv);
+    if (a.attn) tc_attn_plan_destroy(a.attn);
+  };
+  auto ff = [](FfPlans& f) {
+    if (f.fused) tc_ff_plan_destroy(f.fused);
+    if (f.fused_op) tc_ff_plan_destroy(f.fused_op);
+    if (f.ff1) tc_gemm_plan_destroy(f.ff1);
+    if (f.ff2) tc_gemm_plan_destroy(f.ff2);
+  };
+  for (int i = 0; i < 3; ++i) {
+    fa(w->fa[i]); fa(w->ta[i]); ff(w->ff_f[i]); ff(w->ff_t[i]);
+    if (w->conv[i]) tc_gemm_plan_destroy(w->conv[i]);
   }
+  if (w->lin) tc_gemm_plan_destroy(w->lin);
+  for (auto& a : w->la) fa(a);
+  for (auto& f : w->lf) ff(f);
+  delete w;
+}
+
+void free_plans(bt_ctx* c) {
+  for (auto& kv : c->plans) destroy_wave_plans(kv.second);
   c->plans.clear();
+  c->plan_order.clear();
 }
 
 // elements per chunk of the largest frontend activation: F*L*C is the same for all blocks
@@ -270,7 +291,7 @@ int ensure_ws(bt_ctx* c, int need_chunks) {
   const int64_t D = c->hp.transformer_dim;
   const int64_t me = static_cast<int64_t>(BT_CHUNK) * D;                 // main tokens * dim
   const int64_t xe = std::max(fe, me);
-  const size_t act = c->dtype == BT_DTYPE_BF16 ? 2 : 4;
+  const size_t act = c->dtype == BT_DTYPE_H16 ? 2 : 4;
   BT_CUDA(c, cudaMalloc(&c->X0, G * xe * 4));
   BT_CUDA(c, cudaMalloc(&c->X1, G * xe * 4));
   BT_CUDA(c, cudaMalloc(&c->GATES, G * std::max<int64_t>(fe / 32, BT_CHUNK * (D / 32)) * 4));
@@ -278,7 +299,7 @@ int ensure_ws(bt_ctx* c, int need_chunks) {
   BT_CUDA(c, cudaMalloc(&c->QKV, G * 3 * xe * act));
   BT_CUDA(c, cudaMalloc(&c->O, G * xe * act));
   BT_CUDA(c, cudaMalloc(&c->H, G * 4 * xe * act));
-  if (c->dtype == BT_DTYPE_BF16) {
+  if (c->dtype == BT_DTYPE_H16) {
     BT_CUDA(c, cudaMalloc(&c->XB, G * xe * 2));
   }
   c->ws_wave = want;
@@ -292,10 +313,10 @@ struct Wave {
 };
 
 int do_tap(bt_ctx* c, const char* name, const void* buf, int64_t count, bool is_act, cudaStream_t st) {
-  if (c->tap_name.empty() || c->tap_name != name || !c->tap_out) return BT_OK;
+  if (c->tap_name.empty() || !c->tap_out || c->tap_name != name) return BT_OK;
   if (count > c->tap_cap) return fail(c, BT_ERR_ARG, "tap %s needs %lld floats", name, (long long)count);
-  if (is_act && c->dtype == BT_DTYPE_BF16) {
-    launch_bf16_to_f32(buf, c->tap_out, count, st);
+  if (is_act && c->dtype == BT_DTYPE_H16) {
+    launch_h16_to_f32(buf, c->tap_out, count, st);
     BT_LAUNCHED(c, "tap_convert", st);
   } else {
     BT_CUDA(c, cudaMemcpyAsync(c->tap_out, buf, count * 4, cudaMemcpyDeviceToDevice, st));
@@ -312,7 +333,7 @@ GemmShape plain_shape(int planes, int L, int N, int K, int lda) {
 
 int run_gemm(bt_ctx* c, const void* A, const Param* W, TcGemmPlan* plan, const GemmShape& g,
              const EpiParams& e, const char* what, cudaStream_t st) {
-  if (c->dtype == BT_DTYPE_BF16) {
+  if (c->dtype == BT_DTYPE_H16) {
     if (launch_gemm_tc(plan, e, st) != 0) return fail(c, BT_ERR_CUDA, "tc gemm launch %s failed", what);
   } else {
     launch_gemm_simt(reinterpret_cast<const float*>(A), W->f32, g, e, st);
@@ -338,7 +359,7 @@ EpiParams epi_generic(const Param* bias, int gelu, const float* resid, int ldr, 
 // skip_out: the out-projection + residual are done by the following fused FFN kernel (fused_ff_kernel<C, true>).
 int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool freq, const AttnW& w,
                     AttnPlans* tp, int nb, cudaStream_t st, bool skip_out = false) {
-  const bool tc = c->dtype == BT_DTYPE_BF16;
+  const bool tc = c->dtype == BT_DTYPE_H16;
   const int heads = C / kHeadDim;
   const int64_t M = static_cast<int64_t>(planes) * L;
   const float inv_sqrt_d = 0.17677669529663687f;  // 1/sqrt(32): SDPA default scale (roformer.py:78-80)
@@ -346,7 +367,7 @@ int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool f
   const float qscale = tc_time ? inv_sqrt_d * 1.4426950408889634f : 1.0f;
   int r = BT_OK;
   if (tc && tp && tp->fqkv) {  // narrow frontend attentions: norm + gates + QKV + RoPE in one kernel
-    if (launch_fused_qkv(tp->fqkv, X, w.wg->f32, w.bg->f32, find_param(c, "rope.cos")->f32, find_param(c, "rope.sin")->f32,
+    if (launch_fused_qkv(tp->fqkv, X, w.wg->f32, w.bg->f32, c->mw.rope_cos->f32, c->mw.rope_sin->f32,
                          c->QKV, c->GATES, L, F, freq ? 1 : 0, qscale, st) != 0)
       return fail(c, BT_ERR_CUDA, "fused qkv launch failed");
     BT_LAUNCHED(c, "qkv_fused", st);
@@ -369,8 +390,8 @@ int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool f
     EpiParams e{};
     e.kind = 1;
     e.out_act = c->QKV; e.ldo_act = 3 * C;
-    e.rope_cos = find_param(c, "rope.cos")->f32;
-    e.rope_sin = find_param(c, "rope.sin")->f32;
+    e.rope_cos = c->mw.rope_cos->f32;
+    e.rope_sin = c->mw.rope_sin->f32;
     e.C = C; e.heads = heads; e.posmode = freq ? 1 : 0; e.F = F;
     e.qscale = qscale;
     GemmShape g = plain_shape(planes, L, 3 * C, C, C);
@@ -397,7 +418,7 @@ int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool f
 // x += ff(x) (reference roformer.py:38-61); optionally also writes a bf16 copy of the result.
 int ff_block(bt_ctx* c, float* X, int planes, int L, int C, int mult, const FfW& w, FfPlans* tp, void* copy_act,
              cudaStream_t st, bool with_outproj = false) {
-  const bool tc = c->dtype == BT_DTYPE_BF16;
+  const bool tc = c->dtype == BT_DTYPE_H16;
   const int64_t M = static_cast<int64_t>(planes) * L;
   if (with_outproj && !(tc && tp && tp->fused_op)) return fail(c, BT_ERR_ARG, "fused out-projection requested without a plan");
   if (tc && tp && tp->fused) {
@@ -447,9 +468,15 @@ int build_plans(bt_ctx* c, int nb, int L, WavePlans** out) {
   auto key = std::make_pair(nb, L);
   auto it = c->plans.find(key);
   if (it != c->plans.end()) { *out = it->second; return BT_OK; }
-  if (c->plans.size() > 96) free_plans(c);
+  // bounded cache: tensor maps are copied into the kernel parameters at launch, so dropping the oldest geometry is
+  // safe while its kernels are still in flight
+  constexpr size_t kMaxPlans = 48;
+  while (c->plans.size() >= kMaxPlans && !c->plan_order.empty()) {
+    auto old = c->plans.find(c->plan_order.front());
+    if (old != c->plans.end()) { destroy_wave_plans(old->second); c->plans.erase(old); }
+    c->plan_order.erase(c->plan_order.begin());
+  }
   WavePlans* w = new WavePlans();
-  c->plans[key] = w;
   char err[512] = "";
   auto mk = [&](const void* A, const Param* W, const GemmShape& g, int planes_in) -> TcGemmPlan* {
     return tc_gemm_plan_create(A, W->b16, g, planes_in, err, sizeof(err));
@@ -485,37 +512,42 @@ int build_plans(bt_ctx* c, int nb, int L, WavePlans** out) {
   for (int i = 0; i < 3 && ok; ++i) {
     const std::string p = "b" + std::to_string(i);
     if (c->hp.partial_transformers) {
-      ok = ok && mk_attn(w->fa[i], attn_w(c, p + ".attnF"), nb * F, C, true);
-      ok = ok && mk_ff(w->ff_f[i], ff_w(c, p + ".ffF"), nb * F, C, 4, attn_w(c, p + ".attnF").wout);
-      ok = ok && mk_attn(w->ta[i], attn_w(c, p + ".attnT"), nb * F, C, false);
-      ok = ok && mk_ff(w->ff_t[i], ff_w(c, p + ".ffT"), nb * F, C, 4, attn_w(c, p + ".attnT").wout);
+      ok = ok && mk_attn(w->fa[i], c->mw.fa[i], nb * F, C, true);
+      ok = ok && mk_ff(w->ff_f[i], c->mw.ff_f[i], nb * F, C, 4, c->mw.fa[i].wout);
+      ok = ok && mk_attn(w->ta[i], c->mw.ta[i], nb * F, C, false);
+      ok = ok && mk_ff(w->ff_t[i], c->mw.ff_t[i], nb * F, C, 4, c->mw.ta[i].wout);
     }
     if (ok) {
-      w->conv[i] = mk(c->XB, find_param(c, p + ".conv.w"), conv_shape(nb, F, L, C), nb * F);
+      w->conv[i] = mk(c->XB, c->mw.conv_w[i], conv_shape(nb, F, L, C), nb * F);
       ok = w->conv[i] != nullptr;
     }
     C *= 2; F /= 2;
   }
   const int D = c->hp.transformer_dim;
   if (ok) {
-    w->lin = mk(c->XN, find_param(c, "lin.w"), lin_shape(nb, L, D, F, C), nb * F);
+    w->lin = mk(c->XN, c->mw.lin_w, lin_shape(nb, L, D, F, C), nb * F);
     ok = w->lin != nullptr;
   }
   w->la.resize(c->hp.n_layers);
   w->lf.resize(c->hp.n_layers);
   for (int l = 0; l < c->hp.n_layers && ok; ++l) {
     const std::string p = "l" + std::to_string(l);
-    ok = ok && mk_attn(w->la[l], attn_w(c, p + ".attn"), nb, D, false);
-    ok = ok && mk_ff(w->lf[l], ff_w(c, p + ".ff"), nb, D, c->hp.ff_mult);
+    ok = ok && mk_attn(w->la[l], c->mw.la[l], nb, D, false);
+    ok = ok && mk_ff(w->lf[l], c->mw.lf[l], nb, D, c->hp.ff_mult);
   }
-  if (!ok) return fail(c, BT_ERR_CUDA, "tensor-core plan creation failed: %s", err);
+  if (!ok) {  // never cache a half-built entry
+    destroy_wave_plans(w);
+    return fail(c, BT_ERR_CUDA, "tensor-core plan creation failed: %s", err);
+  }
+  c->plans[key] = w;
+  c->plan_order.push_back(key);
   *out = w;
   return BT_OK;
 }
 
 // BeatThis.forward for one wave of nb equal-length chunks, scattering the head output.
 int run_wave(bt_ctx* c, const float* spect, const Wave& wv, float* beat, float* down, cudaStream_t st) {
-  const bool tc = c->dtype == BT_DTYPE_BF16;
+  const bool tc = c->dtype == BT_DTYPE_H16;
   const int nb = wv.nb, L = wv.L;
   WavePlans* wp = nullptr;
   if (tc) {
@@ -526,9 +558,7 @@ int run_wave(bt_ctx* c, const float* spect, const Wave& wv, float* beat, float* 
   float* X = c->X0;
   float* Xalt = c->X1;
   int C = c->hp.stem_dim, F = c->hp.spect_dim / 4;
-  launch_stem(spect, wv.chunks_dev, nb, L, find_param(c, "stem.bn1_scale")->f32,
-              find_param(c, "stem.bn1_shift")->f32, find_param(c, "stem.w")->f32,
-              find_param(c, "stem.bias")->f32, X, st);
+  launch_stem(spect, wv.chunks_dev, nb, L, c->mw.bn1_scale->f32, c->mw.bn1_shift->f32, c->mw.stem_w->f32, c->mw.stem_b->f32, X, st);
   BT_LAUNCHED(c, "stem", st);
   if ((r = do_tap(c, "stem", X, static_cast<int64_t>(nb) * F * L * C, false, st)) != BT_OK) return r;
   for (int i = 0; i < 3; ++i) {
@@ -539,26 +569,26 @@ int run_wave(bt_ctx* c, const float* spect, const Wave& wv, float* beat, float* 
     if (c->hp.partial_transformers) {
       // out-projection + residual of an attention move into the following fused FFN kernel when there is a plan
       // for it (C = 32 / 64) and nobody asked to see the intermediate residual stream (debug tap)
-      const bool op_f = wp && wp->ff_f[i].fused_op && c->tap_name != p + ".attnF";
-      const bool op_t = wp && wp->ff_t[i].fused_op && c->tap_name != p + ".attnT";
-      if ((r = attention_block(c, X, planes, L, C, F, true, attn_w(c, p + ".attnF"), wp ? &wp->fa[i] : nullptr, nb, st, op_f)) != BT_OK) return r;
+      const bool op_f = wp && wp->ff_f[i].fused_op && (c->tap_name.empty() || c->tap_name != p + ".attnF");
+      const bool op_t = wp && wp->ff_t[i].fused_op && (c->tap_name.empty() || c->tap_name != p + ".attnT");
+      if ((r = attention_block(c, X, planes, L, C, F, true, c->mw.fa[i], wp ? &wp->fa[i] : nullptr, nb, st, op_f)) != BT_OK) return r;
       if ((r = do_tap(c, (p + ".attnF").c_str(), X, elems, false, st)) != BT_OK) return r;
-      if ((r = ff_block(c, X, planes, L, C, 4, ff_w(c, p + ".ffF"), wp ? &wp->ff_f[i] : nullptr, nullptr, st, op_f)) != BT_OK) return r;
+      if ((r = ff_block(c, X, planes, L, C, 4, c->mw.ff_f[i], wp ? &wp->ff_f[i] : nullptr, nullptr, st, op_f)) != BT_OK) return r;
       if ((r = do_tap(c, (p + ".ffF").c_str(), X, elems, false, st)) != BT_OK) return r;
-      if ((r = attention_block(c, X, planes, L, C, F, false, attn_w(c, p + ".attnT"), wp ? &wp->ta[i] : nullptr, nb, st, op_t)) != BT_OK) return r;
+      if ((r = attention_block(c, X, planes, L, C, F, false, c->mw.ta[i], wp ? &wp->ta[i] : nullptr, nb, st, op_t)) != BT_OK) return r;
       if ((r = do_tap(c, (p + ".attnT").c_str(), X, elems, false, st)) != BT_OK) return r;
-      if ((r = ff_block(c, X, planes, L, C, 4, ff_w(c, p + ".ffT"), wp ? &wp->ff_t[i] : nullptr, copy_for_conv, st, op_t)) != BT_OK) return r;
+      if ((r = ff_block(c, X, planes, L, C, 4, c->mw.ff_t[i], wp ? &wp->ff_t[i] : nullptr, copy_for_conv, st, op_t)) != BT_OK) return r;
       if ((r = do_tap(c, (p + ".ffT").c_str(), X, elems, false, st)) != BT_OK) return r;
     } else if (tc) {
-      launch_f32_to_bf16(X, c->XB, elems, st);
-      BT_LAUNCHED(c, "f32_to_bf16", st);
+      launch_f32_to_h16(X, c->XB, elems, st);
+      BT_LAUNCHED(c, "f32_to_h16", st);
     }
     // conv C -> 2C (+ folded BN2d + GELU); the last block feeds frontend.linear (activation dtype)
     GemmShape g = conv_shape(nb, F, L, C);
     const bool last = i == 2;
-    EpiParams e = epi_generic(find_param(c, p + ".conv.bias"), 1, nullptr, 0, last ? nullptr : Xalt, 2 * C,
+    EpiParams e = epi_generic(c->mw.conv_b[i], 1, nullptr, 0, last ? nullptr : Xalt, 2 * C,
                               last ? c->XN : nullptr, 2 * C);
-    if ((r = run_gemm(c, tc ? c->XB : static_cast<const void*>(X), find_param(c, p + ".conv.w"),
+    if ((r = run_gemm(c, tc ? c->XB : static_cast<const void*>(X), c->mw.conv_w[i],
                       wp ? wp->conv[i] : nullptr, g, e, "gemm_conv", st)) != BT_OK) return r;
     C *= 2; F /= 2;
     if (!last) std::swap(X, Xalt);
@@ -568,19 +598,46 @@ int run_wave(bt_ctx* c, const float* spect, const Wave& wv, float* beat, float* 
   const int D = c->hp.transformer_dim;
   {
     GemmShape g = lin_shape(nb, L, D, F, C);
-    EpiParams e = epi_generic(find_param(c, "lin.b"), 0, nullptr, 0, X, D, nullptr, 0);
-    if ((r = run_gemm(c, c->XN, find_param(c, "lin.w"), wp ? wp->lin : nullptr, g, e, "gemm_frontend_linear", st)) != BT_OK) return r;
+    EpiParams e = epi_generic(c->mw.lin_b, 0, nullptr, 0, X, D, nullptr, 0);
+    if ((r = run_gemm(c, c->XN, c->mw.lin_w, wp ? wp->lin : nullptr, g, e, "gemm_frontend_linear", st)) != BT_OK) return r;
     if ((r = do_tap(c, "frontend", X, static_cast<int64_t>(nb) * L * D, false, st)) != BT_OK) return r;
   }
   for (int l = 0; l < c->hp.n_layers; ++l) {
     const std::string p = "l" + std::to_string(l);
-    if ((r = attention_block(c, X, nb, L, D, 1, false, attn_w(c, p + ".attn"), wp ? &wp->la[l] : nullptr, nb, st)) != BT_OK) return r;
+    if ((r = attention_block(c, X, nb, L, D, 1, false, c->mw.la[l], wp ? &wp->la[l] : nullptr, nb, st)) != BT_OK) return r;
     if ((r = do_tap(c, (p + ".attn").c_str(), X, static_cast<int64_t>(nb) * L * D, false, st)) != BT_OK) return r;
-    if ((r = ff_block(c, X, nb, L, D, c->hp.ff_mult, ff_w(c, p + ".ff"), wp ? &wp->lf[l] : nullptr, nullptr, st)) != BT_OK) return r;
+    if ((r = ff_block(c, X, nb, L, D, c->hp.ff_mult, c->mw.lf[l], wp ? &wp->lf[l] : nullptr, nullptr, st)) != BT_OK) return r;
     if ((r = do_tap(c, (p + ".ff").c_str(), X, static_cast<int64_t>(nb) * L * D, false, st)) != BT_OK) return r;
   }
-  launch_head(X, D, find_param(c, "head.w")->f32, find_param(c, "head.b")->f32, wv.chunks_dev, nb, L, beat, down, c->hp.sum_head ? 1 : 0, st);
+  launch_head(X, D, c->mw.head_w->f32, c->mw.head_b->f32, wv.chunks_dev, nb, L, beat, down, c->hp.sum_head ? 1 : 0, st);
   BT_LAUNCHED(c, "head", st);
+  return BT_OK;
+}
+
+struct HostChunk { ChunkSrc s; int len; };
+
+// upload the chunk table and run the forward pass in waves of equal-length chunks
+int run_chunks(bt_ctx* c, const float* spect_dev, std::vector<HostChunk>& all, float* beat_dev, float* downbeat_dev,
+               cudaStream_t st) {
+  int r = BT_OK;
+  if (all.empty()) return BT_OK;
+  if ((r = ensure_ws(c, static_cast<int>(all.size()))) != BT_OK) return r;
+  std::stable_sort(all.begin(), all.end(), [](const HostChunk& a, const HostChunk& b) { return a.len > b.len; });
+  const size_t bytes = all.size() * sizeof(ChunkSrc);
+  StageSlot* sl = nullptr;
+  if ((r = acquire_stage(c, bytes, &sl)) != BT_OK) return r;
+  ChunkSrc* hs = static_cast<ChunkSrc*>(sl->host);
+  for (size_t i = 0; i < all.size(); ++i) hs[i] = all[i].s;
+  if ((r = upload_stage(c, sl, bytes, st)) != BT_OK) return r;
+  const ChunkSrc* ds = static_cast<const ChunkSrc*>(sl->dev);
+  size_t i = 0;
+  while (i < all.size()) {
+    size_t j = i;
+    while (j < all.size() && all[j].len == all[i].len && j - i < static_cast<size_t>(c->ws_wave)) ++j;
+    Wave wv{ds + i, static_cast<int>(j - i), all[i].len};
+    if ((r = run_wave(c, spect_dev, wv, beat_dev, downbeat_dev, st)) != BT_OK) return r;
+    i = j;
+  }
   return BT_OK;
 }
 
@@ -610,7 +667,15 @@ bool is_gemm_weight(const std::string& n) {
 // ================================================================================== C ABI
 extern "C" {
 
-int bt_version(void) { return 100; }
+int bt_version(void) { return 200; }
+
+const char* bt_act_dtype(void) {
+#if defined(BT_ACT_BF16)
+  return "bf16";
+#else
+  return "f16";
+#endif
+}
 
 const char* bt_last_error(const bt_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
 
@@ -623,8 +688,8 @@ int64_t bt_plan_chunks(int64_t T, int64_t* starts, int64_t* lens, int64_t cap) {
 int bt_create(bt_ctx** out, int device_ordinal, const bt_hparams* hp, int compute_dtype) {
   if (!out || !hp) return fail(nullptr, BT_ERR_ARG, "bt_create: null argument");
   *out = nullptr;
-  if (compute_dtype != BT_DTYPE_F32 && compute_dtype != BT_DTYPE_BF16)
-    return fail(nullptr, BT_ERR_ARG, "bt_create: compute_dtype must be BT_DTYPE_F32 or BT_DTYPE_BF16");
+  if (compute_dtype != BT_DTYPE_F32 && compute_dtype != BT_DTYPE_H16)
+    return fail(nullptr, BT_ERR_ARG, "bt_create: compute_dtype must be BT_DTYPE_F32 or BT_DTYPE_H16");
   if (hp->spect_dim != 128 || hp->head_dim != 32 || hp->stem_dim != 32 || hp->transformer_dim % 64 != 0 ||
       hp->transformer_dim < 64 || hp->transformer_dim > 1024 || hp->n_layers < 1 || hp->ff_mult < 1 ||
       hp->ff_mult > 4)
@@ -656,11 +721,7 @@ int bt_create(bt_ctx** out, int device_ordinal, const bt_hparams* hp, int comput
   const char* foe = getenv("BT_FUSE_OUTPROJ");
   c->fuse_outproj = !(foe && foe[0] == '0');
 
-  if (cudaEventCreateWithFlags(&c->stage_ev, cudaEventDisableTiming) != cudaSuccess) {
-    delete c;
-    return fail(nullptr, BT_ERR_CUDA, "cudaEventCreate failed");
-  }
-  if (compute_dtype == BT_DTYPE_BF16) {
+  if (compute_dtype == BT_DTYPE_H16) {
     char err[512];
     if (tc_init(err, sizeof(err)) != 0) {
       delete c;
@@ -736,13 +797,35 @@ int bt_finalize(bt_ctx* c) {
     const std::string p = "l" + std::to_string(l);
     if (!chk_attn(p + ".attn", D) || !chk_ff(p + ".ff", D, hp.ff_mult)) return BT_ERR_PARAM;
   }
-  if (c->dtype == BT_DTYPE_BF16) {
+  if (c->dtype == BT_DTYPE_H16) {
     for (auto& kv : c->params) {
       if (!is_gemm_weight(kv.first)) continue;
       BT_CUDA(c, cudaMalloc(&kv.second.b16, kv.second.n * 2));
-      launch_f32_to_bf16(kv.second.f32, kv.second.b16, kv.second.n, nullptr);
+      launch_f32_to_h16(kv.second.f32, kv.second.b16, kv.second.n, nullptr);
     }
     BT_CUDA(c, cudaDeviceSynchronize());
+  }
+  {
+    ModelW& w = c->mw;
+    w.rope_cos = find_param(c, "rope.cos"); w.rope_sin = find_param(c, "rope.sin");
+    w.bn1_scale = find_param(c, "stem.bn1_scale"); w.bn1_shift = find_param(c, "stem.bn1_shift");
+    w.stem_w = find_param(c, "stem.w"); w.stem_b = find_param(c, "stem.bias");
+    w.lin_w = find_param(c, "lin.w"); w.lin_b = find_param(c, "lin.b");
+    w.head_w = find_param(c, "head.w"); w.head_b = find_param(c, "head.b");
+    for (int i = 0; i < 3; ++i) {
+      const std::string p = "b" + std::to_string(i);
+      if (hp.partial_transformers) {
+        w.fa[i] = attn_w(c, p + ".attnF"); w.ff_f[i] = ff_w(c, p + ".ffF");
+        w.ta[i] = attn_w(c, p + ".attnT"); w.ff_t[i] = ff_w(c, p + ".ffT");
+      }
+      w.conv_w[i] = find_param(c, p + ".conv.w");
+      w.conv_b[i] = find_param(c, p + ".conv.bias");
+    }
+    w.la.clear(); w.lf.clear();
+    for (int l = 0; l < hp.n_layers; ++l) {
+      w.la.push_back(attn_w(c, "l" + std::to_string(l) + ".attn"));
+      w.lf.push_back(ff_w(c, "l" + std::to_string(l) + ".ff"));
+    }
   }
   c->finalized = true;
   return BT_OK;
@@ -760,9 +843,11 @@ void bt_destroy(bt_ctx* c) {
     if (kv.second.i32) cudaFree(kv.second.i32);
   }
   if (c->spect_ws) cudaFree(c->spect_ws);
-  if (c->stage_host) cudaFreeHost(c->stage_host);
-  if (c->stage_dev) cudaFree(c->stage_dev);
-  if (c->stage_ev) cudaEventDestroy(c->stage_ev);
+  for (auto& sl : c->stage) {
+    if (sl.host) cudaFreeHost(sl.host);
+    if (sl.dev) cudaFree(sl.dev);
+    if (sl.ev) cudaEventDestroy(sl.ev);
+  }
   for (auto ev : c->ev_pool) cudaEventDestroy(ev);
   delete c;
 }
@@ -853,13 +938,14 @@ int bt_logmel(bt_ctx* c, const float* audio_dev, const int64_t* sample_offsets_h
       return fail(c, BT_ERR_ARG, "bt_logmel: frame_offsets do not match 1 + len/441 for clip %d", i);
   }
   const size_t bytes = static_cast<size_t>(n_clips + 1) * 8 * 2;
-  int r = ensure_stage(c, bytes);
+  StageSlot* sl = nullptr;
+  int r = acquire_stage(c, bytes, &sl);
   if (r != BT_OK) return r;
-  int64_t* h = static_cast<int64_t*>(c->stage_host);
+  int64_t* h = static_cast<int64_t*>(sl->host);
   memcpy(h, sample_offsets_host, (n_clips + 1) * 8);
   memcpy(h + n_clips + 1, frame_offsets_host, (n_clips + 1) * 8);
-  if ((r = upload_stage(c, bytes, st)) != BT_OK) return r;
-  const int64_t* d = static_cast<const int64_t*>(c->stage_dev);
+  if ((r = upload_stage(c, sl, bytes, st)) != BT_OK) return r;
+  const int64_t* d = static_cast<const int64_t*>(sl->dev);
   const int64_t f0 = frame_offsets_host[0];
   const int64_t total = frame_offsets_host[n_clips] - f0;
   if (f0 != 0) return fail(c, BT_ERR_ARG, "bt_logmel: frame_offsets_host[0] must be 0");
@@ -891,13 +977,14 @@ int bt_resample(bt_ctx* c, const float* audio_in_dev, const int64_t* in_offsets_
     max_out = std::max(max_out, out_offsets_host[i + 1] - out_offsets_host[i]);
   }
   const size_t bytes = static_cast<size_t>(n_clips + 1) * 8 * 2;
-  int r = ensure_stage(c, bytes);
+  StageSlot* sl = nullptr;
+  int r = acquire_stage(c, bytes, &sl);
   if (r != BT_OK) return r;
-  int64_t* h = static_cast<int64_t*>(c->stage_host);
+  int64_t* h = static_cast<int64_t*>(sl->host);
   memcpy(h, in_offsets_host, (n_clips + 1) * 8);
   memcpy(h + n_clips + 1, out_offsets_host, (n_clips + 1) * 8);
-  if ((r = upload_stage(c, bytes, st)) != BT_OK) return r;
-  const int64_t* d = static_cast<const int64_t*>(c->stage_dev);
+  if ((r = upload_stage(c, sl, bytes, st)) != BT_OK) return r;
+  const int64_t* d = static_cast<const int64_t*>(sl->dev);
   if (launch_resample(audio_in_dev, d, audio_out_dev, d + n_clips + 1, n_clips, max_out, coef_dev, L, M, K, st) != 0)
     return fail(c, BT_ERR_ARG, "bt_resample: ratio %d/%d with %d taps needs too much shared memory", L, M, K);
   BT_LAUNCHED(c, "resample", st);
@@ -915,7 +1002,6 @@ int bt_spect2frames(bt_ctx* c, const float* spect_dev, const int64_t* frame_offs
   prof_mark(c, st);
   int r = BT_OK;
   // plan: all chunks of all clips, grouped by chunk length (1500 except for pieces <= 1488 frames)
-  struct HostChunk { ChunkSrc s; int len; };
   std::vector<HostChunk> all;
   std::vector<int64_t> starts, lens;
   for (int i = 0; i < n_clips; ++i) {
@@ -941,24 +1027,31 @@ int bt_spect2frames(bt_ctx* c, const float* spect_dev, const int64_t* frame_offs
       all.push_back(hc);
     }
   }
-  if (all.empty()) return BT_OK;
-  if ((r = ensure_ws(c, static_cast<int>(all.size()))) != BT_OK) return r;
-  std::stable_sort(all.begin(), all.end(), [](const HostChunk& a, const HostChunk& b) { return a.len > b.len; });
-  const size_t bytes = all.size() * sizeof(ChunkSrc);
-  if ((r = ensure_stage(c, bytes)) != BT_OK) return r;
-  ChunkSrc* hs = static_cast<ChunkSrc*>(c->stage_host);
-  for (size_t i = 0; i < all.size(); ++i) hs[i] = all[i].s;
-  if ((r = upload_stage(c, bytes, st)) != BT_OK) return r;
-  const ChunkSrc* ds = static_cast<const ChunkSrc*>(c->stage_dev);
-  size_t i = 0;
-  while (i < all.size()) {
-    size_t j = i;
-    while (j < all.size() && all[j].len == all[i].len && j - i < static_cast<size_t>(c->ws_wave)) ++j;
-    Wave wv{ds + i, static_cast<int>(j - i), all[i].len};
-    if ((r = run_wave(c, spect_dev, wv, beat_dev, downbeat_dev, st)) != BT_OK) return r;
-    i = j;
+  return run_chunks(c, spect_dev, all, beat_dev, downbeat_dev, st);
+}
+
+int bt_forward_chunks(bt_ctx* c, const float* chunks_dev, int32_t n_chunks, int32_t chunk_frames, float* beat_dev,
+                      float* downbeat_dev, void* stream) {
+  if (!c || !c->finalized) return fail(c, BT_ERR_STATE, "bt_forward_chunks: context not finalized");
+  if (n_chunks <= 0) return BT_OK;
+  if (!chunks_dev || !beat_dev || !downbeat_dev) return fail(c, BT_ERR_ARG, "bt_forward_chunks: null argument");
+  if (chunk_frames < 1 || chunk_frames > BT_CHUNK)
+    return fail(c, BT_ERR_ARG, "bt_forward_chunks: chunk_frames must be in [1, %d]", BT_CHUNK);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BT_CUDA(c, cudaSetDevice(c->device));
+  prof_mark(c, st);
+  std::vector<HostChunk> all(n_chunks);
+  for (int i = 0; i < n_chunks; ++i) {
+    HostChunk& hc = all[i];
+    hc.s.frame_base = static_cast<int64_t>(i) * chunk_frames;
+    hc.s.out_base = hc.s.frame_base;
+    hc.s.T = chunk_frames;
+    hc.s.start = 0;
+    hc.s.write_lo = 0;
+    hc.s.write_hi = chunk_frames;
+    hc.len = chunk_frames;
   }
-  return BT_OK;
+  return run_chunks(c, chunks_dev, all, beat_dev, downbeat_dev, st);
 }
 
 int bt_audio2frames(bt_ctx* c, const float* audio_dev, const int64_t* sample_offsets_host, int32_t n_clips,
@@ -991,11 +1084,12 @@ int bt_peakpick(bt_ctx* c, const float* beat_dev, const float* downbeat_dev, con
   BT_CUDA(c, cudaSetDevice(c->device));
   prof_mark(c, st);
   const size_t bytes = static_cast<size_t>(n_clips + 1) * 8;
-  int r = ensure_stage(c, bytes);
+  StageSlot* sl = nullptr;
+  int r = acquire_stage(c, bytes, &sl);
   if (r != BT_OK) return r;
-  memcpy(c->stage_host, frame_offsets_host, bytes);
-  if ((r = upload_stage(c, bytes, st)) != BT_OK) return r;
-  launch_peakpick(beat_dev, downbeat_dev, static_cast<const int64_t*>(c->stage_dev), n_clips, beat_times_dev,
+  memcpy(sl->host, frame_offsets_host, bytes);
+  if ((r = upload_stage(c, sl, bytes, st)) != BT_OK) return r;
+  launch_peakpick(beat_dev, downbeat_dev, static_cast<const int64_t*>(sl->dev), n_clips, beat_times_dev,
                   n_beats_dev, down_times_dev, n_down_dev, max_peaks, st);
   BT_LAUNCHED(c, "peakpick", st);
   return BT_OK;
@@ -1008,12 +1102,12 @@ int bt_debug_gemm(bt_ctx* c, const float* a_dev, const float* w_dev, float* d_de
   BT_CUDA(c, cudaSetDevice(c->device));
   GemmShape g = plain_shape(1, M, N, K, K);
   EpiParams e = epi_generic(nullptr, 0, nullptr, 0, d_dev, N, nullptr, 0);
-  if (c->dtype == BT_DTYPE_BF16) {
+  if (c->dtype == BT_DTYPE_H16) {
     void *ab = nullptr, *wb = nullptr;
     BT_CUDA(c, cudaMalloc(&ab, static_cast<size_t>(M) * K * 2));
     BT_CUDA(c, cudaMalloc(&wb, static_cast<size_t>(N) * K * 2));
-    launch_f32_to_bf16(a_dev, ab, static_cast<int64_t>(M) * K, st);
-    launch_f32_to_bf16(w_dev, wb, static_cast<int64_t>(N) * K, st);
+    launch_f32_to_h16(a_dev, ab, static_cast<int64_t>(M) * K, st);
+    launch_f32_to_h16(w_dev, wb, static_cast<int64_t>(N) * K, st);
     char err[512] = "";
     TcGemmPlan* p = tc_gemm_plan_create(ab, wb, g, 1, err, sizeof(err));
     int rc = BT_OK;
@@ -1038,7 +1132,7 @@ int bt_debug_attention(bt_ctx* c, const float* q_dev, const float* k_dev, const 
   BT_CUDA(c, cudaSetDevice(c->device));
   const int C = heads * 32;
   const int64_t M = static_cast<int64_t>(seqs) * L;
-  const bool tc = c->dtype == BT_DTYPE_BF16;
+  const bool tc = c->dtype == BT_DTYPE_H16;
   const size_t act = tc ? 2 : 4;
   void *qkv = nullptr, *o = nullptr;
   float* gates = nullptr;
@@ -1055,7 +1149,7 @@ int bt_debug_attention(bt_ctx* c, const float* q_dev, const float* k_dev, const 
     if (!p) rc = fail(c, BT_ERR_CUDA, "%s", err);
     else {
       launch_attn_time_tc(p, gates, o, st);
-      launch_bf16_to_f32(o, o_dev, M * C, st);
+      launch_h16_to_f32(o, o_dev, M * C, st);
     }
     cudaError_t se = cudaStreamSynchronize(st);
     if (rc == BT_OK && se != cudaSuccess) rc = fail(c, BT_ERR_CUDA, "tc attention: %s", cudaGetErrorString(se));

@@ -25,7 +25,7 @@ struct GemmShape {
   int lda;
 };
 
-// Epilogue description (shared by the fp32 CUDA-core GEMM and the bf16 tcgen05 GEMM).
+// Epilogue description (shared by the fp32 CUDA-core GEMM and the 16-bit tcgen05 GEMM).
 struct EpiParams {
   int kind;            // 0 generic, 1 qkv (RoPE + q scaling), 2 attention gates:
                        //   out_f32[m*heads + n] = sigmoid(acc + bias[n]) for n < heads (N padded to 32)
@@ -57,10 +57,10 @@ void launch_attn_time_simt(const float* qkv, const float* gates, float* out, int
 // ---- shared small kernels (templated on activation dtype inside) ---------------------------
 // frequency-direction attention: tokens m = (b*F + f)*L + t, sequences over f.
 void launch_attn_freq(const void* qkv, const float* gates, void* out, int B, int F, int L,
-                      int heads, float scale, int act_bf16, cudaStream_t st);
+                      int heads, float scale, int act_h16, cudaStream_t st);
 // RMSNorm without gamma (folded into the next weight); optionally also the attention gates
 // sigmoid(xn . wg[h] + bg[h]) for h < heads (used when heads <= 4; wg is [>=heads, C] fp32).
-void launch_norm(const float* x, void* xn, int64_t M, int C, int act_bf16, cudaStream_t st, float* gates = nullptr,
+void launch_norm(const float* x, void* xn, int64_t M, int C, int act_h16, cudaStream_t st, float* gates = nullptr,
                  const float* wg = nullptr, const float* bg = nullptr, int heads = 0);
 // per-chunk source description for the stem (chunk gather from per-clip spectrograms)
 struct ChunkSrc {
@@ -85,35 +85,35 @@ void launch_logmel(const float* audio, const int64_t* sample_off_dev, const int6
 void launch_peakpick(const float* beat, const float* down, const int64_t* frame_off_dev, int n_clips,
                      double* beat_t, int32_t* n_beat, double* down_t, int32_t* n_down,
                      int max_peaks, cudaStream_t st);
-void launch_f32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t st);
-void launch_bf16_to_f32(const void* in, float* out, int64_t n, cudaStream_t st);
+void launch_f32_to_h16(const float* in, void* out, int64_t n, cudaStream_t st);
+void launch_h16_to_f32(const void* in, float* out, int64_t n, cudaStream_t st);
 // [seqs, L, heads*32] fp32 q,k,v -> packed qkv buffer [seqs*L, 3C] of the activation dtype
 // (test hook for bt_debug_attention)
 void launch_pack_qkv_test(const float* q, const float* k, const float* v, void* qkv, int seqs, int L,
-                          int heads, float qscale, int act_bf16, cudaStream_t st);
+                          int heads, float qscale, int act_h16, cudaStream_t st);
 
-// ---- bf16 tcgen05 path ------------------------------------------------------------------------
+// ---- 16-bit (fp16 or bf16 operands) tcgen05 path ------------------------------------------------------------------------
 struct TcGemmPlan;  // cached tensor maps + launch geometry
-TcGemmPlan* tc_gemm_plan_create(const void* A_bf16, const void* W_bf16, const GemmShape& g,
+TcGemmPlan* tc_gemm_plan_create(const void* A_h16, const void* W_h16, const GemmShape& g,
                                 int planes_in, char* err, int errlen);
 void tc_gemm_plan_destroy(TcGemmPlan*);
 int launch_gemm_tc(const TcGemmPlan* plan, const EpiParams& e, cudaStream_t st);
 
 struct TcAttnPlan;
-TcAttnPlan* tc_attn_plan_create(const void* qkv_bf16, int seqs, int L, int heads, char* err, int errlen);
+TcAttnPlan* tc_attn_plan_create(const void* qkv_h16, int seqs, int L, int heads, char* err, int errlen);
 void tc_attn_plan_destroy(TcAttnPlan*);
-int launch_attn_time_tc(const TcAttnPlan* plan, const float* gates, void* out_bf16, cudaStream_t st);
+int launch_attn_time_tc(const TcAttnPlan* plan, const float* gates, void* out_h16, cudaStream_t st);
 
-// fused RMSNorm + FFN + residual for C in {32, 64} (frontend), x updated in place (+ optional bf16 copy)
+// fused RMSNorm + FFN + residual for C in {32, 64} (frontend), x updated in place (+ optional 16-bit copy)
 struct TcFfPlan;
-TcFfPlan* tc_ff_plan_create(const void* w1_bf16, const void* w2_bf16, int C, int64_t M, const void* o_bf16,
-                            const void* wout_bf16, char* err, int errlen);
+TcFfPlan* tc_ff_plan_create(const void* w1_h16, const void* w2_h16, int C, int64_t M, const void* o_h16,
+                            const void* wout_h16, char* err, int errlen);
 void tc_ff_plan_destroy(TcFfPlan*);
 int launch_fused_ff(const TcFfPlan* plan, float* X, const float* b1, const float* b2, void* xb_out, cudaStream_t st);
 
 // fused RMSNorm + gates + QKV projection + RoPE for C in {32, 64} (frontend attentions)
 struct TcQkvPlan;
-TcQkvPlan* tc_qkv_plan_create(const void* wqkv_bf16, int C, int64_t M, char* err, int errlen);
+TcQkvPlan* tc_qkv_plan_create(const void* wqkv_h16, int C, int64_t M, char* err, int errlen);
 void tc_qkv_plan_destroy(TcQkvPlan*);
 int launch_fused_qkv(const TcQkvPlan* plan, const float* X, const float* wg, const float* bg, const float* rope_cos,
                      const float* rope_sin, void* qkv, float* gates, int L, int F, int posmode, float qscale,

@@ -2,13 +2,26 @@
 // (inline PTX), small math helpers.  No torch, no CUTLASS.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 
 namespace bt {
 
-typedef __nv_bfloat16 bf16;
+// 16-bit operand type of the tensor-core path (BT_DTYPE_H16).  Default: IEEE fp16 -- the dtype the reference's
+// float16=True autocasts to on CUDA (beat_this/inference.py:245-246); every operand on this path is RMS-normalised,
+// a folded weight, a softmax probability <= 2^8 or a GELU output, all far inside fp16 range, and its 11-bit
+// significand cuts the logit error of the bf16 build ~8x at the same tcgen05 rate.  -DBT_ACT_BF16 builds bf16.
+#if defined(BT_ACT_BF16)
+typedef __nv_bfloat16 h16;
+#define BT_H16_IS_F16 0
+#define BT_H16_MMA_SYNC "bf16.bf16"
+#else
+typedef __half h16;
+#define BT_H16_IS_F16 1
+#define BT_H16_MMA_SYNC "f16.f16"
+#endif
 
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ constexpr int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -24,16 +37,24 @@ template <typename T>
 __device__ __forceinline__ T to_out(float v);
 template <>
 __device__ __forceinline__ float to_out<float>(float v) { return v; }
+#if BT_H16_IS_F16
 template <>
-__device__ __forceinline__ bf16 to_out<bf16>(float v) { return __float2bfloat16_rn(v); }
-
-__device__ __forceinline__ float to_f32(float v) { return v; }
-__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+__device__ __forceinline__ h16 to_out<h16>(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ float to_f32(h16 v) { return __half2float(v); }
+__device__ __forceinline__ uint32_t pack_h16x2(float lo, float hi) {
+  __half2 p = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+#else
+template <>
+__device__ __forceinline__ h16 to_out<h16>(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ float to_f32(h16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ uint32_t pack_h16x2(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&p);
 }
+#endif
+__device__ __forceinline__ float to_f32(float v) { return v; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -178,85 +199,6 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// ----------------------------------------------------------------------------- PTX: clusters
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// TMA load delivered to the same smem offset (and mbarrier) of every CTA in `mask`
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-// tcgen05.commit arriving on the barrier at the same offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(mask)
-      : "memory");
-}
-
-// shared::cluster address of `local_addr` (a shared::cta offset) inside CTA `rank` of this cluster
-__device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// ---- cta_group::2 (a pair of SMs executes one MMA: M = 256, each SM holds its 128 rows of A/D and half of B)
-template <int COLS>
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_result_addr) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result_addr), "n"(COLS) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-template <int COLS>
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                              uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar_addr, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_addr),
-               "h"(mask)
-               : "memory");
-}
-// TMA loads of a CTA pair: data lands in THIS CTA's smem, completion bytes are signalled on the
-// mbarrier at `bar_cluster_addr` (the leader CTA's barrier)
-__device__ __forceinline__ void tma_load_3d_2sm(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster_addr, int32_t c0,
-                                                int32_t c1, int32_t c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_dst),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster_addr, int32_t c0,
-                                                int32_t c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
-
 // ----------------------------------------------------------------------------- PTX: tcgen05
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {
@@ -277,8 +219,8 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]; bf16 x bf16 -> fp32, issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+// D[tmem] (+)= A[smem desc] * B[smem desc]; h16 x h16 -> fp32, issued by ONE thread.
+__device__ __forceinline__ void umma_h16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -325,9 +267,12 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   return static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) |
          (1ull << 46) | (layout << 61);
 }
-// tcgen05 instruction descriptor, kind::f16: bf16 A/B (K-major both), fp32 accumulate.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+// tcgen05 instruction descriptor, kind::f16: h16 A/B (K-major both), fp32 accumulate.
+//   bits [4,6) D format (1 = f32) | [7,10) A format, [10,13) B format (0 = f16, 1 = bf16) | [15] A MN-major |
+//   [16] B MN-major | [17,23) N >> 3 | [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc_h16(int M, int N) {
+  constexpr uint32_t fmt = BT_H16_IS_F16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 

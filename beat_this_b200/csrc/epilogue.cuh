@@ -1,4 +1,4 @@
-// GEMM epilogues shared by the fp32 CUDA-core GEMM and the bf16 tcgen05 GEMM.
+// GEMM epilogues shared by the fp32 CUDA-core GEMM and the h16 tcgen05 GEMM.
 // A thread hands over CNT consecutive accumulator columns [n0, n0+CNT) of output row m.
 #pragma once
 #include "bt_kernels.h"
@@ -16,10 +16,10 @@ __device__ __forceinline__ void store_act<float, 4>(float* p, const float (&v)[4
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
 template <>
-__device__ __forceinline__ void store_act<bf16, 4>(bf16* p, const float (&v)[4]) {
+__device__ __forceinline__ void store_act<h16, 4>(h16* p, const float (&v)[4]) {
   uint2 u;
-  u.x = pack_bf16x2(v[0], v[1]);
-  u.y = pack_bf16x2(v[2], v[3]);
+  u.x = pack_h16x2(v[0], v[1]);
+  u.y = pack_h16x2(v[2], v[3]);
   *reinterpret_cast<uint2*>(p) = u;
 }
 template <>
@@ -29,14 +29,14 @@ __device__ __forceinline__ void store_act<float, 32>(float* p, const float (&v)[
     reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 template <>
-__device__ __forceinline__ void store_act<bf16, 32>(bf16* p, const float (&v)[32]) {
+__device__ __forceinline__ void store_act<h16, 32>(h16* p, const float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     uint4 u;
-    u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+    u.x = pack_h16x2(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_h16x2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_h16x2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_h16x2(v[8 * i + 6], v[8 * i + 7]);
     reinterpret_cast<uint4*>(p)[i] = u;
   }
 }
@@ -59,8 +59,8 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x + 0.5f * fabsf(x) * erf_abs;         // 0.5x(1 + sign(x) erf_abs)
 }
 // tanh-form GELU on one MUFU op: 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))).  Differs from
-// the exact erf form by <= 5e-4 absolute (and tanh.approx adds ~5e-4): a quarter of a bf16 ulp
-// of the values it produces.  Used only by the bf16 tensor-core path, whose FFN epilogues were
+// the exact erf form by <= 5e-4 absolute (and tanh.approx adds ~5e-4): a quarter of a h16 ulp
+// of the values it produces.  Used only by the h16 tensor-core path, whose FFN epilogues were
 // issue/MUFU-bound on the 16-instruction + 2-MUFU erf evaluation above.
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
   const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);

@@ -1,0 +1,551 @@
+// Persistent fused kernels for the narrow frontend sub-blocks (C = 32 / 64): [out-projection +] RMSNorm + FFN +
+// residual (fused_ff_kernel) and RMSNorm + gates + QKV + RoPE (fused_qkv_kernel); reference
+// roformer.py:38-61,114-128 as called by PartialFTTransformer, beat_tracker.py:290-301.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "tc_common.cuh"
+
+namespace bt {
+
+// ==================================================================== fused frontend FFN
+// x += W2 gelu(W1 rmsnorm(x) + b1) + b2 for the narrow frontend FFNs (C = 32 / 64, hidden 4C) in ONE
+// kernel (reference roformer.py:38-61): the hidden activations never leave the SM.  Unfused, this
+// block streams 32 bytes per element through HBM (norm 6 + ff1 10 + ff2 16); fused it is 8.
+// CTA = 128 tokens; warps 0-3: one token row per thread (RMSNorm, bias+GELU, residual), warp 4
+// (converged, one elected lane issues): TMA (weights) + tcgen05.mma.  Hidden units are processed in chunks of 128:
+//   H_h = Xn W1_h^T (N=128, K=C) -> TMEM cols [0,128) -> bias+GELU -> h16 tile in smem ->
+//   OUT (+)= H_h W2_h^T (N=C, K=128) -> TMEM cols [128,128+C).
+constexpr int FF_THREADS = 160;
+template <int C>
+struct FfCfg {
+  static constexpr int NH = 4 * C / 128;            // hidden chunks
+  static constexpr int A_BYTES = 128 * C * 2;       // normalised tokens, K-major
+  static constexpr int W1_BYTES = 4 * C * C * 2;    // all chunks resident
+  static constexpr int W2C_BYTES = C * 128 * 2;     // one K-chunk of W2
+  static constexpr int H_BYTES = 128 * 128 * 2;
+  static constexpr int WO_BYTES = C * C * 2;       // attention out-projection weight (fused_ff_kernel<C, true>)
+  static constexpr int SMEM = A_BYTES + W1_BYTES + W2C_BYTES + H_BYTES + WO_BYTES + 5 * C * 4 + 1024 + 128;
+  static constexpr int SWZ_A = C * 2 < 128 ? C * 2 : 128;  // 64-byte rows for C=32, 128 for C=64
+  // TMEM: H accumulator [0,128) and OUT accumulator.  With a single hidden chunk (C = 32) OUT reuses the H
+  // columns (every thread has read H before MMA2 is issued) -> 128 columns, 3 CTAs/SM instead of 2.
+  static constexpr int OUT_COL = NH == 1 ? 0 : 128;
+  static constexpr int TCOLS = NH == 1 ? 128 : 256;
+  static constexpr int CTAS = NH == 1 ? 3 : 2;
+  // accumulator of the optional out-projection prologue (O Wo^T): columns that are dead at that point
+  static constexpr int D0_COL = NH == 1 ? 64 : 0;
+};
+
+// OP = true: the attention out-projection is fused in front (reference roformer.py:134-140 followed by
+// roformer.py:38-61): x' = x + O Wo^T is computed per tile by one more MMA (the gated attention output O is
+// TMA-loaded into the A-tile buffer, which the normalised x' overwrites afterwards), then the FFN runs on x'.
+// Saves the separate out-projection GEMM: one fp32 read + write of the residual stream per element.
+template <int C, bool OP>
+__global__ void __launch_bounds__(FF_THREADS, FfCfg<C>::CTAS)
+fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWo,
+                float* __restrict__ X, const float* __restrict__ b1, const float* __restrict__ b2,
+                h16* __restrict__ xb_out, int64_t M) {
+  // PERSISTENT: each CTA walks over token tiles (stride gridDim.x); W1 (and W2 when it is a single chunk) are
+  // fetched once per CTA, barriers / TMEM / bias staging are set up once.  (The one-tile-per-CTA form spent
+  // more time on set-up and on re-fetching 16-64 KB of weights per CTA than on its tile.)
+  using Cfg = FfCfg<C>;
+  constexpr int NH = Cfg::NH;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = sbase;
+  const uint32_t sW1 = sA + Cfg::A_BYTES;
+  const uint32_t sW2 = sW1 + Cfg::W1_BYTES;
+  const uint32_t sH = sW2 + Cfg::W2C_BYTES;
+  const uint32_t sWo = sH + Cfg::H_BYTES;
+  const uint32_t sB = sWo + Cfg::WO_BYTES;        // b1[4C] | b2[C] fp32
+  const uint32_t bar_w1 = sB + 5 * C * 4;
+  const uint32_t bar_w2 = bar_w1 + 8;
+  const uint32_t bar_a = bar_w2 + 8;
+  const uint32_t bar_h = bar_a + 8;
+  const uint32_t bar_h2 = bar_h + 8;
+  const uint32_t bar_o = bar_h2 + 8;
+  const uint32_t bar_of = bar_o + 8;              // O tile landed in the A buffer (OP)
+  const uint32_t bar_d0 = bar_of + 8;             // O Wo^T accumulated (OP)
+  const uint32_t tmem_slot = bar_d0 + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = static_cast<int>((M + 127) / 128);
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    auto init = [](uint32_t bar, uint32_t count) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    };
+    init(bar_w1, 1); init(bar_w2, 1); init(bar_a, 128); init(bar_h, 1); init(bar_h2, 128); init(bar_o, 1);
+    init(bar_of, 1); init(bar_d0, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::TCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 5 * C; i += FF_THREADS)
+    st_shared_f32(sB + 4 * i, i < 4 * C ? __ldg(b1 + i) : __ldg(b2 + i - 4 * C));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 4) {
+    const uint32_t on = elect_one() ? 1u : 0u;  // converged issuer warp, predicated single-lane TMA / MMA (see umma_h16_p)
+    constexpr uint32_t idesc1 = make_idesc_h16(128, 128);
+    constexpr uint32_t idesc2 = make_idesc_h16(128, C);
+    // weights: W1 [4C, C] all chunks (boxes of 128 rows), W2 [C, 4C] one K-chunk at a time (two 64-wide boxes)
+    mbar_expect_tx_p(on, bar_w1, Cfg::W1_BYTES + (OP ? Cfg::WO_BYTES : 0));
+    for (int h = 0; h < NH; ++h) tma_load_2d_p(on, sW1 + h * (128 * C * 2), &tmW1, bar_w1, 0, h * 128);
+    if constexpr (OP) tma_load_2d_p(on, sWo, &tmWo, bar_w1, 0, 0);
+    auto load_o = [&](int tile) {  // gated attention output rows of a tile -> the A buffer (same box / swizzle)
+      mbar_expect_tx_p(on, bar_of, Cfg::A_BYTES);
+      tma_load_2d_p(on, sA, &tmO, bar_of, 0, tile * 128);
+    };
+    if constexpr (OP) {
+      if (static_cast<int>(blockIdx.x) < ntiles) load_o(blockIdx.x);
+    }
+    auto load_w2 = [&](int h) {
+      mbar_expect_tx_p(on, bar_w2, Cfg::W2C_BYTES);
+      for (int a = 0; a < 2; ++a) tma_load_2d_p(on, sW2 + a * (C * 128), &tmW2, bar_w2, h * 128 + a * 64, 0);
+    };
+    load_w2(0);
+    auto issue_mma1 = [&](int h) {
+#pragma unroll
+      for (int k = 0; k < C / 16; ++k)
+        umma_h16_p(on, tmem_base, make_kmajor_desc<Cfg::SWZ_A>(sA + k * 32),
+                    make_kmajor_desc<Cfg::SWZ_A>(sW1 + h * (128 * C * 2) + k * 32), idesc1, k != 0 ? 1u : 0u);
+      umma_commit_p(on, bar_h);
+    };
+    mbar_wait_a(bar_w1, 0);
+    int idx = 0;      // chunk counter over all tiles of this CTA: parity of bar_h / bar_h2 / bar_o
+    int w2_loads = 0; // completed-or-in-flight W2 chunk loads minus one: parity of bar_w2
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      if constexpr (OP) {  // D0 = O Wo^T into columns that nobody reads at this point
+        constexpr uint32_t idesc0 = make_idesc_h16(128, C);
+        mbar_wait_a(bar_of, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < C / 16; ++k)
+          umma_h16_p(on, tmem_base + Cfg::D0_COL, make_kmajor_desc<Cfg::SWZ_A>(sA + k * 32),
+                      make_kmajor_desc<Cfg::SWZ_A>(sWo + k * 32), idesc0, k != 0 ? 1u : 0u);
+        umma_commit_p(on, bar_d0);
+      }
+      mbar_wait_a(bar_a, it & 1);  // normalised tile in smem (and every thread is done with the previous tile's TMEM)
+      tc_fence_after();
+      issue_mma1(0);
+      for (int h = 0; h < NH; ++h, ++idx) {
+        mbar_wait_a(bar_h2, idx & 1);  // h16 H_h tile written, accumulator H consumed
+        tc_fence_after();
+        if (h + 1 < NH) issue_mma1(h + 1);
+        if constexpr (OP) {  // the last MMA1 of this tile has completed (its H was read): the A buffer is free
+          if (h == NH - 1 && tile + static_cast<int>(gridDim.x) < ntiles) load_o(tile + gridDim.x);
+        }
+        if (NH > 1 || idx == 0) mbar_wait_a(bar_w2, w2_loads & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_h16_p(on, tmem_base + Cfg::OUT_COL, make_kmajor_desc<128>(sH + (k >> 2) * 16384 + (k & 3) * 32),
+                      make_kmajor_desc<128>(sW2 + (k >> 2) * (C * 128) + (k & 3) * 32), idesc2, (h | k) != 0 ? 1u : 0u);
+        umma_commit_p(on, bar_o);
+        if (NH > 1 && (h + 1 < NH || tile + static_cast<int>(gridDim.x) < ntiles)) {
+          mbar_wait_a(bar_o, idx & 1);  // MMA2 finished reading this W2 chunk (and the H tile)
+          load_w2((h + 1) % NH);
+          ++w2_loads;
+        }
+      }
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t hrow = sH + row * 128;
+    const uint32_t hsw = static_cast<uint32_t>(row & 7) << 4;
+    int idx = 0, it = 0;
+    constexpr bool PREFETCH = C == 32;  // next tile's row requested while this tile is in the MMAs (register budget: C = 32 only)
+    float4 xn[PREFETCH ? C / 4 : 1];
+    auto load_x = [&](int tile, float4* dst) {
+      const int64_t mm = static_cast<int64_t>(tile) * 128 + row;
+      const float4* xr = reinterpret_cast<const float4*>(X + (mm < M ? mm : 0) * C);
+#pragma unroll
+      for (int i = 0; i < C / 4; ++i) dst[i] = mm < M ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if constexpr (PREFETCH) {
+      if (static_cast<int>(blockIdx.x) < ntiles) load_x(blockIdx.x, xn);
+    }
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int64_t m = static_cast<int64_t>(tile) * 128 + row;
+      const bool valid = m < M;
+      // ---- RMSNorm of this token (x stays in registers for the residual) ----
+      float x[C];
+      {
+        float4 xq[C / 4];
+        if constexpr (PREFETCH) {
+#pragma unroll
+          for (int i = 0; i < C / 4; ++i) xq[i] = xn[i];
+        } else {
+          load_x(tile, xq);
+        }
+#pragma unroll
+        for (int i = 0; i < C / 4; ++i) {
+          const float4 q = xq[i];
+          x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
+        }
+        if constexpr (OP) {  // x' = x + O Wo^T (attention residual)
+          mbar_wait_a(bar_d0, it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c4 = 0; c4 < C / 32; ++c4) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_base + Cfg::D0_COL + c4 * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[c4 * 32 + i] += __uint_as_float(r[i]);
+          }
+        }
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < C; ++i) ss = fmaf(x[i], x[i], ss);
+        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+        constexpr int RB = C * 2;  // bytes per A row
+        const uint32_t arow = sA + row * RB;
+        const uint32_t sw = C == 32 ? (static_cast<uint32_t>((row >> 1) & 3) << 4) : (static_cast<uint32_t>(row & 7) << 4);
+        // the A tile is free: the last MMA1 of the previous tile completed before its bar_h was observed
+#pragma unroll
+        for (int c = 0; c < C / 8; ++c)
+          st_shared_v4(arow + ((c << 4) ^ sw), pack_h16x2(x[8 * c] * inv, x[8 * c + 1] * inv),
+                       pack_h16x2(x[8 * c + 2] * inv, x[8 * c + 3] * inv), pack_h16x2(x[8 * c + 4] * inv, x[8 * c + 5] * inv),
+                       pack_h16x2(x[8 * c + 6] * inv, x[8 * c + 7] * inv));
+        fence_proxy_async_smem();
+        tc_fence_before();  // this thread's TMEM reads of the previous tile are ordered before the next MMAs
+        mbar_arrive_a(bar_a);
+        if constexpr (PREFETCH) {
+          if (tile + static_cast<int>(gridDim.x) < ntiles) load_x(tile + gridDim.x, xn);
+        }
+      }
+      for (int h = 0; h < NH; ++h, ++idx) {
+        mbar_wait_a(bar_h, idx & 1);
+        tc_fence_after();
+        if (h >= 1) {  // the single H tile is free once MMA2_{h-1} has completed (h == 0: waited at the end of the last tile)
+          mbar_wait_a(bar_o, (idx - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_base + c4 * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {  // 4 chunks of 8 hidden units
+            const float4 ba = ld_shared_v4_f32(sB + 4 * (h * 128 + c4 * 32 + 8 * c));
+            const float4 bb = ld_shared_v4_f32(sB + 4 * (h * 128 + c4 * 32 + 8 * c + 4));
+            const float bq[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+            float g[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = gelu_tanh_fast(__uint_as_float(r[8 * c + i]) + bq[i]);
+            const int cc = c4 * 4 + c;  // 16-byte chunk index inside the 128-wide row: atom = cc >> 3
+            st_shared_v4(hrow + (cc >> 3) * 16384 + (((cc & 7) << 4) ^ hsw), pack_h16x2(g[0], g[1]), pack_h16x2(g[2], g[3]),
+                         pack_h16x2(g[4], g[5]), pack_h16x2(g[6], g[7]));
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive_a(bar_h2);
+      }
+      mbar_wait_a(bar_o, (idx - 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c4 = 0; c4 < C / 32; ++c4) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_base + Cfg::OUT_COL + c4 * 32, r);
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bq = ld_shared_v4_f32(sB + 4 * (4 * C + c4 * 32 + 4 * i));
+            v[4 * i] = __uint_as_float(r[4 * i]) + bq.x + x[c4 * 32 + 4 * i];
+            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bq.y + x[c4 * 32 + 4 * i + 1];
+            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bq.z + x[c4 * 32 + 4 * i + 2];
+            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bq.w + x[c4 * 32 + 4 * i + 3];
+          }
+          store_act<float, 32>(X + m * C + c4 * 32, v);
+          if (xb_out) store_act<h16, 32>(xb_out + m * C + c4 * 32, v);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<Cfg::TCOLS>(tmem_base);
+}
+
+struct TcFfPlan {
+  CUtensorMap tmW1, tmW2, tmO, tmWo;
+  int C;
+  int64_t M;
+  bool outproj;
+};
+
+// o_h16 / wout_h16 != nullptr: plan for the variant with the attention out-projection fused in front
+// (o_h16: gated attention output [M, C], wout_h16: [C, C]).
+TcFfPlan* tc_ff_plan_create(const void* w1_h16, const void* w2_h16, int C, int64_t M, const void* o_h16,
+                            const void* wout_h16, char* err, int errlen) {
+  if (C != 32 && C != 64) { snprintf(err, errlen, "fused ff: C must be 32 or 64"); return nullptr; }
+  TcFfPlan* p = new TcFfPlan();
+  p->C = C; p->M = M; p->outproj = o_h16 != nullptr && wout_h16 != nullptr;
+  const uint32_t swz_a = C * 2 < 128 ? C * 2 : 128;
+  {  // W1 [4C, C] row-major: box = {C, 128 rows}
+    const uint64_t dims[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(4 * C)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(C) * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(C), 128};
+    if (!make_tmap(&p->tmW1, w1_h16, 2, dims, strides, box, swz_a, err, errlen)) { delete p; return nullptr; }
+  }
+  {  // W2 [C, 4C] row-major: box = {64 K, C rows}
+    const uint64_t dims[2] = {static_cast<uint64_t>(4 * C), static_cast<uint64_t>(C)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(4 * C) * 2};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(C)};
+    if (!make_tmap(&p->tmW2, w2_h16, 2, dims, strides, box, 128, err, errlen)) { delete p; return nullptr; }
+  }
+  if (p->outproj) {
+    {  // O [M, C] row-major: box = {C, 128 tokens}, same swizzle as the hand-written A tile
+      const uint64_t dims[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(M)};
+      const uint64_t strides[1] = {static_cast<uint64_t>(C) * 2};
+      const uint32_t box[2] = {static_cast<uint32_t>(C), 128};
+      if (!make_tmap(&p->tmO, o_h16, 2, dims, strides, box, swz_a, err, errlen)) { delete p; return nullptr; }
+    }
+    {  // Wo [C, C] row-major
+      const uint64_t dims[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(C)};
+      const uint64_t strides[1] = {static_cast<uint64_t>(C) * 2};
+      const uint32_t box[2] = {static_cast<uint32_t>(C), static_cast<uint32_t>(C)};
+      if (!make_tmap(&p->tmWo, wout_h16, 2, dims, strides, box, swz_a, err, errlen)) { delete p; return nullptr; }
+    }
+  } else {
+    p->tmO = p->tmW1;  // never dereferenced
+    p->tmWo = p->tmW1;
+  }
+  return p;
+}
+void tc_ff_plan_destroy(TcFfPlan* p) { delete p; }
+
+int launch_fused_ff(const TcFfPlan* p, float* X, const float* b1, const float* b2, void* xb_out, cudaStream_t st) {
+  const unsigned ntiles = static_cast<unsigned>((p->M + 127) / 128);
+  const unsigned slots = static_cast<unsigned>(g_num_sms) * (p->C == 32 ? FfCfg<32>::CTAS : FfCfg<64>::CTAS);
+  const unsigned grid = ntiles < slots ? ntiles : slots;  // persistent CTAs
+  h16* xb = reinterpret_cast<h16*>(xb_out);
+#define BT_FF_L(CC, OPP)                                                                                          \
+  fused_ff_kernel<CC, OPP><<<grid, FF_THREADS, FfCfg<CC>::SMEM, st>>>(p->tmW1, p->tmW2, p->tmO, p->tmWo, X, b1, b2, xb, \
+                                                                      p->M)
+  if (p->C == 32) { if (p->outproj) BT_FF_L(32, true); else BT_FF_L(32, false); }
+  else { if (p->outproj) BT_FF_L(64, true); else BT_FF_L(64, false); }
+#undef BT_FF_L
+  return 0;
+}
+
+// ================================================================ fused frontend QKV projection
+// RMSNorm -> gates -> to_qkv GEMM -> RoPE (+ q scaling) for the narrow frontend attentions (C = 32 /
+// 64) in one kernel (reference roformer.py:114-123,127-128): replaces norm_kernel + the QKV GEMM
+// (16 bytes/element through HBM) by 4 in + 6 out.  CTA = 128 tokens; warps 0-3 one token row per
+// thread, warp 4 (converged) TMA (weights) + tcgen05.mma.  N = 3C fits one MMA and 128/256 TMEM columns.
+template <int C>
+struct QkvCfg {
+  static constexpr int A_BYTES = 128 * C * 2;
+  static constexpr int W_BYTES = 3 * C * C * 2;
+  static constexpr int SMEM = A_BYTES + W_BYTES + 1024 + 128;
+  static constexpr int TCOLS = 3 * C <= 128 ? 128 : 256;
+  static constexpr int SWZ = C * 2 < 128 ? C * 2 : 128;
+};
+
+template <int C>
+__global__ void __launch_bounds__(FF_THREADS, (C == 32 ? 3 : 2))
+fused_qkv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ X, const float* __restrict__ wg,
+                 const float* __restrict__ bg, const float* __restrict__ rope_cos, const float* __restrict__ rope_sin,
+                 h16* __restrict__ qkv, float* __restrict__ gates, int64_t M, int L, int F, int posmode, float qscale) {
+  using Cfg = QkvCfg<C>;
+  constexpr int heads = C / 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = sbase;
+  const uint32_t sW = sA + Cfg::A_BYTES;
+  const uint32_t bar_w = sW + Cfg::W_BYTES;
+  const uint32_t bar_a = bar_w + 8;
+  const uint32_t bar_d = bar_a + 8;
+  const uint32_t tmem_slot = bar_d + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = static_cast<int>((M + 127) / 128);  // PERSISTENT: tiles blockIdx.x, +gridDim.x, ... (W fetched once)
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmW);
+    auto init = [](uint32_t bar, uint32_t count) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    };
+    init(bar_w, 1); init(bar_a, 128); init(bar_d, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::TCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 4) {
+    const uint32_t on = elect_one() ? 1u : 0u;  // converged issuer warp (see umma_h16_p)
+    constexpr uint32_t idesc = make_idesc_h16(128, 3 * C);
+    mbar_expect_tx_p(on, bar_w, Cfg::W_BYTES);
+    tma_load_2d_p(on, sW, &tmW, bar_w, 0, 0);
+    mbar_wait_a(bar_w, 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      mbar_wait_a(bar_a, it & 1);  // normalised tile in smem, previous accumulator read by every thread
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < C / 16; ++k)
+        umma_h16_p(on, tmem_base, make_kmajor_desc<Cfg::SWZ>(sA + k * 32), make_kmajor_desc<Cfg::SWZ>(sW + k * 32), idesc,
+                    k != 0 ? 1u : 0u);
+      umma_commit_p(on, bar_d);
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    int it = 0;
+    float4 xn[C / 4];  // next tile's row, requested while this tile is in the MMA / epilogue
+    auto load_x = [&](int tile) {
+      const int64_t mm = static_cast<int64_t>(tile) * 128 + row;
+      const float4* xr = reinterpret_cast<const float4*>(X + (mm < M ? mm : 0) * C);
+#pragma unroll
+      for (int i = 0; i < C / 4; ++i) xn[i] = mm < M ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if (static_cast<int>(blockIdx.x) < ntiles) load_x(blockIdx.x);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int64_t m = static_cast<int64_t>(tile) * 128 + row;
+    const bool valid = m < M;
+    {
+      float x[C];
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < C / 4; ++i) {
+        const float4 q = xn[i];
+        x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
+        ss = fmaf(q.x, q.x, ss); ss = fmaf(q.y, q.y, ss); ss = fmaf(q.z, q.z, ss); ss = fmaf(q.w, q.w, ss);
+      }
+      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+      for (int i = 0; i < C; ++i) x[i] *= inv;
+      // gates = sigmoid(to_gates(x_normed)) (gamma*sqrt(C) folded into wg)
+#pragma unroll
+      for (int h = 0; h < heads; ++h) {
+        const float4* w4 = reinterpret_cast<const float4*>(wg + h * C);
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < C / 4; ++i) {
+          const float4 w = __ldg(w4 + i);
+          a = fmaf(x[4 * i], w.x, a); a = fmaf(x[4 * i + 1], w.y, a); a = fmaf(x[4 * i + 2], w.z, a); a = fmaf(x[4 * i + 3], w.w, a);
+        }
+        if (valid) gates[m * heads + h] = sigmoidf_(a + __ldg(bg + h));
+      }
+      constexpr int RB = C * 2;
+      const uint32_t arow = sA + row * RB;
+      const uint32_t sw = C == 32 ? (static_cast<uint32_t>((row >> 1) & 3) << 4) : (static_cast<uint32_t>(row & 7) << 4);
+#pragma unroll
+      for (int c = 0; c < C / 8; ++c)
+        st_shared_v4(arow + ((c << 4) ^ sw), pack_h16x2(x[8 * c], x[8 * c + 1]), pack_h16x2(x[8 * c + 2], x[8 * c + 3]),
+                     pack_h16x2(x[8 * c + 4], x[8 * c + 5]), pack_h16x2(x[8 * c + 6], x[8 * c + 7]));
+      fence_proxy_async_smem();
+      tc_fence_before();  // TMEM reads of the previous tile are ordered before the next MMA
+      mbar_arrive_a(bar_a);
+      if (tile + static_cast<int>(gridDim.x) < ntiles) load_x(tile + gridDim.x);
+    }
+    // RoPE row of this token (interleaved pairs, rotary_embedding_torch semantics)
+    float cs[16], sn[16];
+    {
+      const int pos = valid ? (posmode == 0 ? static_cast<int>(m % L) : static_cast<int>((m / L) % F)) : 0;
+      const float4* c4 = reinterpret_cast<const float4*>(rope_cos + pos * 16);
+      const float4* s4 = reinterpret_cast<const float4*>(rope_sin + pos * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = __ldg(c4 + i), b = __ldg(s4 + i);
+        cs[4 * i] = a.x; cs[4 * i + 1] = a.y; cs[4 * i + 2] = a.z; cs[4 * i + 3] = a.w;
+        sn[4 * i] = b.x; sn[4 * i + 1] = b.y; sn[4 * i + 2] = b.z; sn[4 * i + 3] = b.w;
+      }
+    }
+    mbar_wait_a(bar_d, it & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 3 * C / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_base + c * 32, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      const int which = (c * 32) / C;  // 0 q, 1 k, 2 v (compile-time after unrolling)
+      if (which < 2) {
+        const float sc = which == 0 ? qscale : 1.0f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float x0 = v[2 * i], x1 = v[2 * i + 1];
+          v[2 * i] = (x0 * cs[i] - x1 * sn[i]) * sc;
+          v[2 * i + 1] = (x1 * cs[i] + x0 * sn[i]) * sc;
+        }
+      }
+      if (valid) store_act<h16, 32>(qkv + m * (3 * C) + c * 32, v);
+    }
+    }  // tile loop
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<Cfg::TCOLS>(tmem_base);
+}
+
+struct TcQkvPlan {
+  CUtensorMap tmW;
+  int C;
+  int64_t M;
+};
+TcQkvPlan* tc_qkv_plan_create(const void* wqkv_h16, int C, int64_t M, char* err, int errlen) {
+  if (C != 32 && C != 64) { snprintf(err, errlen, "fused qkv: C must be 32 or 64"); return nullptr; }
+  TcQkvPlan* p = new TcQkvPlan();
+  p->C = C; p->M = M;
+  const uint64_t dims[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(3 * C)};
+  const uint64_t strides[1] = {static_cast<uint64_t>(C) * 2};
+  const uint32_t box[2] = {static_cast<uint32_t>(C), static_cast<uint32_t>(3 * C)};
+  if (!make_tmap(&p->tmW, wqkv_h16, 2, dims, strides, box, C * 2 < 128 ? C * 2 : 128, err, errlen)) { delete p; return nullptr; }
+  return p;
+}
+void tc_qkv_plan_destroy(TcQkvPlan* p) { delete p; }
+int launch_fused_qkv(const TcQkvPlan* p, const float* X, const float* wg, const float* bg, const float* rope_cos,
+                     const float* rope_sin, void* qkv, float* gates, int L, int F, int posmode, float qscale,
+                     cudaStream_t st) {
+  const unsigned ntiles = static_cast<unsigned>((p->M + 127) / 128);
+  const unsigned slots = static_cast<unsigned>(g_num_sms) * (p->C == 32 ? 3u : 2u);
+  const unsigned grid = ntiles < slots ? ntiles : slots;  // persistent CTAs
+  h16* q = reinterpret_cast<h16*>(qkv);
+  if (p->C == 32)
+    fused_qkv_kernel<32><<<grid, FF_THREADS, QkvCfg<32>::SMEM, st>>>(p->tmW, X, wg, bg, rope_cos, rope_sin, q, gates, p->M, L, F, posmode, qscale);
+  else
+    fused_qkv_kernel<64><<<grid, FF_THREADS, QkvCfg<64>::SMEM, st>>>(p->tmW, X, wg, bg, rope_cos, rope_sin, q, gates, p->M, L, F, posmode, qscale);
+  return 0;
+}
+int tc_init_fused(char* err, int errlen) {
+  cudaError_t r = cudaFuncSetAttribute(fused_ff_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<32>::SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<64>::SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<32>::SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_ff_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfCfg<64>::SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_qkv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, QkvCfg<32>::SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(fused_qkv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, QkvCfg<64>::SMEM);
+  if (r != cudaSuccess) {
+    snprintf(err, errlen, "cudaFuncSetAttribute(fused_ff_kernel / fused_qkv_kernel) failed: %s", cudaGetErrorString(r));
+    return -1;
+  }
+  return 0;
+}
+
+}  // namespace bt

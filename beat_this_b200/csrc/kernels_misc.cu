@@ -288,8 +288,8 @@ norm_kernel(const float* __restrict__ x, TAct* __restrict__ xn, int64_t M, float
       *reinterpret_cast<float4*>(dst) = v[i];
     } else {
       uint2 u;
-      u.x = pack_bf16x2(v[i].x, v[i].y);
-      u.y = pack_bf16x2(v[i].z, v[i].w);
+      u.x = pack_h16x2(v[i].x, v[i].y);
+      u.y = pack_h16x2(v[i].z, v[i].w);
       *reinterpret_cast<uint2*>(dst) = u;
     }
   }
@@ -312,9 +312,9 @@ static void norm_dispatch(const float* x, void* xn, int64_t M, int C, float* gat
 #undef BT_NORM_CASE
 }
 
-void launch_norm(const float* x, void* xn, int64_t M, int C, int act_bf16, cudaStream_t st, float* gates,
+void launch_norm(const float* x, void* xn, int64_t M, int C, int act_h16, cudaStream_t st, float* gates,
                  const float* wg, const float* bg, int heads) {
-  if (act_bf16) norm_dispatch<bf16>(x, xn, M, C, gates, wg, bg, heads, st);
+  if (act_h16) norm_dispatch<h16>(x, xn, M, C, gates, wg, bg, heads, st);
   else norm_dispatch<float>(x, xn, M, C, gates, wg, bg, heads, st);
 }
 
@@ -337,7 +337,7 @@ __device__ __forceinline__ void load_row32<float>(const float* p, float (&v)[32]
   }
 }
 template <>
-__device__ __forceinline__ void load_row32<bf16>(const bf16* p, float (&v)[32]) {
+__device__ __forceinline__ void load_row32<h16>(const h16* p, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint4 q = reinterpret_cast<const uint4*>(p)[i];
@@ -439,15 +439,15 @@ attn_freq_kernel(const TAct* __restrict__ qkv, const float* __restrict__ gates, 
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint4 u;
-        u.x = pack_bf16x2(o[8 * i] * gsc, o[8 * i + 1] * gsc); u.y = pack_bf16x2(o[8 * i + 2] * gsc, o[8 * i + 3] * gsc);
-        u.z = pack_bf16x2(o[8 * i + 4] * gsc, o[8 * i + 5] * gsc); u.w = pack_bf16x2(o[8 * i + 6] * gsc, o[8 * i + 7] * gsc);
+        u.x = pack_h16x2(o[8 * i] * gsc, o[8 * i + 1] * gsc); u.y = pack_h16x2(o[8 * i + 2] * gsc, o[8 * i + 3] * gsc);
+        u.z = pack_h16x2(o[8 * i + 4] * gsc, o[8 * i + 5] * gsc); u.w = pack_h16x2(o[8 * i + 6] * gsc, o[8 * i + 7] * gsc);
         reinterpret_cast<uint4*>(op)[i] = u;
       }
     }
   }
 }
 
-// bf16 path: the same attention on warp-level tensor-core MMAs (mma.sync m16n8k16, fp32 accumulate).
+// h16 path: the same attention on warp-level tensor-core MMAs (mma.sync m16n8k16, fp32 accumulate).
 // A warp stages 32 rows (32/F groups: q | k | v, 64 bytes each) in shared memory with the coalesced
 // row-per-lane loads of the SIMT kernel, then works on two 16-row query tiles: S = Q K^T from
 // ldmatrix fragments, softmax in the accumulator layout (row reductions over the 4 lanes of a quad),
@@ -462,15 +462,15 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+__device__ __forceinline__ void mma_h16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." BT_H16_MMA_SYNC ".f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 template <int F>
 __global__ void __launch_bounds__(128)
-attn_freq_mma_kernel(const bf16* __restrict__ qkv, const float* __restrict__ gates, bf16* __restrict__ out,
+attn_freq_mma_kernel(const h16* __restrict__ qkv, const float* __restrict__ gates, h16* __restrict__ out,
                      int B, int L, int heads, float scale_log2) {
   constexpr int GPW = 32 / F;
   constexpr int RS = 80;  // staged row stride in bytes (64 + 16 pad: conflict-free ldmatrix)
@@ -523,8 +523,8 @@ attn_freq_mma_kernel(const bf16* __restrict__ qkv, const float* __restrict__ gat
       sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
       uint32_t kb[4];
       ldsm_x4(sK + (key_base + 8 * j + (lane & 7)) * RS + ((lane >> 3) * 8) * 2, kb);
-      mma_bf16_16816(sc[j], qa[0], kb[0], kb[1]);
-      mma_bf16_16816(sc[j], qa[1], kb[2], kb[3]);
+      mma_h16_16816(sc[j], qa[0], kb[0], kb[1]);
+      mma_h16_16816(sc[j], qa[1], kb[2], kb[3]);
     }
     if (F == 8) {  // rows 0-7 belong to the tile's first group (keys of tile 0), rows 8-15 to the second
       sc[1][0] = sc[1][1] = -INFINITY;
@@ -554,17 +554,17 @@ attn_freq_mma_kernel(const bf16* __restrict__ qkv, const float* __restrict__ gat
 #pragma unroll
     for (int kk = 0; kk < NT / 2; ++kk) {
       uint32_t pa[4];
-      pa[0] = pack_bf16x2(sc[2 * kk][0], sc[2 * kk][1]);
-      pa[1] = pack_bf16x2(sc[2 * kk][2], sc[2 * kk][3]);
-      pa[2] = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
-      pa[3] = pack_bf16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+      pa[0] = pack_h16x2(sc[2 * kk][0], sc[2 * kk][1]);
+      pa[1] = pack_h16x2(sc[2 * kk][2], sc[2 * kk][3]);
+      pa[2] = pack_h16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+      pa[3] = pack_h16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
 #pragma unroll
       for (int jd = 0; jd < 4; jd += 2) {
         uint32_t vb[4];
         const int q4 = lane >> 3;
         ldsm_x4_trans(sV + (key_base + 16 * kk + (q4 & 1) * 8 + (lane & 7)) * RS + (8 * (jd + (q4 >> 1))) * 2, vb);
-        mma_bf16_16816(o[jd], pa, vb[0], vb[1]);
-        mma_bf16_16816(o[jd + 1], pa, vb[2], vb[3]);
+        mma_h16_16816(o[jd], pa, vb[0], vb[1]);
+        mma_h16_16816(o[jd + 1], pa, vb[2], vb[3]);
       }
     }
 #pragma unroll
@@ -575,7 +575,7 @@ attn_freq_mma_kernel(const bf16* __restrict__ qkv, const float* __restrict__ gat
         uint32_t* op = reinterpret_cast<uint32_t*>(out + m * C + h * 32);
 #pragma unroll
         for (int jd = 0; jd < 4; ++jd)
-          op[4 * jd + c] = pack_bf16x2(o[jd][2 * half] * gsc, o[jd][2 * half + 1] * gsc);
+          op[4 * jd + c] = pack_h16x2(o[jd][2 * half] * gsc, o[jd][2 * half + 1] * gsc);
       }
     }
   }
@@ -594,20 +594,20 @@ static void attn_freq_dispatch(const void* qkv, const float* gates, void* out, i
 }
 
 void launch_attn_freq(const void* qkv, const float* gates, void* out, int B, int F, int L, int heads,
-                      float scale, int act_bf16, cudaStream_t st) {
+                      float scale, int act_h16, cudaStream_t st) {
   static const bool simt = getenv("BT_ATTN_FREQ_SIMT") && atoi(getenv("BT_ATTN_FREQ_SIMT")) != 0;
-  if (act_bf16 && !simt && (F == 32 || F == 16 || F == 8)) {
+  if (act_h16 && !simt && (F == 32 || F == 16 || F == 8)) {
     const int64_t ngrp = static_cast<int64_t>(B) * L * heads;
     const unsigned grid = static_cast<unsigned>(ceil_div64(ngrp, 4 * (32 / F)));
-    const bf16* q = reinterpret_cast<const bf16*>(qkv);
-    bf16* o = reinterpret_cast<bf16*>(out);
+    const h16* q = reinterpret_cast<const h16*>(qkv);
+    h16* o = reinterpret_cast<h16*>(out);
     const float sl2 = scale * 1.4426950408889634f;
     if (F == 32) attn_freq_mma_kernel<32><<<grid, 128, 0, st>>>(q, gates, o, B, L, heads, sl2);
     else if (F == 16) attn_freq_mma_kernel<16><<<grid, 128, 0, st>>>(q, gates, o, B, L, heads, sl2);
     else attn_freq_mma_kernel<8><<<grid, 128, 0, st>>>(q, gates, o, B, L, heads, sl2);
     return;
   }
-  if (act_bf16) attn_freq_dispatch<bf16>(qkv, gates, out, B, F, L, heads, scale, st);
+  if (act_h16) attn_freq_dispatch<h16>(qkv, gates, out, B, F, L, heads, scale, st);
   else attn_freq_dispatch<float>(qkv, gates, out, B, F, L, heads, scale, st);
 }
 
@@ -779,21 +779,21 @@ void launch_peakpick(const float* beat, const float* down, const int64_t* frame_
 }
 
 // ------------------------------------------------------------------------------------------ utils
-__global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
+__global__ void f32_to_h16_kernel(const float* __restrict__ in, h16* __restrict__ out, int64_t n) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+  if (i < n) out[i] = to_out<h16>(in[i]);
 }
-__global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, int64_t n) {
+__global__ void h16_to_f32_kernel(const h16* __restrict__ in, float* __restrict__ out, int64_t n) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __bfloat162float(in[i]);
+  if (i < n) out[i] = to_f32(in[i]);
 }
-void launch_f32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t st) {
+void launch_f32_to_h16(const float* in, void* out, int64_t n, cudaStream_t st) {
   if (n <= 0) return;
-  f32_to_bf16_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, st>>>(in, reinterpret_cast<bf16*>(out), n);
+  f32_to_h16_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, st>>>(in, reinterpret_cast<h16*>(out), n);
 }
-void launch_bf16_to_f32(const void* in, float* out, int64_t n, cudaStream_t st) {
+void launch_h16_to_f32(const void* in, float* out, int64_t n, cudaStream_t st) {
   if (n <= 0) return;
-  bf16_to_f32_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, st>>>(reinterpret_cast<const bf16*>(in), out, n);
+  h16_to_f32_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, st>>>(reinterpret_cast<const h16*>(in), out, n);
 }
 
 template <typename TAct>
@@ -811,11 +811,11 @@ __global__ void pack_qkv_test_kernel(const float* __restrict__ q, const float* _
   qkv[m * 3 * C + 2 * C + c] = to_out<TAct>(v[i]);
 }
 void launch_pack_qkv_test(const float* q, const float* k, const float* v, void* qkv, int seqs, int L, int heads,
-                          float qscale, int act_bf16, cudaStream_t st) {
+                          float qscale, int act_h16, cudaStream_t st) {
   const int64_t n = static_cast<int64_t>(seqs) * L * heads * 32;
   const unsigned grid = static_cast<unsigned>(ceil_div64(n, 256));
-  if (act_bf16)
-    pack_qkv_test_kernel<bf16><<<grid, 256, 0, st>>>(q, k, v, reinterpret_cast<bf16*>(qkv), seqs, L, heads, qscale);
+  if (act_h16)
+    pack_qkv_test_kernel<h16><<<grid, 256, 0, st>>>(q, k, v, reinterpret_cast<h16*>(qkv), seqs, L, heads, qscale);
   else
     pack_qkv_test_kernel<float><<<grid, 256, 0, st>>>(q, k, v, reinterpret_cast<float*>(qkv), seqs, L, heads, qscale);
 }

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BT_DTYPE_BF16, BT_DTYPE_F32, bt_hparams, i64_array
+from ._lib import BT_DTYPE_H16, BT_DTYPE_F32, bt_hparams, i64_array
 
 
 def _cuda_device(device) -> torch.device:
@@ -42,10 +42,11 @@ class _PeakHandle:
 
 
 class Engine:
-    def __init__(self, packed: dict | None, hparams: dict | None, device="cuda", bf16: bool = False, wave_chunks: int | None = None):
+    def __init__(self, packed: dict | None, hparams: dict | None, device="cuda", half: bool = False, wave_chunks: int | None = None):
         self.lib = _lib.load()
         self.device = _cuda_device(device)
-        self.bf16 = bool(bf16)
+        self.half = bool(half)  # 16-bit tcgen05 path (fp16 operands; see bt_act_dtype) instead of fp32 CUDA cores
+        self.act_dtype = self.lib.bt_act_dtype().decode() if half else "f32"
         hp = hparams or {}
         self.hparams = dict(hp)
         chp = bt_hparams(
@@ -59,7 +60,7 @@ class Engine:
             int(bool(hp.get("partial_transformers", True))),
         )
         ctx = c_void_p()
-        code = self.lib.bt_create(ctypes.byref(ctx), self.device.index, ctypes.byref(chp), BT_DTYPE_BF16 if bf16 else BT_DTYPE_F32)
+        code = self.lib.bt_create(ctypes.byref(ctx), self.device.index, ctypes.byref(chp), BT_DTYPE_H16 if half else BT_DTYPE_F32)
         _lib.check(self.lib, None, code)
         self.ctx = ctx
         self._model_ready = False
@@ -168,6 +169,30 @@ class Engine:
                                         c_void_p(beat.data_ptr()), c_void_p(down.data_ptr()), self._stream())
         _lib.check(self.lib, self.ctx, code)
         return beat, down
+
+    def forward_chunks(self, chunks: torch.Tensor):
+        """BeatThis.forward on [B, T<=1500, 128] chunks (no chunk planning, no borders cut): flat (beat, downbeat)."""
+        assert self._model_ready, "model parameters not loaded"
+        assert chunks.is_cuda and chunks.dtype == torch.float32 and chunks.is_contiguous() and chunks.ndim == 3
+        B, T, _ = chunks.shape
+        beat = torch.empty(B * T, dtype=torch.float32, device=self.device)
+        down = torch.empty(B * T, dtype=torch.float32, device=self.device)
+        code = self.lib.bt_forward_chunks(self.ctx, c_void_p(chunks.data_ptr()), B, T, c_void_p(beat.data_ptr()),
+                                          c_void_p(down.data_ptr()), self._stream())
+        _lib.check(self.lib, self.ctx, code)
+        return beat, down
+
+    def tap_chunks(self, name: str, chunks: torch.Tensor, capacity: int):
+        """Test hook: activation `name` of a forward_chunks call (single wave)."""
+        buf = torch.zeros(capacity, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib, self.ctx, self.lib.bt_debug_request_tap(self.ctx, name.encode(), c_void_p(buf.data_ptr()), capacity))
+        try:
+            out = self.forward_chunks(chunks)
+            torch.cuda.synchronize(self.device)
+            n = int(self.lib.bt_debug_tap_count(self.ctx))
+        finally:
+            self.lib.bt_debug_request_tap(self.ctx, b"", None, 0)
+        return buf[:n], out
 
     def audio2frames_cat(self, audio: torch.Tensor, sample_offsets):
         assert self._model_ready, "model parameters not loaded"

@@ -78,10 +78,16 @@ class Postprocessor:
         return self._postp_dbn(beat, downbeat, frame_offsets)
 
     def _postp_dbn(self, beat, downbeat, frame_offsets):
-        # reference postprocessor.py:138-173 (host, float64)
-        bp = beat.double().sigmoid().cpu().numpy()
-        dp = downbeat.double().sigmoid().cpu().numpy()
+        return self.batch_host(beat.float().cpu().numpy(), downbeat.float().cpu().numpy(), frame_offsets)
+
+    def batch_host(self, beat_logits: np.ndarray, downbeat_logits: np.ndarray, frame_offsets):
+        """DBN post-processing of concatenated host logits (reference postprocessor.py:138-173, float64 on the host):
+        list of (beat_times, downbeat_times)."""
+        assert self.type == "dbn"
         eps = 1e-5
+        # sigmoid in float64 as torch.sigmoid(logits.double()) does
+        bp = 1.0 / (1.0 + np.exp(-beat_logits.astype(np.float64)))
+        dp = 1.0 / (1.0 + np.exp(-downbeat_logits.astype(np.float64)))
         bp = bp * (1 - eps) + eps / 2
         dp = dp * (1 - eps) + eps / 2
 

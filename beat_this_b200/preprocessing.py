@@ -3,8 +3,9 @@
 ``LogMelSpect`` keeps the reference's constructor defaults and call signature
 (preprocessing.py:27-59) but runs the fused sm_100a kernel (frame -> Hann -> 1024-point FFT
 -> |.| -> 128-band slaney mel -> log1p(1000 x)) through ``bt_logmel``.
-``load_audio`` (preprocessing.py:6-24) reads PCM/float WAV files with the standard library /
-scipy (torchaudio's decoder backends, soundfile and madmom are not available offline).
+``load_audio`` (preprocessing.py:6-24) walks the reference's decoder chain (torchaudio, soundfile, madmom -- whichever
+is installed) and then two dependency-free WAV readers; the batched File2Beats path reads WAV files natively
+(``bt_stage_wav_files``) and only falls back to this function for other containers.
 """
 from __future__ import annotations
 
@@ -22,43 +23,71 @@ F_MIN = 30.0
 F_MAX = 11000.0
 
 
-def load_audio(path, dtype="float64"):
-    """Returns (waveform[time] or [time, channels], samplerate); float in [-1, 1) like
-    torchaudio/soundfile (reference preprocessing.py:6-24)."""
-    try:
-        try:
-            from scipy.io import wavfile
+def _decode_torchaudio(path, dtype):
+    import torchaudio
 
-            sr, data = wavfile.read(str(path))
-            if data.dtype == np.int16:
-                wav = data.astype(dtype) / 32768.0
-            elif data.dtype == np.int32:
-                wav = data.astype(dtype) / 2147483648.0
-            elif data.dtype == np.uint8:
-                wav = (data.astype(dtype) - 128.0) / 128.0
-            else:
-                wav = data.astype(dtype)
-            return wav, int(sr)
-        except Exception:
-            with wave.open(str(path), "rb") as w:
-                sr, nch, sw, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
-                raw = w.readframes(n)
-            if sw == 2:
-                wav = np.frombuffer(raw, dtype="<i2").astype(dtype) / 32768.0
-            elif sw == 3:
-                b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
-                v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
-                v = np.where(v >= 1 << 23, v - (1 << 24), v)
-                wav = v.astype(dtype) / 8388608.0
-            elif sw == 4:
-                wav = np.frombuffer(raw, dtype="<i4").astype(dtype) / 2147483648.0
-            else:
-                wav = (np.frombuffer(raw, dtype=np.uint8).astype(dtype) - 128.0) / 128.0
-            if nch > 1:
-                wav = wav.reshape(-1, nch)
-            return wav, int(sr)
-    except Exception:
-        raise RuntimeError(f'Could not load audio from "{path}".')
+    waveform, sr = torchaudio.load(str(path), channels_first=False)
+    return np.asanyarray(waveform.squeeze().numpy(), dtype=dtype), int(sr)
+
+
+def _decode_soundfile(path, dtype):
+    import soundfile
+
+    wav, sr = soundfile.read(str(path), dtype=dtype)
+    return wav, int(sr)
+
+
+def _decode_madmom(path, dtype):
+    import madmom.io
+
+    wav, sr = madmom.io.load_audio_file(str(path), dtype=dtype)
+    return wav, int(sr)
+
+
+def _decode_wav_scipy(path, dtype):
+    from scipy.io import wavfile
+
+    sr, data = wavfile.read(str(path))
+    full_scale = {np.dtype(np.int16): 32768.0, np.dtype(np.int32): 2147483648.0}
+    if data.dtype in full_scale:
+        wav = data.astype(dtype) / full_scale[data.dtype]
+    elif data.dtype == np.uint8:
+        wav = (data.astype(dtype) - 128.0) / 128.0
+    else:
+        wav = data.astype(dtype)
+    return wav, int(sr)
+
+
+def _decode_wav_stdlib(path, dtype):
+    with wave.open(str(path), "rb") as w:
+        sr, nch, width = w.getframerate(), w.getnchannels(), w.getsampwidth()
+        raw = np.frombuffer(w.readframes(w.getnframes()), dtype=np.uint8)
+    if width == 1:
+        wav = (raw.astype(dtype) - 128.0) / 128.0
+    else:  # little-endian signed PCM of `width` bytes: assemble in int64, sign-extend
+        b = raw.reshape(-1, width).astype(np.int64)
+        v = sum(b[:, k] << (8 * k) for k in range(width))
+        v = np.where(v >= 1 << (8 * width - 1), v - (1 << (8 * width)), v)
+        wav = v.astype(dtype) / float(1 << (8 * width - 1))
+    return (wav.reshape(-1, nch) if nch > 1 else wav), int(sr)
+
+
+# tried in this order; the first three are the reference's chain (preprocessing.py:6-24), the last two need nothing
+# beyond scipy / the standard library and keep WAV input working where none of those packages has a decoder
+AUDIO_BACKENDS = (("torchaudio", _decode_torchaudio), ("soundfile", _decode_soundfile), ("madmom", _decode_madmom),
+                  ("scipy.io.wavfile", _decode_wav_scipy), ("wave", _decode_wav_stdlib))
+
+
+def load_audio(path, dtype="float64"):
+    """(waveform [time] or [time, channels] in [-1, 1), sample rate) like reference preprocessing.py:6-24: torchaudio,
+    then soundfile, then madmom (each only if it is installed and can decode the file), then two WAV-only readers."""
+    tried = []
+    for name, decode in AUDIO_BACKENDS:
+        try:
+            return decode(path, dtype)
+        except Exception as e:  # missing package, missing codec, unreadable file: next backend
+            tried.append(f"{name}: {type(e).__name__}")
+    raise RuntimeError(f'Could not load audio from "{path}". (' + "; ".join(tried) + ")")
 
 
 # ------------------------------------------------------------------------------------------

@@ -34,9 +34,13 @@ extern "C" {
 #define BT_ERR_CUDA (-2)
 #define BT_ERR_STATE (-3)
 #define BT_ERR_PARAM (-4)
+#define BT_ERR_IO (-5)     /* file could not be opened / read */
+#define BT_ERR_FORMAT (-6) /* not a RIFF/WAVE file this library decodes (caller falls back to another decoder) */
 
 #define BT_DTYPE_F32 0  /* fp32 CUDA-core kernels: the reference's float16=False numerics   */
-#define BT_DTYPE_BF16 1 /* bf16 tcgen05 tensor-core kernels, fp32 accumulate + fp32 residual */
+#define BT_DTYPE_H16 1 /* 16-bit tcgen05 tensor-core kernels, fp32 accumulate + fp32 residual stream.  Operand type
+                        * fp16 (what the reference's float16=True autocasts to on CUDA, inference.py:245-246);
+                        * bt_act_dtype() names it ("f16", or "bf16" for a -DBT_ACT_BF16 build) */
 
 #define BT_SAMPLE_RATE 22050
 #define BT_N_FFT 1024
@@ -64,10 +68,13 @@ typedef struct bt_hparams {
 /* Library / ABI version (major*100 + minor). */
 int bt_version(void);
 
+/* Operand type of the BT_DTYPE_H16 path in this build: "f16" or "bf16". */
+const char* bt_act_dtype(void);
+
 /* ---- model lifetime: replaces load_model (inference.py:56-87) ------------------------ */
 
 /* Create a context on CUDA device `device_ordinal` for a model of shape `hp`.
- * compute_dtype: BT_DTYPE_F32 or BT_DTYPE_BF16. */
+ * compute_dtype: BT_DTYPE_F32 or BT_DTYPE_H16. */
 int bt_create(bt_ctx** out, int device_ordinal, const bt_hparams* hp, int compute_dtype);
 
 /* Upload one packed parameter (fp32, host memory, `count` elements) under `name`.
@@ -77,7 +84,7 @@ int bt_create(bt_ctx** out, int device_ordinal, const bt_hparams* hp, int comput
  * parameters".  Replaces model.load_state_dict (inference.py:84). */
 int bt_set_param(bt_ctx* ctx, const char* name, const float* data_host, int64_t count);
 
-/* Check that every parameter the model shape needs is present, build bf16 copies and TMA
+/* Check that every parameter the model shape needs is present, build 16-bit operand copies and TMA
  * descriptors.  After this the weights are immutable.  (model.to(device).eval(), :87) */
 int bt_finalize(bt_ctx* ctx);
 
@@ -97,6 +104,43 @@ int64_t bt_num_frames(int64_t n_samples);
  * avoid_short_end: writes up to `cap` chunk starts and lengths, returns the chunk count
  * (or the count needed when cap is too small). */
 int64_t bt_plan_chunks(int64_t T, int64_t* starts, int64_t* lens, int64_t cap);
+
+/* ---- host front door: Audio2Frames.signal2spect's host half (inference.py:269-276) ------------------ */
+
+#define BT_SIG_F32 0 /* float32 samples                                                         */
+#define BT_SIG_F64 1 /* float64 samples (what the reference's load_audio returns)                */
+#define BT_SIG_I16 2 /* int16 PCM, scaled by 1/32768 (== soundfile / torchaudio's float decode)  */
+
+/* Mono mix + fp32 cast of n_clips host signals into one host buffer (normally pinned; it is the source of the single
+ * H2D copy of a batch): clip i is signals[i], `frames[i]` x `channels[i]` samples, channels-last and contiguous, of
+ * type dtypes[i]; its mono fp32 samples land at dst + dst_offsets[i].  The arithmetic is the reference's: the mean
+ * over channels in the array's own floating type (numpy `signal.mean(1)`, inference.py:270-271; float64 for PCM),
+ * then the cast of `torch.tensor(signal, dtype=torch.float32)` (:276).  Runs on n_threads host threads (<= 0: all);
+ * no CUDA, no ctx. */
+int bt_stage_audio(const void* const* signals, const int32_t* dtypes, const int64_t* frames,
+                   const int32_t* channels, int32_t n_clips, float* dst, const int64_t* dst_offsets,
+                   int32_t n_threads);
+
+/* RIFF/WAVE front door of load_audio (preprocessing.py:6-24) for the batched File2Beats path. */
+typedef struct bt_wav_info {
+  int32_t sample_rate;
+  int32_t channels;
+  int32_t bytes_per_sample; /* 1, 2, 3, 4 (PCM) or 4, 8 (IEEE float) */
+  int32_t is_float;
+  int64_t frames;
+  int64_t data_offset;      /* byte offset of the first sample in the file */
+} bt_wav_info;
+
+/* Parse the header of a WAV file (PCM 8/16/24/32-bit, IEEE float 32/64-bit, incl. WAVE_FORMAT_EXTENSIBLE).
+ * BT_ERR_IO: cannot open; BT_ERR_FORMAT: not such a file. */
+int bt_wav_probe(const char* path, bt_wav_info* info);
+
+/* Decode n_files probed WAV files on n_threads host threads: samples -> float64 as soundfile would return them
+ * (PCM / 2^(bits-1)), mean over channels in float64, fp32 cast -- i.e. load_audio + the host half of
+ * signal2spect -- written to dst + dst_offsets[i] (infos[i].frames samples each).  status[i] (optional) receives
+ * BT_OK / BT_ERR_IO per file; files that fail are zero-filled and the call returns BT_ERR_IO. */
+int bt_stage_wav_files(const char* const* paths, const bt_wav_info* infos, int32_t n_files, float* dst,
+                       const int64_t* dst_offsets, int32_t n_threads, int32_t* status);
 
 /* ---- the hot path ------------------------------------------------------------------------- */
 
@@ -148,6 +192,12 @@ int bt_dbn_track(const double* activations, const int64_t* frame_offsets, int32_
 int bt_spect2frames(bt_ctx* ctx, const float* spect_dev, const int64_t* frame_offsets_host,
                     int32_t n_clips, float* beat_dev, float* downbeat_dev, void* stream);
 
+/* BeatThis.forward (model/beat_tracker.py:188-192) on n_chunks spectrogram chunks of chunk_frames (<= 1500) frames
+ * each, chunks_dev = [n_chunks, chunk_frames, 128] fp32: no chunk planning, no borders cut -- the model call inside
+ * split_predict_aggregate (inference.py:215), batched.  beat_dev / downbeat_dev: [n_chunks, chunk_frames] fp32. */
+int bt_forward_chunks(bt_ctx* ctx, const float* chunks_dev, int32_t n_chunks, int32_t chunk_frames,
+                      float* beat_dev, float* downbeat_dev, void* stream);
+
 /* Audio2Frames.__call__ (inference.py:279-281) for already mono, 22.05 kHz fp32 audio:
  * bt_logmel + bt_spect2frames with the spectrogram kept in the ctx workspace. */
 int bt_audio2frames(bt_ctx* ctx, const float* audio_dev, const int64_t* sample_offsets_host,
@@ -166,7 +216,7 @@ int bt_peakpick(bt_ctx* ctx, const float* beat_dev, const float* downbeat_dev,
 /* ---- introspection / tuning ----------------------------------------------------------------- */
 
 /* Upper bound on the chunks processed per wave (default 128; one wave = one launch of every
- * kernel of the forward pass).  The workspace (~46 MB per 1500-frame chunk in bf16) grows on
+ * kernel of the forward pass).  The workspace (~46 MB per 1500-frame chunk on the 16-bit path) grows on
  * demand up to this many chunks. */
 int bt_set_wave_chunks(bt_ctx* ctx, int32_t chunks);
 
@@ -192,7 +242,7 @@ int bt_debug_request_tap(bt_ctx* ctx, const char* tap, float* out_dev, int64_t c
 int64_t bt_debug_tap_count(const bt_ctx* ctx);
 
 /* Test hook: D[M,N] = A[M,K] * W[N,K]^T through the ctx's GEMM for its compute dtype
- * (fp32 inputs on device; the bf16 path rounds A and W to bf16 first). */
+ * (fp32 inputs on device; the 16-bit path rounds A and W to its operand type first). */
 int bt_debug_gemm(bt_ctx* ctx, const float* a_dev, const float* w_dev, float* d_dev,
                   int32_t M, int32_t N, int32_t K, void* stream);
 

@@ -78,6 +78,62 @@ def main():
     table["Ts"] = np.asarray(Ts, dtype=np.int64)
     np.savez_compressed(os.path.join(GOLD, "chunking.npz"), **table)
 
+    # ---- 2b. function-level API: split_piece chunk CONTENTS and aggregate_prediction (both overlap modes), other
+    # chunk sizes than 1500 / 6 included.  "Predictions" are the chunk's own first two columns, so the fixtures pin
+    # exactly which chunk every output frame is taken from.
+    host = {}
+    cases = [(37, 16, 2), (100, 16, 2), (1501, 1500, 6), (3001, 1500, 6), (250, 1500, 6), (64, 20, 0), (95, 32, 5)]
+    for k, (T, cs, bs) in enumerate(cases):
+        g = torch.Generator().manual_seed(100 + k)
+        sp = torch.rand(T, 3, generator=g) + 1.0
+        chunks, starts = ref_inf.split_piece(sp, cs, bs, True)
+        preds = [{"beat": c[:, 0] * (i + 1), "downbeat": c[:, 1] - i} for i, c in enumerate(chunks)]
+        host[f"case{k}"] = np.asarray([T, cs, bs], dtype=np.int64)
+        host[f"spect{k}"] = sp.numpy()
+        host[f"starts{k}"] = np.asarray(starts, dtype=np.int64)
+        host[f"chunks{k}"] = torch.cat(chunks).numpy()
+        host[f"lens{k}"] = np.asarray([len(c) for c in chunks], dtype=np.int64)
+        for mode in ("keep_first", "keep_last"):
+            b, d = ref_inf.aggregate_prediction(preds, starts, T, cs, bs, mode, "cpu")
+            host[f"{mode}_beat{k}"] = b.numpy()
+            host[f"{mode}_down{k}"] = d.numpy()
+    host["n"] = np.int64(len(cases))
+    np.savez_compressed(os.path.join(GOLD, "host_api.npz"), **host)
+
+    # ---- 2c. .beats writer (reference beat_this/utils.py:26-102): beat numbers and the exact file text for seeded
+    # beat / downbeat sets incl. pickup bars, a pickup longer than the first bar, fewer than two downbeats, no beats
+    import contextlib
+    import io
+    import tempfile
+
+    import beat_this.utils as ref_utils
+
+    rng = np.random.default_rng(21)
+    tsv = {}
+    sets = []
+    for _ in range(6):  # regular material: random tempo, random bar length, random pickup
+        n = int(rng.integers(8, 60))
+        beats = np.cumsum(rng.uniform(0.3, 0.9, n)).round(2)
+        bar = int(rng.integers(2, 6))
+        first = int(rng.integers(0, bar + 3))
+        sets.append((beats, beats[first::bar]))
+    b = np.arange(12) * 0.5
+    sets += [(b, b[5:6]), (b, b[:0]), (b, b[7::2]), (b[:0], b[:0]), (b, b[[0, 3, 7, 9]]), (b[:1], b[:1])]
+    for k, (beats, downs) in enumerate(sets):
+        out = io.StringIO()
+        with contextlib.redirect_stdout(out):
+            numbers = ref_utils.infer_beat_numbers(beats, downs)
+        with tempfile.TemporaryDirectory() as td, contextlib.redirect_stdout(io.StringIO()):
+            ref_utils.save_beat_tsv(beats, downs, os.path.join(td, "x.beats"))
+            text = open(os.path.join(td, "x.beats")).read()
+        tsv[f"beats{k}"] = np.asarray(beats, dtype=np.float64)
+        tsv[f"downs{k}"] = np.asarray(downs, dtype=np.float64)
+        tsv[f"numbers{k}"] = np.asarray(numbers, dtype=np.int64)
+        tsv[f"text{k}"] = np.frombuffer(text.encode(), dtype=np.uint8)
+        tsv[f"warned{k}"] = np.int64(1 if out.getvalue().strip() else 0)
+    tsv["n"] = np.int64(len(sets))
+    np.savez_compressed(os.path.join(GOLD, "beats_tsv.npz"), **tsv)
+
     # ---- 3. minimal postprocessor known-answer cases --------------------------------------------
     post = RefPostprocessor("minimal")
     rng = np.random.default_rng(7)
