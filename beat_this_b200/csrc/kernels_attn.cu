@@ -24,8 +24,14 @@ constexpr int A6_SK = 4096, A6_SV = 4096;
 constexpr int A6_SMEM = AT_SQ + A6_NST * (A6_SK + A6_SV) + 1024 + 128;
 constexpr int A6_THREADS = 160;
 constexpr uint32_t A6_TM_O = 64, A6_TM_P = 96;
+constexpr int A6_DEFAULT_PP = 3;
 
-template <int POLY>  // every POLY-th exponential on the FMA pipe (0: all on MUFU)
+// which of every 8 score pairs take the polynomial exp2 (spread out so that MUFU and FMA work interleave)
+__host__ __device__ constexpr uint32_t attn_poly_mask(int pp) {
+  return pp == 0 ? 0x00u : pp == 1 ? 0x08u : pp == 2 ? 0x44u : pp == 3 ? 0x52u : pp == 4 ? 0xAAu : pp == 5 ? 0xB5u : pp == 6 ? 0xBBu : 0xFFu;
+}
+
+template <int PP>  // PP of every 8 score pairs: exp2 on the FMA pipe (packed polynomial); the rest on MUFU
 __global__ void __launch_bounds__(A6_THREADS, 4)
 attn_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const float* __restrict__ gates, h16* __restrict__ out, int L, int heads) {
@@ -50,6 +56,7 @@ attn_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int nkv = ceil_div(L, A6_BKV);
   constexpr int MMA_WARP = 4;
   constexpr int NSOFT = 128;
+  constexpr uint32_t POLY_MASK = attn_poly_mask(PP);
 
   if (warp == MMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -147,37 +154,47 @@ attn_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int i = 0; i < 64; ++i)
           if (i >= lim) s[i] = -INFINITY;
       }
-      float mxs[8];
+      // row maximum: four independent chains of 3-input maxima (FMNMX3, ALU pipe)
+      float mq[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) mxs[k] = fmaxf(s[k], s[8 + k]);
+      for (int k = 0; k < 4; ++k) {
+        float m = max3f(s[16 * k], s[16 * k + 1], s[16 * k + 2]);
 #pragma unroll
-      for (int i = 16; i < 64; i += 16) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) mxs[k] = fmaxf(mxs[k], fmaxf(s[i + k], s[i + 8 + k]));
+        for (int i = 3; i < 15; i += 2) m = max3f(m, s[16 * k + i], s[16 * k + i + 1]);
+        mq[k] = fmaxf(m, s[16 * k + 15]);
       }
-      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
-                             fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+      const float mx = fmaxf(max3f(mq[0], mq[1], mq[2]), mq[3]);
       const bool need = mx > m_ref + AT_TAU;  // always true for j == 0 (m_ref = -inf)
       const bool any_need = __any_sync(0xffffffffu, need);
       const float a_corr = (need && j > 0) ? ex2_approx(m_ref - mx) : 1.0f;
       if (need) { m_ref = mx; l *= a_corr; }
+      // P = exp2(S - m_ref) two scores at a time on packed fp32 (FADD2 / FFMA2: one issue slot per pair).  PP of every
+      // 8 pairs take the Cody-Waite + degree-3 polynomial on the FMA pipe instead of MUFU.EX2 (16 /clk/SM): with
+      // head_dim 32 there are only 128 tensor FLOPs per exponential, so this kernel is bound by the exponentials.
       uint32_t pk[32];
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      uint64_t ls2[2] = {0ull, 0ull};
+      const uint64_t m2 = pack_f32x2(m_ref, m_ref);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float p[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float x = s[c * 8 + i] - m_ref;
-          p[i] = (POLY > 0 && i % (POLY > 0 ? POLY : 1) == (POLY > 0 ? POLY : 1) - 1) ? ex2_poly(x) : ex2_approx(x);
+      for (int q = 0; q < 32; ++q) {
+        const uint64_t x2 = sub_f32x2(pack_f32x2(s[2 * q], s[2 * q + 1]), m2);
+        uint64_t p2;
+        if ((POLY_MASK >> (q & 7)) & 1u) {
+          p2 = ex2_poly_f32x2(x2);
+        } else {
+          float x0, x1;
+          unpack_f32x2(x2, x0, x1);
+          p2 = pack_f32x2(ex2_approx(x0), ex2_approx(x1));
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          pk[c * 4 + i] = pack_h16x2(p[2 * i], p[2 * i + 1]);
-          ls[i] += p[2 * i] + p[2 * i + 1];
-        }
+        float p0, p1;
+        unpack_f32x2(p2, p0, p1);
+        pk[q] = pack_h16x2(p0, p1);
+        ls2[q & 1] = add_f32x2(ls2[q & 1], p2);
       }
-      l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      {
+        float a0, a1;
+        unpack_f32x2(add_f32x2(ls2[0], ls2[1]), a0, a1);
+        l += a0 + a1;
+      }
       if (j >= 1) {  // PV_{j-1} complete: P may be overwritten, O holds tiles 0..j-1
         mbar_wait_a(bar_pv + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
         tc_fence_after();
@@ -249,20 +266,28 @@ void tc_attn_plan_destroy(TcAttnPlan* p) { delete p; }
 
 int launch_attn_time_tc(const TcAttnPlan* p, const float* gates, void* out, cudaStream_t st) {
   dim3 grid(ceil_div(p->L, AT_BQ), p->heads, p->seqs);
-  static const int poly64 = getenv("BT_ATTN_POLY") ? atoi(getenv("BT_ATTN_POLY")) : 0;
-  if (poly64 == 8)
-    attn_tc64_kernel<8><<<grid, A6_THREADS, A6_SMEM, st>>>(p->tmQK, p->tmKV64, gates, reinterpret_cast<h16*>(out), p->L, p->heads);
-  else if (poly64 == 4)
-    attn_tc64_kernel<4><<<grid, A6_THREADS, A6_SMEM, st>>>(p->tmQK, p->tmKV64, gates, reinterpret_cast<h16*>(out), p->L, p->heads);
-  else
-    attn_tc64_kernel<0><<<grid, A6_THREADS, A6_SMEM, st>>>(p->tmQK, p->tmKV64, gates, reinterpret_cast<h16*>(out), p->L, p->heads);
+  // BT_ATTN_POLY = number of score pairs out of 8 whose exp2 runs on the FMA pipe (default: measured best)
+  static const int pp = getenv("BT_ATTN_POLY") ? atoi(getenv("BT_ATTN_POLY")) : A6_DEFAULT_PP;
+  h16* o = reinterpret_cast<h16*>(out);
+#define BT_A6_L(P_) attn_tc64_kernel<P_><<<grid, A6_THREADS, A6_SMEM, st>>>(p->tmQK, p->tmKV64, gates, o, p->L, p->heads)
+  switch (pp) {
+    case 0: BT_A6_L(0); break;
+    case 1: BT_A6_L(1); break;
+    case 2: BT_A6_L(2); break;
+    case 3: BT_A6_L(3); break;
+    case 4: BT_A6_L(4); break;
+    default: return -3;
+  }
+#undef BT_A6_L
   return 0;
 }
 
 int tc_init_attn(char* err, int errlen) {
   cudaError_t r = cudaFuncSetAttribute(attn_tc64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(attn_tc64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(attn_tc64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(attn_tc64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM);
   if (r == cudaSuccess) r = cudaFuncSetAttribute(attn_tc64_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM);
-  if (r == cudaSuccess) r = cudaFuncSetAttribute(attn_tc64_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM);
   if (r != cudaSuccess) {
     snprintf(err, errlen, "cudaFuncSetAttribute(attn_tc64_kernel) failed: %s", cudaGetErrorString(r));
     return -1;

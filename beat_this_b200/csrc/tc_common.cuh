@@ -68,20 +68,56 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x for x <= AT_TAU on the FMA/ALU pipes (Cody-Waite split + degree-3 polynomial, rel. error
-// 8e-5, far below the h16 rounding of P).  The MUFU pipe (16 ex2/clk/SM) is one bottleneck
-// of head_dim-32 attention -- 128 tensor FLOPs per exponential -- so a fixed fraction of the
-// exponentials is moved to the FMA pipe (the FlashAttention-4 trick).
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -120.0f);
-  const float t = x + 12582912.0f;        // 1.5 * 2^23: round(x) lands in the low mantissa bits
-  const float r = x - (t - 12582912.0f);  // [-0.5, 0.5]
-  float p = fmaf(0.05508868f, r, 0.24260405f);
-  p = fmaf(p, r, 0.69327623f);
-  p = fmaf(p, r, 0.99992895f);
-  int y;  // p * 2^round(x): add round(x) (low mantissa bits of t) to the exponent field, one IMAD
-  asm("mad.lo.s32 %0, %1, 8388608, %2;" : "=r"(y) : "r"(__float_as_int(t)), "r"(__float_as_int(p)));
-  return __int_as_float(y);
+// ---- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 take one issue slot for two lanes' worth of work) ----
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float max3f(float a, float b, float c) {  // FMNMX3
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// 2^x for a pair of scores on the FMA / ALU pipes: Cody-Waite split (n = round(x) through the 1.5 * 2^23 trick,
+// r = x - n in [-0.5, 0.5]) + degree-3 minimax polynomial (relative error 8e-5, a fifth of an fp16 ulp of the
+// probability it produces) + exponent insertion by an integer shift-add.  Inputs below -120 (masked keys are -inf)
+// are clamped; the result underflows to 0 in the 16-bit pack either way.
+__device__ __forceinline__ uint64_t ex2_poly_f32x2(uint64_t x2) {
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  const uint64_t x = pack_f32x2(fmaxf(x0, -120.0f), fmaxf(x1, -120.0f));
+  const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);
+  const uint64_t t = add_f32x2(x, magic);
+  const uint64_t r = sub_f32x2(x, sub_f32x2(t, magic));
+  uint64_t p = fma_f32x2(pack_f32x2(0.05508868f, 0.05508868f), r, pack_f32x2(0.24260405f, 0.24260405f));
+  p = fma_f32x2(p, r, pack_f32x2(0.69327623f, 0.69327623f));
+  p = fma_f32x2(p, r, pack_f32x2(0.99992895f, 0.99992895f));
+  float t0, t1, p0, p1;
+  unpack_f32x2(t, t0, t1);
+  unpack_f32x2(p, p0, p1);
+  int y0, y1;  // p * 2^n: n sits in the low mantissa bits of t
+  asm("mad.lo.s32 %0, %1, 8388608, %2;" : "=r"(y0) : "r"(__float_as_int(t0)), "r"(__float_as_int(p0)));
+  asm("mad.lo.s32 %0, %1, 8388608, %2;" : "=r"(y1) : "r"(__float_as_int(t1)), "r"(__float_as_int(p1)));
+  return pack_f32x2(__int_as_float(y0), __int_as_float(y1));
 }
 __device__ __forceinline__ uint32_t tmem_ld_32x32b_x1(uint32_t taddr) {
   uint32_t r;

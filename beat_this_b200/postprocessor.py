@@ -85,9 +85,9 @@ class Postprocessor:
         list of (beat_times, downbeat_times)."""
         assert self.type == "dbn"
         eps = 1e-5
-        # sigmoid in float64 as torch.sigmoid(logits.double()) does
-        bp = 1.0 / (1.0 + np.exp(-beat_logits.astype(np.float64)))
-        dp = 1.0 / (1.0 + np.exp(-downbeat_logits.astype(np.float64)))
+        # beat.double().sigmoid() with the reference's own torch op (postprocessor.py:139-140)
+        bp = torch.from_numpy(np.ascontiguousarray(beat_logits)).double().sigmoid().numpy()
+        dp = torch.from_numpy(np.ascontiguousarray(downbeat_logits)).double().sigmoid().numpy()
         bp = bp * (1 - eps) + eps / 2
         dp = dp * (1 - eps) + eps / 2
 

@@ -4,7 +4,9 @@ golden fixtures written from the reference's own outputs (tests/golden, oracle/m
 
 Tolerances (stated, per north_star):
   fp32 path  : frame logits within 1e-3 of the fp32 reference (measured ~1e-4).
-  bf16 path  : frame logits within BF16_TOL (absolute, logits have std ~2 and range +-8).
+  16-bit path: fp16 operands (the reference's float16=True autocast dtype), fp32 accumulate and residual stream:
+               frame logits within H16_TOL = 0.05 absolute of the fp32 reference (logits have std ~2, range +-8);
+               per-stage activations within H16_STAGE_TOL absolute.
 """
 import math
 import os
@@ -18,7 +20,8 @@ from conftest import GOLDEN
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 F32_TOL = 1e-3
-BF16_TOL = 0.35
+H16_TOL = 0.05
+H16_STAGE_TOL = 0.03
 
 
 @pytest.fixture(scope="module")
@@ -28,10 +31,10 @@ def dev():
     return torch.device("cuda:0")
 
 
-def _engine(ckpt, bf16):
+def _engine(ckpt, half):
     from beat_this_b200.inference import load_model
 
-    return load_model(ckpt, "cuda:0", float16=bf16)
+    return load_model(ckpt, "cuda:0", float16=half)
 
 
 @pytest.fixture(scope="module")
@@ -40,7 +43,7 @@ def small_f32(small0_ckpt, lib_built, dev):
 
 
 @pytest.fixture(scope="module")
-def small_bf16(small0_ckpt, lib_built, dev):
+def small_h16(small0_ckpt, lib_built, dev):
     return _engine(small0_ckpt, True)
 
 
@@ -50,7 +53,7 @@ def final_f32(final0_ckpt, lib_built, dev):
 
 
 @pytest.fixture(scope="module")
-def final_bf16(final0_ckpt, lib_built, dev):
+def final_h16(final0_ckpt, lib_built, dev):
     return _engine(final0_ckpt, True)
 
 
@@ -123,25 +126,25 @@ def test_peakpick_golden_bit_exact(lib_built, dev):
 GEMM_SHAPES = [(300, 96, 32), (1500, 32, 128), (1000, 64, 64), (700, 192, 64), (1500, 1536, 512), (520, 512, 2048), (257, 128, 256)]
 
 
-@pytest.mark.parametrize("bf16", [False, True])
-def test_debug_gemm(small_f32, small_bf16, bf16):
-    eng = (small_bf16 if bf16 else small_f32).engine
+@pytest.mark.parametrize("half", [False, True])
+def test_debug_gemm(small_f32, small_h16, half):
+    eng = (small_h16 if half else small_f32).engine
     g = torch.Generator(device="cpu").manual_seed(1)
     for M, N, K in GEMM_SHAPES:
         a = torch.randn(M, K, generator=g)
         w = torch.randn(N, K, generator=g) / math.sqrt(K)
-        if bf16:
-            a, w = a.bfloat16().float(), w.bfloat16().float()
+        if half:  # the 16-bit path rounds its operands: compare on the rounded values (fp32 accumulation is what is tested)
+            a, w = a.half().float(), w.half().float()
         ref = a.double() @ w.double().T
         d = eng.debug_gemm(a.cuda(), w.cuda()).cpu().double()
         err = (d - ref).abs().max().item()
-        print(f"gemm bf16={bf16} {M}x{N}x{K}: max abs err {err:.3e}")
-        assert err < (2e-3 if bf16 else 1e-4), (M, N, K)
+        print(f"gemm half={half} {M}x{N}x{K}: max abs err {err:.3e}")
+        assert err < 1e-4, (M, N, K)
 
 
-@pytest.mark.parametrize("bf16", [False, True])
-def test_debug_attention(small_f32, small_bf16, bf16):
-    eng = (small_bf16 if bf16 else small_f32).engine
+@pytest.mark.parametrize("half", [False, True])
+def test_debug_attention(small_f32, small_h16, half):
+    eng = (small_h16 if half else small_f32).engine
     g = torch.Generator(device="cpu").manual_seed(2)
     for seqs, L, heads in [(3, 1500, 2), (2, 200, 1), (1, 13, 4), (2, 128, 1), (1, 129, 1)]:
         q = torch.randn(seqs, L, heads * 32, generator=g) * 1.5
@@ -151,8 +154,8 @@ def test_debug_attention(small_f32, small_bf16, bf16):
         ref = torch.nn.functional.scaled_dot_product_attention(sh(q), sh(k), sh(v)).permute(0, 2, 1, 3).reshape(seqs, L, -1)
         o = eng.debug_attention(q.cuda(), k.cuda(), v.cuda()).cpu().double()
         err = (o - ref).abs().max().item()
-        print(f"attention bf16={bf16} seqs={seqs} L={L} heads={heads}: max abs err {err:.3e}")
-        assert err < (3e-2 if bf16 else 1e-4), (seqs, L, heads)
+        print(f"attention half={half} seqs={seqs} L={L} heads={heads}: max abs err {err:.3e}")
+        assert err < (5e-3 if half else 1e-4), (seqs, L, heads)
 
 
 @pytest.mark.parametrize("sr", [44100, 48000, 16000, 96000])
@@ -216,11 +219,50 @@ def test_stage_parity_fp32(small_f32, small0_ckpt):
     assert max(r[1] for r in rows) < 1e-3
 
 
-def test_stage_parity_bf16(small_bf16, small0_ckpt):
-    rows = _stage_errors(small_bf16, small0_ckpt)
+def test_stage_parity_h16(small_h16, small0_ckpt):
+    rows = _stage_errors(small_h16, small0_ckpt)
     for name, err, mag in rows:
-        print(f"bf16 stage {name:10s} max abs err {err:.3e} (|ref| max {mag:.2f})")
-    assert max(r[1] / max(r[2], 1.0) for r in rows) < 0.05
+        print(f"h16 stage {name:10s} max abs err {err:.3e} (|ref| max {mag:.2f})")
+    assert max(r[1] for r in rows) < H16_STAGE_TOL
+
+
+def _stage_errors_full_chunks(model, ckpt, nchunks=2, T=1500):
+    """Per-stage taps on FULL 1500-frame chunks (the shape the bench runs: 256x64 GEMM tiles, 24 key tiles per
+    attention row) through bt_forward_chunks, against the oracle forward of the same chunks."""
+    from oracle import beat_this_oracle as O
+
+    sd = _sd(ckpt)
+    torch.manual_seed(4)
+    chunks = torch.rand(nchunks, T, 128) * 7
+    taps = {}
+    with torch.inference_mode():
+        rb, rd = O.forward(sd, chunks, taps)
+    dev_chunks = chunks.cuda()
+    rows = []
+    for name in TAPS:
+        ref = taps[name]
+        got, _ = model.engine.tap_chunks(name, dev_chunks, ref.numel())
+        assert got.numel() == ref.numel(), name
+        rows.append((name, (got.cpu().view(ref.shape) - ref).abs().max().item(), ref.abs().max().item()))
+    out = model(dev_chunks)
+    rows.append(("logits", max((out["beat"].cpu() - rb).abs().max().item(), (out["downbeat"].cpu() - rd).abs().max().item()),
+                 max(rb.abs().max().item(), rd.abs().max().item())))
+    return rows
+
+
+def test_stage_parity_final0_full_chunks_fp32(final_f32, final0_ckpt):
+    rows = _stage_errors_full_chunks(final_f32, final0_ckpt)
+    for name, err, mag in rows:
+        print(f"final0 T=1500 fp32 stage {name:10s} max abs err {err:.3e} (|ref| max {mag:.2f})")
+    assert max(r[1] for r in rows) < 1e-3
+
+
+def test_stage_parity_final0_full_chunks_h16(final_h16, final0_ckpt):
+    rows = _stage_errors_full_chunks(final_h16, final0_ckpt)
+    for name, err, mag in rows:
+        print(f"final0 T=1500 h16 stage {name:10s} max abs err {err:.3e} (|ref| max {mag:.2f})")
+    assert max(r[1] for r in rows[:-1]) < H16_STAGE_TOL
+    assert rows[-1][1] < H16_TOL
 
 
 def test_postprocessor_batched_with_padding_mask(lib_built, dev):

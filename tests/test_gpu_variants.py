@@ -11,10 +11,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 VARIANTS = [
-    {"BT_ATTN_VARIANT": "128"},                       # 2 CTAs/SM attention kernel, two threads per row
-    {"BT_ATTN_VARIANT": "128", "BT_ATTN_KS": "4"},    # ... four threads per row
-    {"BT_ATTN_VARIANT": "128", "BT_ATTN_POLY": "4"},  # ... polynomial exp2 on every 4th score
-    {"BT_ATTN_POLY": "8"},                            # default kernel with polynomial exp2 share
+    {"BT_ATTN_POLY": "0"},                            # attention: every exponential on MUFU
+    {"BT_ATTN_POLY": "2"},                            # ... 2 / 4 of every 8 score pairs on the packed FMA-pipe polynomial
+    {"BT_ATTN_POLY": "4"},
     {"BT_ATTN_FREQ_SIMT": "1"},                       # CUDA-core frequency attention
     {"BT_FUSE_FF": "0"},                              # unfused frontend blocks (norm + GEMMs)
     {"BT_FUSE_OUTPROJ": "0"},                         # separate attention out-projection GEMM in front of the fused FFN
@@ -29,6 +28,6 @@ def test_variant_kernel_parity(env, lib_built):
     e.update(env)
     r = subprocess.run(
         [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_kernels.py"), "-m", "gpu", "-q", "-x",
-         "-p", "no:cacheprovider", "-k", "debug_attention or stage_parity_bf16 or debug_gemm"],
+         "-p", "no:cacheprovider", "-k", "debug_attention or stage_parity_h16 or debug_gemm"],
         cwd=ROOT, env=e, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
