@@ -45,7 +45,14 @@ __device__ __forceinline__ uint32_t pack_h16x2(float lo, float hi) {
   __half2 p = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&p);
 }
+__device__ __forceinline__ void unpack_h16x2(uint32_t w, float& lo, float& hi) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+  lo = f.x; hi = f.y;
+}
 #else
+__device__ __forceinline__ void unpack_h16x2(uint32_t w, float& lo, float& hi) {  // bf16 = the top half of an fp32
+  lo = __uint_as_float(w << 16); hi = __uint_as_float(w & 0xffff0000u);
+}
 template <>
 __device__ __forceinline__ h16 to_out<h16>(float v) { return __float2bfloat16_rn(v); }
 __device__ __forceinline__ float to_f32(h16 v) { return __bfloat162float(v); }

@@ -24,7 +24,7 @@ constexpr int A6_SK = 4096, A6_SV = 4096;
 constexpr int A6_SMEM = AT_SQ + A6_NST * (A6_SK + A6_SV) + 1024 + 128;
 constexpr int A6_THREADS = 160;
 constexpr uint32_t A6_TM_O = 64, A6_TM_P = 96;
-constexpr int A6_DEFAULT_PP = 3;
+constexpr int A6_DEFAULT_PP = 0;  // measured (profiles/r2_notes.md): every polynomial share is slower than 0
 
 // which of every 8 score pairs take the polynomial exp2 (spread out so that MUFU and FMA work interleave)
 __host__ __device__ constexpr uint32_t attn_poly_mask(int pp) {

@@ -58,38 +58,66 @@ constexpr int TG_BM = 128;
 constexpr int TG_EPI_WARPS = 8;
 constexpr int TG_THREADS = 64 + 32 * TG_EPI_WARPS;  // warp0 TMA, warp1 MMA, 8 epilogue warps
 
-template <int BN, int BK>
+// TE = epilogue through TMA in both directions (BN >= 128): every epilogue warp owns a staging area
+//   [fp32 tile 0: 32 rows x 128 B][fp32 tile 1][optional 16-bit tile: 32 rows x 64 B][bias of the warp's columns]
+// the fp32 residual tile is TMA-loaded into a staging tile (the next chunk's tile is in flight while the current one
+// is processed), the result overwrites it in place and is TMA-stored from there; 16-bit outputs rotate through the
+// same area as 2 KB tiles.  Threads never touch global memory: the row-per-lane ld/st.global of the direct epilogue
+// (32 sectors per warp instruction) kept the LSU queue full and the next tcgen05.ld waiting on the registers of
+// stores still queued (ncu source view, profiles/r2_notes.md).
+template <int BN, int BK, bool TE>
 struct TgCfg {
   static constexpr int A_BYTES = TG_BM * BK * 2;
   static constexpr int W_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
-  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+  static constexpr int EPI_H16_EXTRA = (TE && BN <= 192) ? 2048 : 0;   // third staging tile: fp32 + 16-bit outputs together
+  static constexpr int EPI_WARP = TE ? 8192 + EPI_H16_EXTRA : 0;      // staging tiles of one warp (multiple of 1024)
+  // bias: TE: 512 B slice per warp (the warp's <= 128 columns of the current tile); direct epilogue: whole vector
+  static constexpr int BIAS_BYTES = TE ? TG_EPI_WARPS * 512 : 16384;
+  static constexpr int FIXED = 1024 /*align*/ + 512 /*barriers*/ + BIAS_BYTES + TG_EPI_WARPS * EPI_WARP;
+  static constexpr int STAGES_FIT = (232448 - FIXED) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int TCOLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
-  static constexpr int BIAS_BYTES = 16384;  // bias vector (N <= 4096 floats) staged for the epilogue
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BIAS_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + FIXED;
   static constexpr int SWZ = BK * 2;  // 128 or 64 byte rows
 };
 
-template <int BN, int BK>
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {  // at most N of this thread's bulk groups still read shared memory
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+template <int BN, int BK, bool TE>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const GemmShape g, const EpiParams e, int num_tiles, int t_tiles, int n_tiles, int m_tiles) {
-  using Cfg = TgCfg<BN, BK>;
+               const __grid_constant__ CUtensorMap tmOutAct, const __grid_constant__ CUtensorMap tmOutF32,
+               const __grid_constant__ CUtensorMap tmResid, const GemmShape g, const EpiParams e, int num_tiles,
+               int t_tiles, int n_tiles, int m_tiles) {
+  using Cfg = TgCfg<BN, BK, TE>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sW = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (STAGE_BYTES % 1024 == 0): TE staging tiles
+  uint64_t* full = reinterpret_cast<uint64_t*>(sEpi + TG_EPI_WARPS * Cfg::EPI_WARP);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sBias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+  uint64_t* rbar = tempty + 4;  // TE: [TG_EPI_WARPS][2] residual-tile barriers
+  float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 512);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool stage_bias = e.kind == 0 && e.bias != nullptr && g.N <= Cfg::BIAS_BYTES / 4;
+  const bool stage_bias = !TE && e.kind == 0 && e.bias != nullptr && g.N <= Cfg::BIAS_BYTES / 4;
   if (stage_bias)
     for (int i = threadIdx.x; i < g.N; i += TG_THREADS) sBias[i] = __ldg(e.bias + i);
   const uint32_t bias_smem = stage_bias ? smem_u32(sBias) : 0u;
@@ -97,10 +125,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
+    if constexpr (TE) {
+      if (e.out_act) tma_prefetch_desc(&tmOutAct);
+      if (e.out_f32) tma_prefetch_desc(&tmOutF32);
+      if (e.resid) tma_prefetch_desc(&tmResid);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], BN <= 64 ? TG_EPI_WARPS / 2 : TG_EPI_WARPS); }
+    if constexpr (TE)
+      for (int i = 0; i < 2 * TG_EPI_WARPS; ++i) mbar_init(&rbar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TCOLS>(tmem_ptr);
@@ -162,6 +197,162 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+  } else if constexpr (TE) {
+    // TMA epilogue (see TgCfg).  Warp (quarter, half): TMEM lanes / tile rows [32*quarter, +32), columns
+    // [half*BN/2, +BN/2) in chunks of 32; thread = one output row of the chunk.
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    constexpr int NCH = BN / 32;
+    constexpr int SPLIT = (NCH + 1) / 2;
+    const int c_begin = half == 0 ? 0 : SPLIT;
+    const int nch = half == 0 ? SPLIT : NCH - SPLIT;
+    const uint32_t ebase = smem_u32(sEpi) + static_cast<uint32_t>(ew) * Cfg::EPI_WARP;
+    const uint32_t bias_w = smem_u32(sBias) + 512u * ew;  // this warp's bias slice
+    const uint32_t rb0 = smem_u32(&rbar[2 * ew]);
+    const bool has_bias = e.kind == 0 && e.bias != nullptr;
+    const bool has_resid = e.kind == 0 && e.resid != nullptr;
+    const bool f32_out = e.out_f32 != nullptr;
+    const bool act_out = e.out_act != nullptr;
+    const bool act_only = act_out && !f32_out;
+    // 16-bit tile of a chunk: rotates through the 8 KB as four 2 KB tiles when it is the only output, else the extra tile
+    const uint32_t sw64 = static_cast<uint32_t>((lane >> 1) & 3) << 4;
+    const uint32_t sw128 = static_cast<uint32_t>(lane & 7) << 4;
+    uint32_t rphase = 0;   // bit b: parity of residual barrier b
+    int ck = 0;            // running chunk counter of this warp (staging tile rotation continues across tiles)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / n_tiles, nt = tile % n_tiles;
+      const int p_out = mt / t_tiles;
+      const int trow0 = (mt - p_out * t_tiles) * TG_BM + quarter * 32;  // first row of this warp inside the plane
+      const int t = trow0 + lane;
+      const int64_t m = static_cast<int64_t>(p_out) * g.L + t;
+      const int col_w = nt * BN + c_begin * 32;  // first column of this warp
+      if (has_bias) {  // bias of the warp's columns -> shared memory (broadcast reads in the chunk loop)
+        if (4 * lane < nch * 32) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col_w) + lane);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bias_w + 16u * lane), "f"(b4.x), "f"(b4.y), "f"(b4.z), "f"(b4.w) : "memory");
+        }
+        __syncwarp();
+      }
+      float cs[16], sn[16];  // kind 1: cos | sin of this row's position, reused by every q / k head of the row
+      if (e.kind == 1) {
+        const int tt = t < g.L ? t : 0;
+        const int pos = e.posmode == 0 ? tt : static_cast<int>(p_out % e.F);
+        const float4* c4 = reinterpret_cast<const float4*>(e.rope_cos + pos * 16);
+        const float4* s4 = reinterpret_cast<const float4*>(e.rope_sin + pos * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 a = __ldg(c4 + i), b = __ldg(s4 + i);
+          cs[4 * i] = a.x; cs[4 * i + 1] = a.y; cs[4 * i + 2] = a.z; cs[4 * i + 3] = a.w;
+          sn[4 * i] = b.x; sn[4 * i + 1] = b.y; sn[4 * i + 2] = b.z; sn[4 * i + 3] = b.w;
+        }
+      }
+      if (has_resid) {  // residual tile of the first chunk (its staging tile was released two chunks ago)
+        const int b = ck & 1;
+        if (lane == 0) {
+          bulk_wait_read<1>();
+          mbar_expect_tx_a(rb0 + 8 * b, 4096);
+          tma_load_3d_a(ebase + 4096 * b, &tmResid, rb0 + 8 * b, col_w, trow0, p_out);
+        }
+        __syncwarp();
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int k = 0; k < nch; ++k, ++ck) {
+        const int n0 = col_w + k * 32;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + (c_begin + k) * 32, r);
+        const int b = ck & 1;
+        const uint32_t fbuf = ebase + 4096 * b;                                  // fp32 staging tile of this chunk
+        const uint32_t hbuf = act_only ? ebase + 2048 * (ck & 3) : ebase + 8192;  // 16-bit staging tile
+        if (lane == 0) {
+          // staging tiles about to be (re)written must have been read by their last TMA store
+          if (has_resid) {
+            // next chunk's residual tile goes into the other fp32 tile, last stored one chunk ago; a 16-bit copy
+            // (single extra tile) was last stored one chunk ago as well
+            if (k + 1 < nch || (act_out && !act_only)) bulk_wait_read<0>();
+            if (k + 1 < nch) {
+              mbar_expect_tx_a(rb0 + 8 * (b ^ 1), 4096);
+              tma_load_3d_a(ebase + 4096 * (b ^ 1), &tmResid, rb0 + 8 * (b ^ 1), n0 + 32, trow0, p_out);
+            }
+          } else if (act_only) {
+            bulk_wait_read<3>();
+          } else {
+            bulk_wait_read<Cfg::EPI_H16_EXTRA ? 0 : 1>();
+          }
+        }
+        __syncwarp();
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (e.kind == 0) {
+          if (has_bias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 q = ld_shared_v4_f32(bias_w + static_cast<uint32_t>(k * 32 + 4 * i) * 4u);
+              v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+            }
+          }
+          if (e.gelu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_fast(v[i]);
+          }
+          if (has_resid) {
+            mbar_wait_a(rb0 + 8 * b, (rphase >> b) & 1u);
+            rphase ^= 1u << b;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 q = ld_shared_v4_f32(fbuf + lane * 128 + ((static_cast<uint32_t>(i) << 4) ^ sw128));
+              v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+            }
+          }
+        } else {  // kind 1: RoPE on interleaved pairs (rotary_embedding_torch semantics, roformer.py:121-123) + q scaling
+          const int which = n0 / e.C;  // 0 q, 1 k, 2 v: a 32-column chunk is one head of one of them
+          if (which < 2) {
+            const float sc = which == 0 ? e.qscale : 1.0f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float x0 = v[2 * i], x1 = v[2 * i + 1];
+              v[2 * i] = (x0 * cs[i] - x1 * sn[i]) * sc;
+              v[2 * i + 1] = (x1 * cs[i] + x0 * sn[i]) * sc;
+            }
+          }
+        }
+        if (f32_out) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(fbuf + lane * 128 + ((static_cast<uint32_t>(i) << 4) ^ sw128)),
+                         "f"(v[4 * i]), "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
+        }
+        if (act_out && (act_only || Cfg::EPI_H16_EXTRA)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            st_shared_v4(hbuf + lane * 64 + ((static_cast<uint32_t>(i) << 4) ^ sw64), pack_h16x2(v[8 * i], v[8 * i + 1]),
+                         pack_h16x2(v[8 * i + 2], v[8 * i + 3]), pack_h16x2(v[8 * i + 4], v[8 * i + 5]),
+                         pack_h16x2(v[8 * i + 6], v[8 * i + 7]));
+        } else if (act_out) {  // fp32 + 16-bit outputs without room for a third staging tile: direct row store
+          if (t < g.L) store_act<h16, 32>(reinterpret_cast<h16*>(e.out_act) + m * e.ldo_act + n0, v);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (f32_out) tma_store_3d(&tmOutF32, fbuf, n0, trow0, p_out);
+          if (act_out && (act_only || Cfg::EPI_H16_EXTRA)) tma_store_3d(&tmOutAct, hbuf, n0, trow0, p_out);
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last stores' reads
+    __syncwarp();
   } else {
     // Epilogue warps.  A warp may only touch TMEM lanes [32*(warp%4), +32); thread = one output row.
     //  BN >= 96: the 8 warps split the columns of every tile (2 warps per lane quarter);
@@ -255,6 +446,12 @@ struct TcGemmPlan {
   GemmShape g;
   int BN, BK;
   int num_tiles, t_tiles, n_tiles, m_tiles, grid;
+  // TMA epilogue: output / residual tensor maps, (re)encoded when the epilogue targets of a launch change (a call
+  // site always passes the same ones, so this happens once)
+  mutable CUtensorMap tmOutAct, tmOutF32, tmResid;
+  mutable const void *k_act = nullptr, *k_f32 = nullptr, *k_res = nullptr;
+  mutable int k_lda = 0, k_ldf = 0, k_ldr = 0;
+  mutable bool epi_ok = false;
 };
 
 static int pick_bn(int N) {
@@ -264,18 +461,50 @@ static int pick_bn(int N) {
   return 0;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool TE>
 static int gemm_tc_launch(const TcGemmPlan* p, const EpiParams& e, cudaStream_t st) {
-  using Cfg = TgCfg<BN, BK>;
+  using Cfg = TgCfg<BN, BK, TE>;
+  static_assert(Cfg::STAGES >= 2, "pipeline too shallow");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t r = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t r = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (r != cudaSuccess) return -1;
     attr_set = true;
   }
-  gemm_tc_kernel<BN, BK><<<p->grid, TG_THREADS, Cfg::SMEM, st>>>(p->tmA, p->tmW, p->g, e, p->num_tiles, p->t_tiles,
-                                                                   p->n_tiles, p->m_tiles);
+  gemm_tc_kernel<BN, BK, TE><<<p->grid, TG_THREADS, Cfg::SMEM, st>>>(p->tmA, p->tmW, p->tmOutAct, p->tmOutF32, p->tmResid, p->g,
+                                                                       e, p->num_tiles, p->t_tiles, p->n_tiles, p->m_tiles);
   return 0;
+}
+
+// tensor maps of the epilogue targets: [planes_out, L, ld] row-major views with 32-row x 32-column boxes, so that
+// the rows a tile has beyond the end of its plane (L is not a multiple of 128) are clipped / zero-filled by TMA
+static bool prepare_tma_epilogue(const TcGemmPlan* p, const EpiParams& e) {
+  if (p->k_act == e.out_act && p->k_f32 == e.out_f32 && p->k_res == e.resid && p->k_lda == e.ldo_act && p->k_ldf == e.ldo_f32 &&
+      p->k_ldr == e.ldr)
+    return p->epi_ok;
+  p->k_act = e.out_act; p->k_f32 = e.out_f32; p->k_res = e.resid;
+  p->k_lda = e.ldo_act; p->k_ldf = e.ldo_f32; p->k_ldr = e.ldr;
+  char err[256];
+  const GemmShape& g = p->g;
+  bool ok = true;
+  auto enc = [&](CUtensorMap* tm, const void* base, int ld, bool f32) {
+    const uint64_t es = f32 ? 4 : 2;
+    const uint64_t dims[3] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(g.L), static_cast<uint64_t>(g.planes_out)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(ld) * es, static_cast<uint64_t>(g.L) * ld * es};
+    const uint32_t box[3] = {32, 32, 1};
+    return f32 ? make_tmap_f32(tm, base, 3, dims, strides, box, 128, err, sizeof(err))
+               : make_tmap(tm, base, 3, dims, strides, box, 64, err, sizeof(err));
+  };
+  // TMA needs 16-byte aligned bases and row pitches
+  auto aligned = [](const void* q, int ld, int es) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (static_cast<int64_t>(ld) * es) % 16 == 0; };
+  if (e.out_act) ok = ok && aligned(e.out_act, e.ldo_act, 2) && enc(&p->tmOutAct, e.out_act, e.ldo_act, false);
+  if (e.out_f32) ok = ok && aligned(e.out_f32, e.ldo_f32, 4) && enc(&p->tmOutF32, e.out_f32, e.ldo_f32, true);
+  if (e.resid) ok = ok && aligned(e.resid, e.ldr, 4) && enc(&p->tmResid, e.resid, e.ldr, true);
+  if (!e.out_act) p->tmOutAct = p->tmA;  // never dereferenced
+  if (!e.out_f32) p->tmOutF32 = p->tmA;
+  if (!e.resid) p->tmResid = p->tmA;
+  p->epi_ok = ok;
+  return ok;
 }
 
 TcGemmPlan* tc_gemm_plan_create(const void* A, const void* W, const GemmShape& g, int planes_in, char* err,
@@ -314,8 +543,18 @@ TcGemmPlan* tc_gemm_plan_create(const void* A, const void* W, const GemmShape& g
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 
 int launch_gemm_tc(const TcGemmPlan* p, const EpiParams& e, cudaStream_t st) {
+  // BT_GEMM_TMA_EPI=0: direct (row-per-lane ld/st.global) epilogue everywhere, for A/B measurements
+  static const bool te_enabled = !(getenv("BT_GEMM_TMA_EPI") && getenv("BT_GEMM_TMA_EPI")[0] == '0');
+  const bool te = te_enabled && p->BN >= 128 && p->BK == 64 && e.kind != 2 && (e.out_act || e.out_f32) &&
+                  (e.kind == 0 || e.C % 32 == 0) && prepare_tma_epilogue(p, e);
+  if (te) {
+    if (p->BN == 256) return gemm_tc_launch<256, 64, true>(p, e, st);
+    if (p->BN == 192) return gemm_tc_launch<192, 64, true>(p, e, st);
+    if (p->BN == 128) return gemm_tc_launch<128, 64, true>(p, e, st);
+  }
+  if (!p->epi_ok) { p->tmOutAct = p->tmA; p->tmOutF32 = p->tmA; p->tmResid = p->tmA; }
 #define BT_TG_CASE(bn, bk) \
-  if (p->BN == bn && p->BK == bk) return gemm_tc_launch<bn, bk>(p, e, st);
+  if (p->BN == bn && p->BK == bk) return gemm_tc_launch<bn, bk, false>(p, e, st);
   BT_TG_CASE(256, 64) BT_TG_CASE(192, 64) BT_TG_CASE(128, 64) BT_TG_CASE(96, 64) BT_TG_CASE(64, 64)
   BT_TG_CASE(32, 64) BT_TG_CASE(128, 32) BT_TG_CASE(96, 32) BT_TG_CASE(64, 32) BT_TG_CASE(32, 32)
 #undef BT_TG_CASE

@@ -343,10 +343,7 @@ __device__ __forceinline__ void load_row32<h16>(const h16* p, float (&v)[32]) {
     const uint4 q = reinterpret_cast<const uint4*>(p)[i];
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v[8 * i + 2 * j] = __uint_as_float(w[j] << 16);
-      v[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
-    }
+    for (int j = 0; j < 4; ++j) unpack_h16x2(w[j], v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
   }
 }
 
