@@ -376,7 +376,7 @@ int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool f
     static const int gin_max = getenv("BT_GATES_IN_NORM_MAX") ? atoi(getenv("BT_GATES_IN_NORM_MAX")) : 2;
     const bool gates_in_norm = heads <= gin_max;
     launch_norm(X, c->XN, M, C, tc, st, gates_in_norm ? c->GATES : nullptr, w.wg->f32, w.bg->f32, heads);
-    BT_LAUNCHED(c, gates_in_norm ? "norm_gates" : "norm", st);
+    BT_LAUNCHED(c, gates_in_norm ? "norm_gates" : (F > 1 ? "norm_front" : "norm"), st);
     if (!gates_in_norm) {  // gates = sigmoid(to_gates(x_normed)): a [heads -> 32 padded] x C GEMM on the same rows
       GemmShape gg = plain_shape(planes, L, 32, C, C);
       EpiParams eg{};
@@ -384,7 +384,7 @@ int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool f
       eg.bias = w.bg->f32;
       eg.heads = heads;
       eg.out_f32 = c->GATES;
-      int rg = run_gemm(c, c->XN, w.wg, tp ? tp->gates : nullptr, gg, eg, "gemm_gates", st);
+      int rg = run_gemm(c, c->XN, w.wg, tp ? tp->gates : nullptr, gg, eg, F > 1 ? "gemm_gates_front" : "gemm_gates", st);
       if (rg != BT_OK) return rg;
     }
     EpiParams e{};
@@ -395,7 +395,7 @@ int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool f
     e.C = C; e.heads = heads; e.posmode = freq ? 1 : 0; e.F = F;
     e.qscale = qscale;
     GemmShape g = plain_shape(planes, L, 3 * C, C, C);
-    r = run_gemm(c, c->XN, w.wqkv, tp ? tp->qkv : nullptr, g, e, "gemm_qkv", st);
+    r = run_gemm(c, c->XN, w.wqkv, tp ? tp->qkv : nullptr, g, e, F > 1 ? "gemm_qkv_front" : "gemm_qkv", st);
     if (r != BT_OK) return r;
   }
   if (freq) {
@@ -412,12 +412,12 @@ int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool f
   if (skip_out) return BT_OK;
   GemmShape go = plain_shape(planes, L, C, C, C);
   EpiParams eo = epi_generic(nullptr, 0, X, C, X, C, nullptr, 0);
-  return run_gemm(c, c->O, w.wout, tp ? tp->out : nullptr, go, eo, "gemm_attn_out", st);
+  return run_gemm(c, c->O, w.wout, tp ? tp->out : nullptr, go, eo, F > 1 ? "gemm_attn_out_front" : "gemm_attn_out", st);
 }
 
 // x += ff(x) (reference roformer.py:38-61); optionally also writes a bf16 copy of the result.
 int ff_block(bt_ctx* c, float* X, int planes, int L, int C, int mult, const FfW& w, FfPlans* tp, void* copy_act,
-             cudaStream_t st, bool with_outproj = false) {
+             cudaStream_t st, bool with_outproj = false, bool front = false) {
   const bool tc = c->dtype == BT_DTYPE_H16;
   const int64_t M = static_cast<int64_t>(planes) * L;
   if (with_outproj && !(tc && tp && tp->fused_op)) return fail(c, BT_ERR_ARG, "fused out-projection requested without a plan");
@@ -428,14 +428,14 @@ int ff_block(bt_ctx* c, float* X, int planes, int L, int C, int mult, const FfW&
     return BT_OK;
   }
   launch_norm(X, c->XN, M, C, tc, st);
-  BT_LAUNCHED(c, "norm", st);
+  BT_LAUNCHED(c, front ? "norm_front" : "norm", st);
   GemmShape g1 = plain_shape(planes, L, mult * C, C, C);
   EpiParams e1 = epi_generic(w.b1, 1, nullptr, 0, nullptr, 0, c->H, mult * C);
-  int r = run_gemm(c, c->XN, w.w1, tp ? tp->ff1 : nullptr, g1, e1, "gemm_ff1", st);
+  int r = run_gemm(c, c->XN, w.w1, tp ? tp->ff1 : nullptr, g1, e1, front ? "gemm_ff1_front" : "gemm_ff1", st);
   if (r != BT_OK) return r;
   GemmShape g2 = plain_shape(planes, L, C, mult * C, mult * C);
   EpiParams e2 = epi_generic(w.b2, 0, X, C, X, C, copy_act, C);
-  return run_gemm(c, c->H, w.w2, tp ? tp->ff2 : nullptr, g2, e2, "gemm_ff2", st);
+  return run_gemm(c, c->H, w.w2, tp ? tp->ff2 : nullptr, g2, e2, front ? "gemm_ff2_front" : "gemm_ff2", st);
 }
 
 AttnW attn_w(const bt_ctx* c, const std::string& p) {
@@ -573,11 +573,11 @@ int run_wave(bt_ctx* c, const float* spect, const Wave& wv, float* beat, float* 
       const bool op_t = wp && wp->ff_t[i].fused_op && (c->tap_name.empty() || c->tap_name != p + ".attnT");
       if ((r = attention_block(c, X, planes, L, C, F, true, c->mw.fa[i], wp ? &wp->fa[i] : nullptr, nb, st, op_f)) != BT_OK) return r;
       if ((r = do_tap(c, (p + ".attnF").c_str(), X, elems, false, st)) != BT_OK) return r;
-      if ((r = ff_block(c, X, planes, L, C, 4, c->mw.ff_f[i], wp ? &wp->ff_f[i] : nullptr, nullptr, st, op_f)) != BT_OK) return r;
+      if ((r = ff_block(c, X, planes, L, C, 4, c->mw.ff_f[i], wp ? &wp->ff_f[i] : nullptr, nullptr, st, op_f, true)) != BT_OK) return r;
       if ((r = do_tap(c, (p + ".ffF").c_str(), X, elems, false, st)) != BT_OK) return r;
       if ((r = attention_block(c, X, planes, L, C, F, false, c->mw.ta[i], wp ? &wp->ta[i] : nullptr, nb, st, op_t)) != BT_OK) return r;
       if ((r = do_tap(c, (p + ".attnT").c_str(), X, elems, false, st)) != BT_OK) return r;
-      if ((r = ff_block(c, X, planes, L, C, 4, c->mw.ff_t[i], wp ? &wp->ff_t[i] : nullptr, copy_for_conv, st, op_t)) != BT_OK) return r;
+      if ((r = ff_block(c, X, planes, L, C, 4, c->mw.ff_t[i], wp ? &wp->ff_t[i] : nullptr, copy_for_conv, st, op_t, true)) != BT_OK) return r;
       if ((r = do_tap(c, (p + ".ffT").c_str(), X, elems, false, st)) != BT_OK) return r;
     } else if (tc) {
       launch_f32_to_h16(X, c->XB, elems, st);

@@ -94,12 +94,17 @@ __device__ __forceinline__ void bulk_wait_read() {  // at most N of this thread'
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
-template <int BN, int BK, bool TE>
+// EM: 0 direct epilogue (epilogue.cuh, any EpiParams); TMA epilogues: EM_QKV RoPE + q scale -> 16-bit; EM_ACT bias +
+// GELU -> 16-bit; EM_RESID [bias +] fp32 residual -> fp32 in place [+ 16-bit copy]; EM_F32 bias [+ GELU] -> fp32
+enum { EM_DIRECT = 0, EM_QKV = 1, EM_ACT = 2, EM_RESID = 3, EM_F32 = 4 };
+
+template <int BN, int BK, int EM>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmOutAct, const __grid_constant__ CUtensorMap tmOutF32,
                const __grid_constant__ CUtensorMap tmResid, const GemmShape g, const EpiParams e, int num_tiles,
                int t_tiles, int n_tiles, int m_tiles) {
+  constexpr bool TE = EM != EM_DIRECT;
   using Cfg = TgCfg<BN, BK, TE>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -198,8 +203,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (acc == 0) acc_phase ^= 1;
     }
   } else if constexpr (TE) {
-    // TMA epilogue (see TgCfg).  Warp (quarter, half): TMEM lanes / tile rows [32*quarter, +32), columns
-    // [half*BN/2, +BN/2) in chunks of 32; thread = one output row of the chunk.
+    // TMA epilogue (see TgCfg), specialised at compile time by EM (what the call site needs) so that the chunk loop
+    // is straight-line code on packed fp32 pairs.  Warp (quarter, half): TMEM lanes / tile rows [32*quarter, +32),
+    // columns [half*BN/2, +BN/2) in chunks of 32; thread = one output row of the chunk.  The accumulator chunk k+1
+    // is requested (tcgen05.ld) before chunk k is processed.
     const int ew = warp - 2;
     const int quarter = warp & 3;
     const int half = ew >> 2;
@@ -210,14 +217,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t ebase = smem_u32(sEpi) + static_cast<uint32_t>(ew) * Cfg::EPI_WARP;
     const uint32_t bias_w = smem_u32(sBias) + 512u * ew;  // this warp's bias slice
     const uint32_t rb0 = smem_u32(&rbar[2 * ew]);
-    const bool has_bias = e.kind == 0 && e.bias != nullptr;
-    const bool has_resid = e.kind == 0 && e.resid != nullptr;
-    const bool f32_out = e.out_f32 != nullptr;
-    const bool act_out = e.out_act != nullptr;
-    const bool act_only = act_out && !f32_out;
-    // 16-bit tile of a chunk: rotates through the 8 KB as four 2 KB tiles when it is the only output, else the extra tile
+    const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    constexpr bool RESID = EM == EM_RESID;
+    constexpr bool F32_OUT = EM == EM_RESID || EM == EM_F32;
+    constexpr bool ACT_ONLY = EM == EM_QKV || EM == EM_ACT;
+    const bool has_bias = EM != EM_QKV && e.bias != nullptr;
+    const bool do_gelu = EM == EM_ACT || (EM == EM_F32 && e.gelu);
+    const bool act_copy = RESID && e.out_act != nullptr;  // 16-bit copy next to the fp32 result (frontend block 2 -> conv)
     const uint32_t sw64 = static_cast<uint32_t>((lane >> 1) & 3) << 4;
     const uint32_t sw128 = static_cast<uint32_t>(lane & 7) << 4;
+    const uint32_t frow = static_cast<uint32_t>(lane) * 128u, hrow = static_cast<uint32_t>(lane) * 64u;
     uint32_t rphase = 0;   // bit b: parity of residual barrier b
     int ck = 0;            // running chunk counter of this warp (staging tile rotation continues across tiles)
     int acc = 0;
@@ -227,7 +236,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int p_out = mt / t_tiles;
       const int trow0 = (mt - p_out * t_tiles) * TG_BM + quarter * 32;  // first row of this warp inside the plane
       const int t = trow0 + lane;
-      const int64_t m = static_cast<int64_t>(p_out) * g.L + t;
       const int col_w = nt * BN + c_begin * 32;  // first column of this warp
       if (has_bias) {  // bias of the warp's columns -> shared memory (broadcast reads in the chunk loop)
         if (4 * lane < nch * 32) {
@@ -236,8 +244,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
       }
-      float cs[16], sn[16];  // kind 1: cos | sin of this row's position, reused by every q / k head of the row
-      if (e.kind == 1) {
+      float cs[EM == EM_QKV ? 16 : 1], sn[EM == EM_QKV ? 16 : 1];  // cos | sin of this row's position (every q / k head)
+      if constexpr (EM == EM_QKV) {
         const int tt = t < g.L ? t : 0;
         const int pos = e.posmode == 0 ? tt : static_cast<int>(p_out % e.F);
         const float4* c4 = reinterpret_cast<const float4*>(e.rope_cos + pos * 16);
@@ -249,7 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           sn[4 * i] = b.x; sn[4 * i + 1] = b.y; sn[4 * i + 2] = b.z; sn[4 * i + 3] = b.w;
         }
       }
-      if (has_resid) {  // residual tile of the first chunk (its staging tile was released two chunks ago)
+      if constexpr (RESID) {  // residual tile of the first chunk (its staging tile was released two chunks ago)
         const int b = ck & 1;
         if (lane == 0) {
           bulk_wait_read<1>();
@@ -260,89 +268,115 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int k = 0; k < nch; ++k, ++ck) {
-        const int n0 = col_w + k * 32;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + (c_begin + k) * 32, r);
-        const int b = ck & 1;
-        const uint32_t fbuf = ebase + 4096 * b;                                  // fp32 staging tile of this chunk
-        const uint32_t hbuf = act_only ? ebase + 2048 * (ck & 3) : ebase + 8192;  // 16-bit staging tile
-        if (lane == 0) {
-          // staging tiles about to be (re)written must have been read by their last TMA store
-          if (has_resid) {
-            // next chunk's residual tile goes into the other fp32 tile, last stored one chunk ago; a 16-bit copy
-            // (single extra tile) was last stored one chunk ago as well
-            if (k + 1 < nch || (act_out && !act_only)) bulk_wait_read<0>();
-            if (k + 1 < nch) {
-              mbar_expect_tx_a(rb0 + 8 * (b ^ 1), 4096);
-              tma_load_3d_a(ebase + 4096 * (b ^ 1), &tmResid, rb0 + 8 * (b ^ 1), n0 + 32, trow0, p_out);
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32b_x32(tm_lane + acc * BN + c_begin * 32, ra);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < SPLIT; ++k) {
+        if (k < nch) {
+          uint32_t (&r)[32] = (k & 1) ? rb : ra;
+          uint32_t (&rn)[32] = (k & 1) ? ra : rb;
+          if (k + 1 < nch) tmem_ld_32x32b_x32(tm_lane + acc * BN + (c_begin + k + 1) * 32, rn);  // in flight during chunk k
+          const int n0 = col_w + k * 32;
+          const int b = ck & 1;
+          const uint32_t fbuf = ebase + 4096 * b;                                   // fp32 staging tile of this chunk
+          const uint32_t hbuf = ACT_ONLY ? ebase + 2048 * (ck & 3) : ebase + 8192;  // 16-bit staging tile
+          if (lane == 0) {  // staging tiles about to be (re)written must have been read by their last TMA store
+            if constexpr (RESID) {
+              // next chunk's residual tile goes into the other fp32 tile, last stored one chunk ago; the 16-bit copy
+              // (single extra tile) was last stored one chunk ago as well
+              if (k + 1 < nch || act_copy) bulk_wait_read<0>();
+              if (k + 1 < nch) {
+                mbar_expect_tx_a(rb0 + 8 * (b ^ 1), 4096);
+                tma_load_3d_a(ebase + 4096 * (b ^ 1), &tmResid, rb0 + 8 * (b ^ 1), n0 + 32, trow0, p_out);
+              }
+            } else if constexpr (ACT_ONLY) {
+              bulk_wait_read<3>();
+            } else {
+              bulk_wait_read<1>();
             }
-          } else if (act_only) {
-            bulk_wait_read<3>();
+          }
+          __syncwarp();
+          uint64_t v[16];  // 32 accumulator columns as fp32 pairs
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = pack_f32x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+          if constexpr (EM == EM_QKV) {
+            // RoPE on interleaved pairs (rotary_embedding_torch semantics, roformer.py:121-123) + q scaling
+            const int which = n0 / e.C;  // 0 q, 1 k, 2 v: a 32-column chunk is one head of one of them
+            if (which < 2) {
+              const float sc = which == 0 ? e.qscale : 1.0f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float x0, x1;
+                unpack_f32x2(v[i], x0, x1);
+                const float co = cs[i] * sc, si = sn[i] * sc;
+                v[i] = pack_f32x2(fmaf(-x1, si, x0 * co), fmaf(x0, si, x1 * co));
+              }
+            }
           } else {
-            bulk_wait_read<Cfg::EPI_H16_EXTRA ? 0 : 1>();
-          }
-        }
-        __syncwarp();
-        tmem_ld_wait();
-        float v[32];
+            if (has_bias) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (e.kind == 0) {
-          if (has_bias) {
+              for (int i = 0; i < 8; ++i) {
+                const float4 q = ld_shared_v4_f32(bias_w + static_cast<uint32_t>(k * 32 + 4 * i) * 4u);
+                v[2 * i] = add_f32x2(v[2 * i], pack_f32x2(q.x, q.y));
+                v[2 * i + 1] = add_f32x2(v[2 * i + 1], pack_f32x2(q.z, q.w));
+              }
+            }
+            if (do_gelu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = gelu_tanh_f32x2(v[i]);
+            }
+            if constexpr (RESID) {
+              mbar_wait_a(rb0 + 8 * b, (rphase >> b) & 1u);
+              rphase ^= 1u << b;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 q = ld_shared_v4_f32(fbuf + frow + ((static_cast<uint32_t>(i) << 4) ^ sw128));
+                v[2 * i] = add_f32x2(v[2 * i], pack_f32x2(q.x, q.y));
+                v[2 * i + 1] = add_f32x2(v[2 * i + 1], pack_f32x2(q.z, q.w));
+              }
+            }
+          }
+          if constexpr (F32_OUT) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 q = ld_shared_v4_f32(bias_w + static_cast<uint32_t>(k * 32 + 4 * i) * 4u);
-              v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+              float a0, a1, a2, a3;
+              unpack_f32x2(v[2 * i], a0, a1);
+              unpack_f32x2(v[2 * i + 1], a2, a3);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(fbuf + frow + ((static_cast<uint32_t>(i) << 4) ^ sw128)),
+                           "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
             }
           }
-          if (e.gelu) {
+          const bool h16_tile = ACT_ONLY || (act_copy && Cfg::EPI_H16_EXTRA != 0);
+          if (h16_tile) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_fast(v[i]);
-          }
-          if (has_resid) {
-            mbar_wait_a(rb0 + 8 * b, (rphase >> b) & 1u);
-            rphase ^= 1u << b;
+            for (int i = 0; i < 4; ++i) {
+              uint32_t w[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 q = ld_shared_v4_f32(fbuf + lane * 128 + ((static_cast<uint32_t>(i) << 4) ^ sw128));
-              v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+              for (int j = 0; j < 4; ++j) {
+                float a0, a1;
+                unpack_f32x2(v[4 * i + j], a0, a1);
+                w[j] = pack_h16x2(a0, a1);
+              }
+              st_shared_v4(hbuf + hrow + ((static_cast<uint32_t>(i) << 4) ^ sw64), w[0], w[1], w[2], w[3]);
+            }
+          } else if (act_copy) {  // no room for a third staging tile (BN = 256): direct row store of the 16-bit copy
+            if (t < g.L) {
+              float f[32];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) unpack_f32x2(v[i], f[2 * i], f[2 * i + 1]);
+              store_act<h16, 32>(reinterpret_cast<h16*>(e.out_act) + (static_cast<int64_t>(p_out) * g.L + t) * e.ldo_act + n0, f);
             }
           }
-        } else {  // kind 1: RoPE on interleaved pairs (rotary_embedding_torch semantics, roformer.py:121-123) + q scaling
-          const int which = n0 / e.C;  // 0 q, 1 k, 2 v: a 32-column chunk is one head of one of them
-          if (which < 2) {
-            const float sc = which == 0 ? e.qscale : 1.0f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float x0 = v[2 * i], x1 = v[2 * i + 1];
-              v[2 * i] = (x0 * cs[i] - x1 * sn[i]) * sc;
-              v[2 * i + 1] = (x1 * cs[i] + x0 * sn[i]) * sc;
-            }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (F32_OUT) tma_store_3d(&tmOutF32, fbuf, n0, trow0, p_out);
+            if (h16_tile) tma_store_3d(&tmOutAct, hbuf, n0, trow0, p_out);
+            bulk_commit();
           }
-        }
-        if (f32_out) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(fbuf + lane * 128 + ((static_cast<uint32_t>(i) << 4) ^ sw128)),
-                         "f"(v[4 * i]), "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
-        }
-        if (act_out && (act_only || Cfg::EPI_H16_EXTRA)) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            st_shared_v4(hbuf + lane * 64 + ((static_cast<uint32_t>(i) << 4) ^ sw64), pack_h16x2(v[8 * i], v[8 * i + 1]),
-                         pack_h16x2(v[8 * i + 2], v[8 * i + 3]), pack_h16x2(v[8 * i + 4], v[8 * i + 5]),
-                         pack_h16x2(v[8 * i + 6], v[8 * i + 7]));
-        } else if (act_out) {  // fp32 + 16-bit outputs without room for a third staging tile: direct row store
-          if (t < g.L) store_act<h16, 32>(reinterpret_cast<h16*>(e.out_act) + m * e.ldo_act + n0, v);
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (f32_out) tma_store_3d(&tmOutF32, fbuf, n0, trow0, p_out);
-          if (act_out && (act_only || Cfg::EPI_H16_EXTRA)) tma_store_3d(&tmOutAct, hbuf, n0, trow0, p_out);
-          bulk_commit();
+          ++ck;
+          if (k + 1 < nch) tmem_ld_wait();
         }
       }
       tc_fence_before();
@@ -461,17 +495,17 @@ static int pick_bn(int N) {
   return 0;
 }
 
-template <int BN, int BK, bool TE>
+template <int BN, int BK, int EM>
 static int gemm_tc_launch(const TcGemmPlan* p, const EpiParams& e, cudaStream_t st) {
-  using Cfg = TgCfg<BN, BK, TE>;
+  using Cfg = TgCfg<BN, BK, EM != EM_DIRECT>;
   static_assert(Cfg::STAGES >= 2, "pipeline too shallow");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t r = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t r = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (r != cudaSuccess) return -1;
     attr_set = true;
   }
-  gemm_tc_kernel<BN, BK, TE><<<p->grid, TG_THREADS, Cfg::SMEM, st>>>(p->tmA, p->tmW, p->tmOutAct, p->tmOutF32, p->tmResid, p->g,
+  gemm_tc_kernel<BN, BK, EM><<<p->grid, TG_THREADS, Cfg::SMEM, st>>>(p->tmA, p->tmW, p->tmOutAct, p->tmOutF32, p->tmResid, p->g,
                                                                        e, p->num_tiles, p->t_tiles, p->n_tiles, p->m_tiles);
   return 0;
 }
@@ -548,13 +582,25 @@ int launch_gemm_tc(const TcGemmPlan* p, const EpiParams& e, cudaStream_t st) {
   const bool te = te_enabled && p->BN >= 128 && p->BK == 64 && e.kind != 2 && (e.out_act || e.out_f32) &&
                   (e.kind == 0 || e.C % 32 == 0) && prepare_tma_epilogue(p, e);
   if (te) {
-    if (p->BN == 256) return gemm_tc_launch<256, 64, true>(p, e, st);
-    if (p->BN == 192) return gemm_tc_launch<192, 64, true>(p, e, st);
-    if (p->BN == 128) return gemm_tc_launch<128, 64, true>(p, e, st);
+    // which specialised epilogue covers this call site (anything else takes the direct epilogue)
+    int em = EM_DIRECT;
+    if (e.kind == 1 && e.out_act && !e.out_f32) em = EM_QKV;
+    else if (e.kind == 0 && e.out_act && !e.out_f32 && !e.resid && e.bias && e.gelu) em = EM_ACT;
+    else if (e.kind == 0 && e.resid && e.out_f32 && !e.gelu) em = EM_RESID;
+    else if (e.kind == 0 && !e.resid && e.out_f32 && !e.out_act && e.bias) em = EM_F32;
+#define BT_TE_CASE(bn) \
+    if (p->BN == bn) { \
+      if (em == EM_QKV) return gemm_tc_launch<bn, 64, EM_QKV>(p, e, st); \
+      if (em == EM_ACT) return gemm_tc_launch<bn, 64, EM_ACT>(p, e, st); \
+      if (em == EM_RESID) return gemm_tc_launch<bn, 64, EM_RESID>(p, e, st); \
+      if (em == EM_F32) return gemm_tc_launch<bn, 64, EM_F32>(p, e, st); \
+    }
+    BT_TE_CASE(256) BT_TE_CASE(192) BT_TE_CASE(128)
+#undef BT_TE_CASE
   }
   if (!p->epi_ok) { p->tmOutAct = p->tmA; p->tmOutF32 = p->tmA; p->tmResid = p->tmA; }
 #define BT_TG_CASE(bn, bk) \
-  if (p->BN == bn && p->BK == bk) return gemm_tc_launch<bn, bk, false>(p, e, st);
+  if (p->BN == bn && p->BK == bk) return gemm_tc_launch<bn, bk, EM_DIRECT>(p, e, st);
   BT_TG_CASE(256, 64) BT_TG_CASE(192, 64) BT_TG_CASE(128, 64) BT_TG_CASE(96, 64) BT_TG_CASE(64, 64)
   BT_TG_CASE(32, 64) BT_TG_CASE(128, 32) BT_TG_CASE(96, 32) BT_TG_CASE(64, 32) BT_TG_CASE(32, 32)
 #undef BT_TG_CASE
