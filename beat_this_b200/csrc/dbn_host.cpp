@@ -18,6 +18,36 @@
 
 namespace {
 
+// The two inner loops of the Viterbi recursion, compiled for AVX2 / AVX-512 where the host has them (plain adds,
+// compares and blends: results are identical to the scalar build).
+#if defined(__x86_64__) && defined(__GNUC__)
+#define BT_SIMD_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
+#else
+#define BT_SIMD_CLONES
+#endif
+
+// best[k] = max_f from[f] + log_tempo[f][k], arg[k] = the FIRST f that attains it (f ascending, strict >)
+// [klo[f], khi[f]) = the k with a finite log_tempo[f][k] (the exponential tempo model leaves a band around f)
+BT_SIMD_CLONES void tempo_step(const double* from, const double* log_tempo, int n_int, const int32_t* klo, const int32_t* khi,
+                               double* best, int32_t* arg) {
+  for (int k = 0; k < n_int; ++k) { best[k] = -std::numeric_limits<double>::infinity(); arg[k] = 0; }
+  for (int f = 0; f < n_int; ++f) {
+    const double ff = from[f];
+    const double* lt = log_tempo + static_cast<size_t>(f) * n_int;
+    for (int k = klo[f]; k < khi[f]; ++k) {
+      const double c = ff + lt[k];
+      const bool better = c > best[k];
+      best[k] = better ? c : best[k];
+      arg[k] = better ? f : arg[k];
+    }
+  }
+}
+
+// nv[i] = v[i - 1] + c for i in [lo, hi)
+BT_SIMD_CLONES void shift_add(const double* v, double* nv, int64_t lo, int64_t hi, double c) {
+  for (int64_t i = lo; i < hi; ++i) nv[i] = v[i - 1] + c;
+}
+
 int viterbi(const double* log_dens, int64_t T, int32_t beats, int32_t n_int, const int32_t* intervals,
             const double* log_tempo, const int32_t* pointers, int64_t* path_out, double* logp_out) {
   int64_t per_beat = 0;
@@ -29,26 +59,51 @@ int viterbi(const double* log_dens, int64_t T, int32_t beats, int32_t n_int, con
     last[k] = per_beat - 1;
   }
   const int64_t S = per_beat * beats;
+  // inside one tempo of one beat the density pointer is a run of (down)beat states followed by non-beat states:
+  // nrun[b][k] = length of the leading run that shares the pointer of the first state
+  std::vector<int32_t> nrun(static_cast<size_t>(beats) * n_int);
+  bool runs_ok = true;
+  for (int b = 0; b < beats && runs_ok; ++b)
+    for (int k = 0; k < n_int && runs_ok; ++k) {
+      const int64_t s0 = b * per_beat + first[k];
+      int32_t n = 1;
+      while (n < intervals[k] && pointers[s0 + n] == pointers[s0]) ++n;
+      for (int32_t p = n; p < intervals[k]; ++p) runs_ok = runs_ok && pointers[s0 + p] == 0;
+      nrun[static_cast<size_t>(b) * n_int + k] = n;
+    }
+  std::vector<int32_t> klo(n_int), khi(n_int);
+  for (int f = 0; f < n_int; ++f) {
+    int lo = 0, hi = n_int;
+    while (lo < n_int && std::isinf(log_tempo[static_cast<size_t>(f) * n_int + lo])) ++lo;
+    while (hi > lo && std::isinf(log_tempo[static_cast<size_t>(f) * n_int + hi - 1])) --hi;
+    klo[f] = lo; khi[f] = hi;
+  }
   std::vector<double> v(S, -std::log(static_cast<double>(S))), nv(S);
   std::vector<int16_t> back(static_cast<size_t>(T) * beats * n_int);
-  std::vector<double> from(n_int);
-  const double ninf = -std::numeric_limits<double>::infinity();
+  std::vector<double> from(n_int), best(n_int);
+  std::vector<int32_t> arg(n_int);
   for (int64_t t = 0; t < T; ++t) {
     const double* d = log_dens + 3 * t;
+    // every state that is not the first of its tempo follows its predecessor; most of them are non-beat states:
+    // one vector pass with the non-beat density over the whole state space, then the few (down)beat-run states and
+    // the first state of every tempo are rewritten
+    if (runs_ok) shift_add(v.data(), nv.data(), 1, S, d[0]);
     for (int b = 0; b < beats; ++b) {
       const int64_t base = b * per_beat, prev_base = ((b + beats - 1) % beats) * per_beat;
       for (int k = 0; k < n_int; ++k) from[k] = v[prev_base + last[k]];
-      for (int k = 0; k < n_int; ++k) {  // first position of tempo k: best previous tempo
-        double best = ninf;
-        int arg = 0;
-        for (int f = 0; f < n_int; ++f) {
-          const double c = from[f] + log_tempo[f * n_int + k];
-          if (c > best) { best = c; arg = f; }
-        }
-        back[(static_cast<size_t>(t) * beats + b) * n_int + k] = static_cast<int16_t>(arg);
+      tempo_step(from.data(), log_tempo, n_int, klo.data(), khi.data(), best.data(), arg.data());  // first position of every tempo: best previous tempo
+      int16_t* bk = &back[(static_cast<size_t>(t) * beats + b) * n_int];
+      for (int k = 0; k < n_int; ++k) {
+        bk[k] = static_cast<int16_t>(arg[k]);
         const int64_t s0 = base + first[k];
-        nv[s0] = best + d[pointers[s0]];
-        for (int64_t p = 1; p < intervals[k]; ++p) nv[s0 + p] = v[s0 + p - 1] + d[pointers[s0 + p]];
+        const double db = d[pointers[s0]];
+        nv[s0] = best[k] + db;
+        if (runs_ok) {
+          const int32_t n = nrun[static_cast<size_t>(b) * n_int + k];
+          for (int32_t p = 1; p < n; ++p) nv[s0 + p] = v[s0 + p - 1] + db;
+        } else {
+          for (int64_t p = 1; p < intervals[k]; ++p) nv[s0 + p] = v[s0 + p - 1] + d[pointers[s0 + p]];
+        }
       }
     }
     v.swap(nv);

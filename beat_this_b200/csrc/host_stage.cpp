@@ -68,25 +68,36 @@ inline void mix_float(const T* src, int32_t ch, int64_t lo, int64_t hi, float* d
 }
 
 // integer PCM: value / 2^(bits-1) in float64 (what soundfile / torchaudio hand to load_audio), float64 channel mean
-inline void mix_pcm(const uint8_t* src, int32_t bytes_per_sample, int32_t ch, int64_t lo, int64_t hi, float* dst) {
-  const double scale = bytes_per_sample == 1 ? 1.0 / 128.0 : bytes_per_sample == 2 ? 1.0 / 32768.0
-                       : bytes_per_sample == 3 ? 1.0 / 8388608.0 : 1.0 / 2147483648.0;
-  const int64_t stride = static_cast<int64_t>(bytes_per_sample) * ch;
+template <int BPS>
+inline int32_t pcm_value(const uint8_t* s) {
+  if constexpr (BPS == 1) return static_cast<int32_t>(s[0]) - 128;  // 8-bit WAV is unsigned
+  else if constexpr (BPS == 2) return static_cast<int16_t>(s[0] | (s[1] << 8));
+  else if constexpr (BPS == 3) return (static_cast<int32_t>(s[0] | (s[1] << 8) | (s[2] << 16)) << 8) >> 8;
+  else return static_cast<int32_t>(static_cast<uint32_t>(s[0]) | (static_cast<uint32_t>(s[1]) << 8) |
+                                   (static_cast<uint32_t>(s[2]) << 16) | (static_cast<uint32_t>(s[3]) << 24));
+}
+template <int BPS>
+inline void mix_pcm_t(const uint8_t* src, int32_t ch, int64_t lo, int64_t hi, float* dst) {
+  constexpr double scale = BPS == 1 ? 1.0 / 128.0 : BPS == 2 ? 1.0 / 32768.0 : BPS == 3 ? 1.0 / 8388608.0 : 1.0 / 2147483648.0;
+  if (ch == 1) {  // value * 2^-k is exact in float64 and (for <= 24 bits) in float32: one multiply, one rounding
+    for (int64_t t = lo; t < hi; ++t) dst[t] = static_cast<float>(static_cast<double>(pcm_value<BPS>(src + t * BPS)) * scale);
+    return;
+  }
+  const int64_t stride = static_cast<int64_t>(BPS) * ch;
+  const double n = static_cast<double>(ch);
   for (int64_t t = lo; t < hi; ++t) {
     const uint8_t* f = src + t * stride;
-    double acc = 0.0;
-    for (int32_t c = 0; c < ch; ++c) {
-      const uint8_t* s = f + c * bytes_per_sample;
-      int32_t v;
-      if (bytes_per_sample == 1) v = static_cast<int32_t>(s[0]) - 128;  // 8-bit WAV is unsigned
-      else if (bytes_per_sample == 2) v = static_cast<int16_t>(s[0] | (s[1] << 8));
-      else if (bytes_per_sample == 3) v = (static_cast<int32_t>(s[0] | (s[1] << 8) | (s[2] << 16)) << 8) >> 8;
-      else v = static_cast<int32_t>(static_cast<uint32_t>(s[0]) | (static_cast<uint32_t>(s[1]) << 8) |
-                                    (static_cast<uint32_t>(s[2]) << 16) | (static_cast<uint32_t>(s[3]) << 24));
-      const double x = static_cast<double>(v) * scale;
-      acc = c == 0 ? x : acc + x;
-    }
-    dst[t] = static_cast<float>(ch == 1 ? acc : acc / static_cast<double>(ch));
+    double acc = static_cast<double>(pcm_value<BPS>(f)) * scale;
+    for (int32_t c = 1; c < ch; ++c) acc += static_cast<double>(pcm_value<BPS>(f + c * BPS)) * scale;
+    dst[t] = static_cast<float>(acc / n);
+  }
+}
+inline void mix_pcm(const uint8_t* src, int32_t bytes_per_sample, int32_t ch, int64_t lo, int64_t hi, float* dst) {
+  switch (bytes_per_sample) {
+    case 1: mix_pcm_t<1>(src, ch, lo, hi, dst); break;
+    case 2: mix_pcm_t<2>(src, ch, lo, hi, dst); break;
+    case 3: mix_pcm_t<3>(src, ch, lo, hi, dst); break;
+    default: mix_pcm_t<4>(src, ch, lo, hi, dst); break;
   }
 }
 

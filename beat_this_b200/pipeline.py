@@ -16,6 +16,7 @@ stays one group ahead of the host.
 from __future__ import annotations
 
 import ctypes
+import time
 from collections import deque
 from ctypes import c_void_p
 
@@ -88,6 +89,8 @@ class BeatPipeline:
         self.host_threads = int(host_threads)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        # host seconds spent staging (mono mix / decode into pinned memory), enqueueing and waiting for results
+        self.stats = {"stage_s": 0.0, "enqueue_s": 0.0, "collect_wait_s": 0.0, "groups": 0}
 
     # ---- staging --------------------------------------------------------------------------------
     def _slot(self, n_samples: int):
@@ -155,8 +158,13 @@ class BeatPipeline:
     def submit_signals(self, arrays, sr: int = 22050, want: str = "beats"):
         idx, s = self._slot(sum(a.shape[0] for a in arrays))
         try:
+            t0 = time.perf_counter()
             so = self.stage_signals(arrays, s.host)
+            t1 = time.perf_counter()
             self._enqueue(idx, s, so, int(sr), want)
+            self.stats["stage_s"] += t1 - t0
+            self.stats["enqueue_s"] += time.perf_counter() - t1
+            self.stats["groups"] += 1
         except Exception:
             self.free.append(idx)
             raise
@@ -172,11 +180,16 @@ class BeatPipeline:
             cpaths = (ctypes.c_char_p * n)(*[str(p).encode() for p in paths])
             offs = (ctypes.c_int64 * (n + 1))(*so)
             status = (ctypes.c_int32 * n)()
+            t0 = time.perf_counter()
             code = self.lib.bt_stage_wav_files(cpaths, infos, n, c_void_p(s.host.data_ptr()), offs, self.host_threads, status)
             if code != 0:
                 bad = [str(paths[i]) for i in range(n) if status[i] != 0]
                 raise RuntimeError(f"Could not load audio from {bad}")
+            t1 = time.perf_counter()
             self._enqueue(idx, s, so, int(sr), want)
+            self.stats["stage_s"] += t1 - t0
+            self.stats["enqueue_s"] += time.perf_counter() - t1
+            self.stats["groups"] += 1
         except Exception:
             self.free.append(idx)
             raise
@@ -193,6 +206,7 @@ class BeatPipeline:
         """Oldest group: list of (beat_times, downbeat_times) ["beats"], (beat, down, fo) host arrays
         ["logits_host"] or device tensors ["frames"]."""
         idx, (kind, p) = self.inflight.popleft()
+        t0 = time.perf_counter()
         try:
             if kind == "beats":
                 return p.result()
@@ -205,6 +219,7 @@ class BeatPipeline:
             s.done.synchronize()
             return beat, down, fo
         finally:
+            self.stats["collect_wait_s"] += time.perf_counter() - t0
             self.free.append(idx)
 
     def run(self, n_groups: int, submit):

@@ -310,7 +310,7 @@ def test_config4_audio2beats_dbn_on_host(small0_ckpt, lib_built):
     host DBN (madmom if installed, else beat_this_b200/dbn.py).  The host side must equal running the same tracker
     on the oracle-style activations of OUR logits (postprocessor.py:138-173 arithmetic)."""
     from beat_this_b200 import synthetic
-    from beat_this_b200.inference import Audio2Beats
+    from beat_this_b200.inference import Audio2Beats, Audio2Frames
 
     a2b = Audio2Beats(small0_ckpt, "cuda:0", False, True)
     clips = [synthetic.synth_clip(90 + i, s) for i, s in enumerate((20.0, 8.0))]
