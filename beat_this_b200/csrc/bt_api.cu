@@ -281,9 +281,11 @@ int64_t front_elems(const bt_ctx* c) {
 }
 
 int ensure_ws(bt_ctx* c, int need_chunks) {
-  int want = std::min(c->wave, std::max(need_chunks, 1));
+  // sized once for a full wave (bt_set_wave_chunks; ~46 MB per 1500-frame chunk on the 16-bit path): growing later
+  // would mean cudaFree / cudaMalloc -- device-wide synchronisation -- in the middle of a stream of batches
+  (void)need_chunks;
+  const int want = c->wave;
   if (want <= c->ws_wave) return BT_OK;
-  if (want < c->wave) want = std::min(c->wave, std::max(want, 2 * c->ws_wave));  // amortise growth
   free_ws(c);
   free_plans(c);
   const int64_t G = want;

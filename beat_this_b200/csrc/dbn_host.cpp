@@ -11,6 +11,8 @@
 #include <cmath>
 #include <cstdint>
 #include <limits>
+#include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -27,31 +29,46 @@ namespace {
 #endif
 
 // best[k] = max_f from[f] + log_tempo[f][k], arg[k] = the FIRST f that attains it (f ascending, strict >)
-// [klo[f], khi[f]) = the k with a finite log_tempo[f][k] (the exponential tempo model leaves a band around f)
-BT_SIMD_CLONES void tempo_step(const double* from, const double* log_tempo, int n_int, const int32_t* klo, const int32_t* khi,
-                               double* best, int32_t* arg) {
-  for (int k = 0; k < n_int; ++k) { best[k] = -std::numeric_limits<double>::infinity(); arg[k] = 0; }
+// [klo[f], khi[f]) = the k with a finite log_tempo[f][k] (the exponential tempo model leaves a band around f).
+// The argmax is tracked as a double so that every array in the loop has 8-byte lanes (the compiler vectorises it).
+BT_SIMD_CLONES void tempo_step(const double* __restrict from, const double* __restrict log_tempo, int n_int,
+                               const int32_t* __restrict klo, const int32_t* __restrict khi, double* __restrict best,
+                               double* __restrict argd) {
+  for (int k = 0; k < n_int; ++k) { best[k] = -std::numeric_limits<double>::infinity(); argd[k] = 0.0; }
   for (int f = 0; f < n_int; ++f) {
-    const double ff = from[f];
-    const double* lt = log_tempo + static_cast<size_t>(f) * n_int;
-    for (int k = klo[f]; k < khi[f]; ++k) {
+    const double ff = from[f], fd = static_cast<double>(f);
+    const double* __restrict lt = log_tempo + static_cast<size_t>(f) * n_int;
+    const int lo = klo[f], hi = khi[f];
+    for (int k = lo; k < hi; ++k) {
       const double c = ff + lt[k];
-      const bool better = c > best[k];
-      best[k] = better ? c : best[k];
-      arg[k] = better ? f : arg[k];
+      const double b = best[k];
+      argd[k] = c > b ? fd : argd[k];
+      best[k] = c > b ? c : b;
     }
   }
 }
 
 // nv[i] = v[i - 1] + c for i in [lo, hi)
-BT_SIMD_CLONES void shift_add(const double* v, double* nv, int64_t lo, int64_t hi, double c) {
+BT_SIMD_CLONES void shift_add(const double* __restrict v, double* __restrict nv, int64_t lo, int64_t hi, double c) {
   for (int64_t i = lo; i < hi; ++i) nv[i] = v[i - 1] + c;
 }
 
+// Per-worker buffers, kept between pieces and between calls (grow only): with one short-lived allocation per piece,
+// 64 threads mmap / munmap megabytes concurrently and the kernel's address-space lock plus the TLB shootdowns
+// serialise them (measured: 64 pieces on 128 CPUs took 5x the single-piece time).
+struct Scratch {
+  std::vector<double> v, nv, from, best, dens;
+  std::vector<int16_t> back;
+  std::vector<double> argd;
+  std::vector<int32_t> nrun, klo, khi;
+  std::vector<int64_t> first, last, path, best_path;
+};
+
 int viterbi(const double* log_dens, int64_t T, int32_t beats, int32_t n_int, const int32_t* intervals,
-            const double* log_tempo, const int32_t* pointers, int64_t* path_out, double* logp_out) {
+            const double* log_tempo, const int32_t* pointers, int64_t* path_out, double* logp_out, Scratch& ws) {
   int64_t per_beat = 0;
-  std::vector<int64_t> first(n_int), last(n_int);
+  std::vector<int64_t>&first = ws.first, &last = ws.last;
+  first.resize(n_int); last.resize(n_int);
   for (int k = 0; k < n_int; ++k) {
     if (intervals[k] <= 0) return BT_ERR_ARG;
     first[k] = per_beat;
@@ -61,7 +78,8 @@ int viterbi(const double* log_dens, int64_t T, int32_t beats, int32_t n_int, con
   const int64_t S = per_beat * beats;
   // inside one tempo of one beat the density pointer is a run of (down)beat states followed by non-beat states:
   // nrun[b][k] = length of the leading run that shares the pointer of the first state
-  std::vector<int32_t> nrun(static_cast<size_t>(beats) * n_int);
+  std::vector<int32_t>& nrun = ws.nrun;
+  nrun.resize(static_cast<size_t>(beats) * n_int);
   bool runs_ok = true;
   for (int b = 0; b < beats && runs_ok; ++b)
     for (int k = 0; k < n_int && runs_ok; ++k) {
@@ -71,17 +89,22 @@ int viterbi(const double* log_dens, int64_t T, int32_t beats, int32_t n_int, con
       for (int32_t p = n; p < intervals[k]; ++p) runs_ok = runs_ok && pointers[s0 + p] == 0;
       nrun[static_cast<size_t>(b) * n_int + k] = n;
     }
-  std::vector<int32_t> klo(n_int), khi(n_int);
+  std::vector<int32_t>&klo = ws.klo, &khi = ws.khi;
+  klo.resize(n_int); khi.resize(n_int);
   for (int f = 0; f < n_int; ++f) {
     int lo = 0, hi = n_int;
     while (lo < n_int && std::isinf(log_tempo[static_cast<size_t>(f) * n_int + lo])) ++lo;
     while (hi > lo && std::isinf(log_tempo[static_cast<size_t>(f) * n_int + hi - 1])) --hi;
     klo[f] = lo; khi[f] = hi;
   }
-  std::vector<double> v(S, -std::log(static_cast<double>(S))), nv(S);
-  std::vector<int16_t> back(static_cast<size_t>(T) * beats * n_int);
-  std::vector<double> from(n_int), best(n_int);
-  std::vector<int32_t> arg(n_int);
+  std::vector<double>&v = ws.v, &nv = ws.nv, &from = ws.from, &best = ws.best;
+  v.assign(S, -std::log(static_cast<double>(S)));
+  nv.resize(S);
+  std::vector<int16_t>& back = ws.back;
+  back.resize(static_cast<size_t>(T) * beats * n_int);  // every entry is written before the backtrace reads it
+  from.resize(n_int); best.resize(n_int);
+  std::vector<double>& arg = ws.argd;
+  arg.resize(n_int);
   for (int64_t t = 0; t < T; ++t) {
     const double* d = log_dens + 3 * t;
     // every state that is not the first of its tempo follows its predecessor; most of them are non-beat states:
@@ -188,7 +211,7 @@ struct Tracker {
   bool correct = true;
 
   // beat_this_b200/dbn.py::DBNDownBeatTracker.__call__; returns the number of beats written
-  int64_t track(const double* act_in, int64_t T_in, double* times, int32_t* numbers) const {
+  int64_t track(const double* act_in, int64_t T_in, double* times, int32_t* numbers, Scratch& ws) const {
     int64_t first = 0, T = T_in;
     const double* act = act_in;
     if (threshold > 0) {  // decode between the first and the last frame with an activation above the threshold
@@ -202,19 +225,21 @@ struct Tracker {
     bool any = false;
     for (int64_t t = 0; t < 2 * T && !any; ++t) any = act[t] != 0.0;
     if (!any) return 0;
-    std::vector<double> dens(3 * T);
+    std::vector<double>& dens = ws.dens;
+    dens.resize(3 * T);
     for (int64_t t = 0; t < T; ++t) {
       dens[3 * t] = std::log((1.0 - (act[2 * t] + act[2 * t + 1])) / (observation_lambda - 1.0));
       dens[3 * t + 1] = std::log(act[2 * t]);
       dens[3 * t + 2] = std::log(act[2 * t + 1]);
     }
-    std::vector<int64_t> best_path, path(T);
+    std::vector<int64_t>&best_path = ws.best_path, &path = ws.path;
+    path.resize(T);
     double best_logp = -std::numeric_limits<double>::infinity();
     const BarModel* best = nullptr;
     for (const BarModel& m : models) {
       double logp = 0;
-      viterbi(dens.data(), T, m.beats, m.n_int, m.intervals.data(), m.log_tempo.data(), m.pointers.data(), path.data(), &logp);
-      if (best == nullptr || logp > best_logp) { best_logp = logp; best = &m; best_path = path; }
+      viterbi(dens.data(), T, m.beats, m.n_int, m.intervals.data(), m.log_tempo.data(), m.pointers.data(), path.data(), &logp, ws);
+      if (best == nullptr || logp > best_logp) { best_logp = logp; best = &m; best_path.assign(path.begin(), path.end()); }
     }
     int64_t n = 0;
     auto number_of = [&](int64_t t) { return static_cast<int32_t>(best_path[t] / best->per_beat) + 1; };
@@ -248,7 +273,8 @@ extern "C" int bt_dbn_viterbi(const double* log_dens, int64_t T, int32_t beats, 
                               const double* log_tempo, const int32_t* pointers, int64_t* path_out, double* logp_out) {
   if (!log_dens || !intervals || !log_tempo || !pointers || !path_out || !logp_out || T <= 0 || beats <= 0 || n_int <= 0)
     return BT_ERR_ARG;
-  return viterbi(log_dens, T, beats, n_int, intervals, log_tempo, pointers, path_out, logp_out);
+  Scratch ws;
+  return viterbi(log_dens, T, beats, n_int, intervals, log_tempo, pointers, path_out, logp_out, ws);
 }
 
 extern "C" int bt_dbn_track(const double* activations, const int64_t* frame_offsets, int32_t n_clips,
@@ -266,18 +292,32 @@ extern "C" int bt_dbn_track(const double* activations, const int64_t* frame_offs
     if (beats_per_bar[i] <= 0) return BT_ERR_ARG;
     trk.models[i].build(beats_per_bar[i], 60.0 * fps / max_bpm, 60.0 * fps / min_bpm, num_tempi, transition_lambda, observation_lambda);
   }
-  std::atomic<int32_t> next{0};
-  auto work = [&]() {
-    for (int32_t i = next.fetch_add(1); i < n_clips; i = next.fetch_add(1)) {
-      const int64_t f0 = frame_offsets[i], T = frame_offsets[i + 1] - f0;
-      counts_out[i] = T > 0 ? trk.track(activations + 2 * f0, T, times_out + f0, numbers_out + f0) : 0;
-    }
-  };
   int nt = n_threads > 0 ? n_threads : static_cast<int>(std::thread::hardware_concurrency());
   nt = std::max(1, std::min(nt, static_cast<int>(n_clips)));
+  // borrow nt scratch sets from the process-wide pool (returned below; concurrent calls get their own)
+  static std::mutex pool_mutex;
+  static std::vector<std::unique_ptr<Scratch>> pool_free;
+  std::vector<std::unique_ptr<Scratch>> mine;
+  {
+    std::lock_guard<std::mutex> lk(pool_mutex);
+    while (static_cast<int>(mine.size()) < nt && !pool_free.empty()) { mine.push_back(std::move(pool_free.back())); pool_free.pop_back(); }
+  }
+  while (static_cast<int>(mine.size()) < nt) mine.emplace_back(new Scratch());
+  std::atomic<int32_t> next{0};
+  auto work = [&](int w) {
+    Scratch& ws = *mine[w];
+    for (int32_t i = next.fetch_add(1); i < n_clips; i = next.fetch_add(1)) {
+      const int64_t f0 = frame_offsets[i], T = frame_offsets[i + 1] - f0;
+      counts_out[i] = T > 0 ? trk.track(activations + 2 * f0, T, times_out + f0, numbers_out + f0, ws) : 0;
+    }
+  };
   std::vector<std::thread> pool;
-  for (int i = 1; i < nt; ++i) pool.emplace_back(work);
-  work();
+  for (int i = 1; i < nt; ++i) pool.emplace_back(work, i);
+  work(0);
   for (auto& th : pool) th.join();
+  {
+    std::lock_guard<std::mutex> lk(pool_mutex);
+    for (auto& m : mine) pool_free.push_back(std::move(m));
+  }
   return BT_OK;
 }

@@ -159,31 +159,39 @@ class DBNDownBeatTracker:
     def batch(self, activations_list, n_threads: int = 0):
         """Many pieces at once on the C++ tracker of the shared library (bt_dbn_track: model construction, Viterbi
         and peak correction in C++, one host thread per piece); `track_numpy` is its numpy twin."""
-        lib = _native()
-        if lib is None:
+        if _native() is None:
             return [self.track_numpy(a) for a in activations_list]
         acts = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1, 2) for a in activations_list]
         fo = np.zeros(len(acts) + 1, dtype=np.int64)
         for i, a in enumerate(acts):
             fo[i + 1] = fo[i] + len(a)
         cat = np.concatenate(acts) if acts else np.zeros((0, 2))
-        cat = np.ascontiguousarray(cat)
+        return self.batch_cat(cat, fo, n_threads)
+
+    def batch_cat(self, activations: np.ndarray, frame_offsets, n_threads: int = 0):
+        """Same, for pieces that already sit back to back in one [total_frames, 2] float64 array."""
+        lib = _native()
+        fo = np.ascontiguousarray(frame_offsets, dtype=np.int64)
+        n = len(fo) - 1
+        if lib is None:
+            return [self.track_numpy(activations[fo[i] : fo[i + 1]]) for i in range(n)]
+        cat = np.ascontiguousarray(activations, dtype=np.float64).reshape(-1, 2)
         total = max(int(fo[-1]), 1)
         times = np.empty(total, dtype=np.float64)
         numbers = np.empty(total, dtype=np.int32)
-        counts = np.zeros(max(len(acts), 1), dtype=np.int64)
+        counts = np.zeros(max(n, 1), dtype=np.int64)
         bpb = np.asarray(self.params["beats_per_bar"], dtype=np.int32)
         p = self.params
-        code = lib.bt_dbn_track(cat.ctypes.data, fo.ctypes.data, len(acts), bpb.ctypes.data, len(bpb), p["min_bpm"], p["max_bpm"],
+        code = lib.bt_dbn_track(cat.ctypes.data, fo.ctypes.data, n, bpb.ctypes.data, len(bpb), p["min_bpm"], p["max_bpm"],
                                 p["num_tempi"], p["transition_lambda"], p["observation_lambda"], float(self.threshold or 0.0),
                                 int(bool(self.correct)), self.fps, int(n_threads), times.ctypes.data, numbers.ctypes.data,
                                 counts.ctypes.data)
         if code != 0:
             raise RuntimeError(f"bt_dbn_track failed ({code})")
         out = []
-        for i in range(len(acts)):
-            a, n = int(fo[i]), int(counts[i])
-            out.append(np.vstack((times[a : a + n], numbers[a : a + n].astype(np.float64))).T if n else np.empty((0, 2)))
+        for i in range(n):
+            a, k = int(fo[i]), int(counts[i])
+            out.append(np.stack((times[a : a + k], numbers[a : a + k].astype(np.float64)), axis=1) if k else np.empty((0, 2)))
         return out
 
     def track_numpy(self, activations):

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from .engine import Engine
-from .pipeline import BeatPipeline, as_signal_array, plan_groups
+from .pipeline import BeatPipeline, as_signal_array, chunk_cost, plan_groups
 from .postprocessor import Postprocessor
 from .preprocessing import LogMelSpect, load_audio
 from .utils import replace_state_dict_key, save_beat_tsv
@@ -27,9 +27,10 @@ from .weights import filter_hparams, pack_parameters
 
 CHECKPOINT_URL = "https://cloud.cp.jku.at/public.php/dav/files/7ik4RrBKTS273gp"
 
-# one group = one pass of every kernel: 64 clips of 30 s (128 chunks of 1500 frames) by default
-GROUP_CLIPS = 64
-GROUP_SAMPLES = 64 * 30 * 22050
+# one group = one pass of every kernel over up to GROUP_CHUNKS model passes (chunks of 1500 frames): 64 clips of 30 s
+# (two chunks each, inference.py:119-125), one full wave of the C library
+GROUP_CHUNKS = 128
+GROUP_CLIPS = 256
 
 
 def _checkpoint_source(name) -> tuple[str, str | None]:
@@ -290,7 +291,7 @@ class Audio2Frames(Spect2Frames):
     def _run_groups(self, arrays, sr, want):
         """Generator over groups: (first index, last index + 1, pipeline result)."""
         pipe = self.pipeline
-        groups = plan_groups([a.shape[0] for a in arrays], GROUP_SAMPLES * max(1, int(sr)) // 22050, GROUP_CLIPS)
+        groups = plan_groups([chunk_cost(a.shape[0], sr) for a in arrays], GROUP_CHUNKS, GROUP_CLIPS)
         try:
             results = pipe.run(len(groups), lambda g: pipe.submit_signals(arrays[groups[g][0] : groups[g][1]], sr, want))
             for (lo, hi), res in zip(groups, results):
@@ -331,8 +332,14 @@ class Audio2Beats(Audio2Frames):
         """pipeline result of one group -> list of (beat_times, downbeat_times)."""
         if self.frames2beats.type == "minimal":
             return res
+        import time
+
         beat_h, down_h, fo = res
-        return self.frames2beats.batch_host(beat_h, down_h, fo)
+        t0 = time.perf_counter()
+        out = self.frames2beats.batch_host(beat_h, down_h, fo)
+        st = self.pipeline.stats
+        st["post_s"] = st.get("post_s", 0.0) + time.perf_counter() - t0
+        return out
 
     @property
     def _want_beats(self):
@@ -343,8 +350,18 @@ class Audio2Beats(Audio2Frames):
         Viterbi of group g runs while the GPU works on group g+1."""
         arrays, sr = self._prepare(signals, sr)
         out = [None] * len(arrays)
-        for lo, hi, res in self._run_groups(arrays, sr, self._want_beats):
-            out[lo:hi] = self._finish(res)
+        if self.frames2beats.type == "minimal":
+            for lo, hi, res in self._run_groups(arrays, sr, "beats"):
+                out[lo:hi] = res
+            return out
+        # DBN: the host Viterbi of a group runs on a worker thread (numpy and the C++ tracker release the GIL), so the
+        # calling thread is free to stage and enqueue the next groups
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=1) as post:
+            pending = [(lo, hi, post.submit(self._finish, res)) for lo, hi, res in self._run_groups(arrays, sr, "logits_host")]
+            for lo, hi, fut in pending:
+                out[lo:hi] = fut.result()
         return out
 
 
@@ -386,7 +403,7 @@ class File2Beats(Audio2Beats):
         want = self._want_beats
         for sr in sorted({infos[i].sample_rate for i in range(len(paths)) if is_wav[i]}):
             idx = [i for i in range(len(paths)) if is_wav[i] and infos[i].sample_rate == sr]
-            groups = plan_groups([infos[i].frames for i in idx], GROUP_SAMPLES * max(1, sr) // 22050, GROUP_CLIPS)
+            groups = plan_groups([chunk_cost(infos[i].frames, sr) for i in idx], GROUP_CHUNKS, GROUP_CLIPS)
 
             def submit(g, idx=idx, groups=groups, sr=sr):
                 sel = idx[groups[g][0] : groups[g][1]]

@@ -42,18 +42,24 @@ def as_signal_array(signal) -> np.ndarray:
     return np.ascontiguousarray(a)
 
 
-def plan_groups(lengths, max_samples: int, max_clips: int):
-    """Consecutive clips -> groups of at most `max_clips` clips / `max_samples` samples (a clip longer than the limit
-    is a group of its own).  Returns a list of (first, last+1) index pairs."""
+def plan_groups(costs, max_cost: int, max_clips: int):
+    """Consecutive clips -> groups of at most `max_clips` clips / `max_cost` total cost (a clip above the limit is a
+    group of its own).  Returns a list of (first, last+1) index pairs."""
     groups, lo, acc = [], 0, 0
-    for i, n in enumerate(lengths):
-        if i > lo and (acc + n > max_samples or i - lo >= max_clips):
+    for i, n in enumerate(costs):
+        if i > lo and (acc + n > max_cost or i - lo >= max_clips):
             groups.append((lo, i))
             lo, acc = i, 0
         acc += int(n)
-    if lo < len(lengths):
-        groups.append((lo, len(lengths)))
+    if lo < len(costs):
+        groups.append((lo, len(costs)))
     return groups
+
+
+def chunk_cost(n_samples: int, sr: int = 22050) -> int:
+    """1500-frame model passes a clip of n_samples at `sr` Hz needs: ceil(frames / 1488) (split_piece, inference.py:119-125)."""
+    frames = 1 + (int(n_samples) * 22050 // max(1, int(sr))) // 441
+    return max(1, -(-frames // 1488))
 
 
 class _Slot:
@@ -64,6 +70,8 @@ class _Slot:
         self.peak = {}        # reusable buffers of Engine.peakpick_async
         self.logits_h = None  # pinned logits (DBN path)
         self.done = None
+        self.t0 = None        # events around the group's kernels (stats: GPU busy time)
+        self.t1 = None
 
 
 class BeatPipeline:
@@ -90,7 +98,7 @@ class BeatPipeline:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         # host seconds spent staging (mono mix / decode into pinned memory), enqueueing and waiting for results
-        self.stats = {"stage_s": 0.0, "enqueue_s": 0.0, "collect_wait_s": 0.0, "groups": 0}
+        self.stats = {"stage_s": 0.0, "enqueue_s": 0.0, "collect_wait_s": 0.0, "gpu_busy_s": 0.0, "groups": 0}
 
     # ---- staging --------------------------------------------------------------------------------
     def _slot(self, n_samples: int):
@@ -129,8 +137,11 @@ class BeatPipeline:
             s.copied.record(self.copy_stream)
         self.h2d_bytes += n * 4
         eng = self.engine
+        if s.t0 is None:
+            s.t0, s.t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(s.copied)
+            s.t0.record(self.compute_stream)
             audio, offs = s.dev[:n], so
             if sr != 22050:
                 audio, offs = eng.resample_cat(audio, so, sr)
@@ -153,6 +164,7 @@ class BeatPipeline:
                 s.done = torch.cuda.Event()
                 s.done.record(self.compute_stream)
                 payload = ("frames", (s, beat, down, fo))
+            s.t1.record(self.compute_stream)
         self.inflight.append((idx, payload))
 
     def submit_signals(self, arrays, sr: int = 22050, want: str = "beats"):
@@ -220,6 +232,11 @@ class BeatPipeline:
             return beat, down, fo
         finally:
             self.stats["collect_wait_s"] += time.perf_counter() - t0
+            try:
+                self.slots[idx].t1.synchronize()
+                self.stats["gpu_busy_s"] += self.slots[idx].t0.elapsed_time(self.slots[idx].t1) / 1000.0
+            except Exception:
+                pass
             self.free.append(idx)
 
     def run(self, n_groups: int, submit):

@@ -85,22 +85,26 @@ class Postprocessor:
         list of (beat_times, downbeat_times)."""
         assert self.type == "dbn"
         eps = 1e-5
-        # beat.double().sigmoid() with the reference's own torch op (postprocessor.py:139-140)
-        bp = torch.from_numpy(np.ascontiguousarray(beat_logits)).double().sigmoid().numpy()
-        dp = torch.from_numpy(np.ascontiguousarray(downbeat_logits)).double().sigmoid().numpy()
+        # beat.double().sigmoid() with the reference's own torch op (postprocessor.py:139-140) -- on ONE thread: a
+        # 100 k element op gains nothing from torch's intra-op pool, and waking a 128-thread pool costs tens of ms
+        nthr = torch.get_num_threads()
+        torch.set_num_threads(1)
+        try:
+            bp = torch.from_numpy(np.ascontiguousarray(beat_logits)).double().sigmoid().numpy()
+            dp = torch.from_numpy(np.ascontiguousarray(downbeat_logits)).double().sigmoid().numpy()
+        finally:
+            torch.set_num_threads(nthr)
         bp = bp * (1 - eps) + eps / 2
         dp = dp * (1 - eps) + eps / 2
 
-        def activation(i):  # the artificial multiclass prediction of postprocessor.py:159-167
-            b = bp[frame_offsets[i] : frame_offsets[i + 1]]
-            d = dp[frame_offsets[i] : frame_offsets[i + 1]]
-            return np.vstack((np.maximum(b - d, eps / 2), d)).T
+        # the artificial multiclass prediction of postprocessor.py:159-167, for all pieces at once: [total, 2]
+        act = np.stack((np.maximum(bp - dp, eps / 2), dp), axis=1)
 
         def split(out):
             return out[:, 0], out[out[:, 1] == 1][:, 0]
 
         n = len(frame_offsets) - 1
-        if hasattr(self.dbn, "batch"):  # native tracker: all pieces in one multi-threaded C++ call
-            return [split(o) for o in self.dbn.batch([activation(i) for i in range(n)])]
+        if hasattr(self.dbn, "batch_cat"):  # native tracker: all pieces in one multi-threaded C++ call
+            return [split(o) for o in self.dbn.batch_cat(act, frame_offsets)]
         with ThreadPoolExecutor() as ex:  # madmom: one piece per thread, as in the reference
-            return list(ex.map(lambda i: split(self.dbn(activation(i))), range(n)))
+            return list(ex.map(lambda i: split(self.dbn(act[frame_offsets[i] : frame_offsets[i + 1]])), range(n)))

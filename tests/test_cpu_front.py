@@ -167,3 +167,7 @@ def test_plan_groups():
     assert plan_groups([100, 1, 1], 25, 64) == [(0, 1), (1, 3)]
     assert plan_groups([1] * 10, 1000, 4) == [(0, 4), (4, 8), (8, 10)]
     assert plan_groups([], 10, 4) == []
+    from beat_this_b200.pipeline import chunk_cost
+
+    assert [chunk_cost(n) for n in (22050 * 5, 656082, 656083 + 441, 661500, 22050 * 300)] == [1, 1, 2, 2, 11]
+    assert chunk_cost(44100 * 30, 44100) == 2

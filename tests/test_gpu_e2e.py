@@ -212,7 +212,7 @@ def test_grouped_pipeline_equals_single_calls(small0_ckpt, lib_built, monkeypatc
     clips = [c if i % 3 else c.astype(np.float32) for i, c in enumerate(base)]
     clips[4] = np.stack([clips[4], 0.5 * clips[4][::-1]], axis=1)  # one stereo clip
     single = [a2b(c, 22050) for c in clips]
-    monkeypatch.setattr(I, "GROUP_CLIPS", 2)
+    monkeypatch.setattr(I, "GROUP_CHUNKS", 2)
     grouped = a2b.batch(clips, 22050)
     frames_g = I.Audio2Frames.batch(a2b, clips, 22050)
     for c, (b, d), (gb, gd), (fb, fd) in zip(clips, single, grouped, frames_g):
