@@ -77,6 +77,10 @@ class _Slot:
 class BeatPipeline:
     """Ring of `depth` slots; `submit_*` enqueues one group, `collect` returns the oldest group's result."""
 
+    # staging slots are sized once for a full group (128 chunks = 128 * 1488 frames of 441 samples, 336 MB of fp32):
+    # page-locking hundreds of MB takes ~0.1 s, which must not recur while batches stream through
+    SLOT_SAMPLES = 128 * 1488 * 441 + 6 * 441
+
     def __init__(self, engine, depth: int = 3, host_threads: int | None = None):
         self.engine = engine
         self.lib = engine.lib
@@ -107,7 +111,7 @@ class BeatPipeline:
         idx = self.free.popleft()
         s = self.slots[idx]
         if s.host is None or s.host.numel() < n_samples:
-            cap = max(int(n_samples * 1.25), 1 << 16)
+            cap = max(int(n_samples), self.SLOT_SAMPLES)
             s.host = torch.empty(cap, dtype=torch.float32, pin_memory=True)
             s.dev = torch.empty(cap, dtype=torch.float32, device=self.device)
             s.copied = torch.cuda.Event()

@@ -567,8 +567,7 @@ def run_config(args, rank, world, local):
             x[:: int(SR * 60.0 / g.uniform(60, 180))] += 0.8
             mine.append(x)
         runner = Audio2Frames.from_model(model)
-        runner.batch(mine[:4], SR)
-        runner.batch(mine[-4:], SR)
+        runner.batch(mine[: max(4, len(mine) // 2)], SR)  # warm-up: pinned staging ring (3 slots), plans of common lengths
         barrier()
         t0 = time.perf_counter()
         res = runner.batch(mine, SR)
