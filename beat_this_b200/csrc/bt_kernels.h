@@ -47,12 +47,18 @@ struct EpiParams {
   float qscale;  // multiplied into q after RoPE
 };
 
+struct ChunkSrc;
+
 // ---- fp32 CUDA-core path -------------------------------------------------------------------
 void launch_gemm_simt(const float* A, const float* W, const GemmShape& g, const EpiParams& e,
                       cudaStream_t st);
 // qkv [seqs*L, 3C] fp32 (q,k roped; q NOT pre-scaled) -> out [seqs*L, C] (gated)
+// chunks != nullptr: sequence s belongs to chunk s / seqs_per_chunk and only its first chunks[..].len keys exist
 void launch_attn_time_simt(const float* qkv, const float* gates, float* out, int seqs, int L,
-                           int heads, cudaStream_t st);
+                           int heads, cudaStream_t st, const ChunkSrc* chunks = nullptr, int seqs_per_chunk = 1);
+// rows [len_b, L) of every plane of chunk b <- 0 (the zero padding a k(2,3) convolution sees beyond the end of a
+// chunk that is shorter than the wave's padded length).  buf: [nchunks * F, L, C] of elem_bytes-sized elements.
+void launch_zero_tail(void* buf, int elem_bytes, const ChunkSrc* chunks, int nchunks, int F, int L, int C, cudaStream_t st);
 
 // ---- shared small kernels (templated on activation dtype inside) ---------------------------
 // frequency-direction attention: tokens m = (b*F + f)*L + t, sequences over f.
@@ -70,6 +76,8 @@ struct ChunkSrc {
   int64_t out_base;    // first frame of the clip inside the concatenated outputs
   int32_t write_lo;    // chunk-local frame range [write_lo, write_hi) this chunk owns
   int32_t write_hi;
+  int32_t len;         // frames of this chunk (<= the wave's padded length L): rows [len, L) of its planes are padding
+  int32_t pad_;
 };
 void launch_stem(const float* spect, const ChunkSrc* chunks, int nchunks, int L, const float* bn1_scale,
                  const float* bn1_shift, const float* w, const float* bias, float* out,
@@ -102,7 +110,8 @@ int launch_gemm_tc(const TcGemmPlan* plan, const EpiParams& e, cudaStream_t st);
 struct TcAttnPlan;
 TcAttnPlan* tc_attn_plan_create(const void* qkv_h16, int seqs, int L, int heads, char* err, int errlen);
 void tc_attn_plan_destroy(TcAttnPlan*);
-int launch_attn_time_tc(const TcAttnPlan* plan, const float* gates, void* out_h16, cudaStream_t st);
+int launch_attn_time_tc(const TcAttnPlan* plan, const float* gates, void* out_h16, cudaStream_t st,
+                        const ChunkSrc* chunks = nullptr, int seqs_per_chunk = 1);
 
 // fused RMSNorm + FFN + residual for C in {32, 64} (frontend), x updated in place (+ optional 16-bit copy)
 struct TcFfPlan;

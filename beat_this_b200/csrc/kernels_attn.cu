@@ -34,7 +34,8 @@ __host__ __device__ constexpr uint32_t attn_poly_mask(int pp) {
 template <int PP>  // PP of every 8 score pairs: exp2 on the FMA pipe (packed polynomial); the rest on MUFU
 __global__ void __launch_bounds__(A6_THREADS, 4)
 attn_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                 const float* __restrict__ gates, h16* __restrict__ out, int L, int heads) {
+                 const float* __restrict__ gates, h16* __restrict__ out, int L, int heads,
+                 const ChunkSrc* __restrict__ chunks, int seqs_per_chunk) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = sbase;
@@ -53,7 +54,9 @@ attn_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int h = blockIdx.y;
   const int seq = blockIdx.z;
   const int C = heads * 32;
-  const int nkv = ceil_div(L, A6_BKV);
+  // keys that exist for this sequence: the whole plane, or (waves of chunks of different lengths) its chunk's frames
+  const int Lk = chunks ? chunks[seq / seqs_per_chunk].len : L;
+  const int nkv = ceil_div(Lk, A6_BKV);
   constexpr int MMA_WARP = 4;
   constexpr int NSOFT = 128;
   constexpr uint32_t POLY_MASK = attn_poly_mask(PP);
@@ -149,7 +152,7 @@ attn_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]); }
       }
       if (j == nkv - 1) {
-        const int lim = L - j * A6_BKV;  // keys >= lim are padding
+        const int lim = Lk - j * A6_BKV;  // keys >= lim are padding
 #pragma unroll
         for (int i = 0; i < 64; ++i)
           if (i >= lim) s[i] = -INFINITY;
@@ -264,12 +267,13 @@ TcAttnPlan* tc_attn_plan_create(const void* qkv, int seqs, int L, int heads, cha
 }
 void tc_attn_plan_destroy(TcAttnPlan* p) { delete p; }
 
-int launch_attn_time_tc(const TcAttnPlan* p, const float* gates, void* out, cudaStream_t st) {
+int launch_attn_time_tc(const TcAttnPlan* p, const float* gates, void* out, cudaStream_t st, const ChunkSrc* chunks,
+                        int seqs_per_chunk) {
   dim3 grid(ceil_div(p->L, AT_BQ), p->heads, p->seqs);
   // BT_ATTN_POLY = number of score pairs out of 8 whose exp2 runs on the FMA pipe (default: measured best)
   static const int pp = getenv("BT_ATTN_POLY") ? atoi(getenv("BT_ATTN_POLY")) : A6_DEFAULT_PP;
   h16* o = reinterpret_cast<h16*>(out);
-#define BT_A6_L(P_) attn_tc64_kernel<P_><<<grid, A6_THREADS, A6_SMEM, st>>>(p->tmQK, p->tmKV64, gates, o, p->L, p->heads)
+#define BT_A6_L(P_) attn_tc64_kernel<P_><<<grid, A6_THREADS, A6_SMEM, st>>>(p->tmQK, p->tmKV64, gates, o, p->L, p->heads, chunks, seqs_per_chunk)
   switch (pp) {
     case 0: BT_A6_L(0); break;
     case 1: BT_A6_L(1); break;

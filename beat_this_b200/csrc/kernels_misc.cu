@@ -195,7 +195,7 @@ stem_kernel(const float* __restrict__ spect, const ChunkSrc* __restrict__ chunks
 #pragma unroll
   for (int dt = 0; dt < 3; ++dt) {
     const int tl = t + dt - 1;
-    const bool conv_ok = tl >= 0 && tl < L;
+    const bool conv_ok = tl >= 0 && tl < cs.len;  // zero padding of the convolution at the ends of THIS chunk
     const int64_t fr = static_cast<int64_t>(cs.start) + tl;
     const bool clip_ok = fr >= 0 && fr < cs.T;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -222,6 +222,18 @@ stem_kernel(const float* __restrict__ spect, const ChunkSrc* __restrict__ chunks
     }
     reinterpret_cast<float4*>(op)[c4] = make_float4(r[0], r[1], r[2], r[3]);
   }
+}
+
+__global__ void __launch_bounds__(256)
+zero_tail_kernel(uint4* __restrict__ buf, const ChunkSrc* __restrict__ chunks, int F, int L, int row_vec) {
+  const int plane = blockIdx.x;
+  const int len = chunks[plane / F].len;
+  const int64_t n = static_cast<int64_t>(L - len) * row_vec;  // 16-byte vectors to clear
+  uint4* p = buf + (static_cast<int64_t>(plane) * L + len) * row_vec;
+  for (int64_t i = threadIdx.x; i < n; i += 256) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+void launch_zero_tail(void* buf, int elem_bytes, const ChunkSrc* chunks, int nchunks, int F, int L, int C, cudaStream_t st) {
+  zero_tail_kernel<<<nchunks * F, 256, 0, st>>>(reinterpret_cast<uint4*>(buf), chunks, F, L, C * elem_bytes / 16);
 }
 
 void launch_stem(const float* spect, const ChunkSrc* chunks, int nchunks, int L, const float* bn1_scale,

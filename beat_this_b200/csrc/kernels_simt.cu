@@ -83,7 +83,8 @@ constexpr int SA_BQ = 128, SA_BK = 64;
 
 __global__ void __launch_bounds__(SA_BQ)
 attn_time_simt_kernel(const float* __restrict__ qkv, const float* __restrict__ gates,
-                      float* __restrict__ out, int L, int heads, float scale) {
+                      float* __restrict__ out, int L, int heads, float scale, const ChunkSrc* __restrict__ chunks,
+                      int seqs_per_chunk) {
   __shared__ __align__(16) float Ks[SA_BK][32];
   __shared__ __align__(16) float Vs[SA_BK][32];
   const int C = heads * 32;
@@ -104,12 +105,13 @@ attn_time_simt_kernel(const float* __restrict__ qkv, const float* __restrict__ g
   for (int i = 0; i < 32; ++i) o[i] = 0.f;
   float mx = -INFINITY, l = 0.f;
 
-  for (int k0 = 0; k0 < L; k0 += SA_BK) {
+  const int Lk = chunks ? chunks[seq / seqs_per_chunk].len : L;  // keys that exist (the rest of the plane is padding)
+  for (int k0 = 0; k0 < Lk; k0 += SA_BK) {
     __syncthreads();
     for (int i = threadIdx.x; i < SA_BK * 8; i += SA_BQ) {
       const int r = i / 8, c4 = i % 8;
       float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-      if (k0 + r < L) {
+      if (k0 + r < Lk) {
         const float* rp = base + static_cast<int64_t>(k0 + r) * 3 * C + h * 32;
         kv = reinterpret_cast<const float4*>(rp + C)[c4];
         vv = reinterpret_cast<const float4*>(rp + 2 * C)[c4];
@@ -118,7 +120,7 @@ attn_time_simt_kernel(const float* __restrict__ qkv, const float* __restrict__ g
       reinterpret_cast<float4*>(&Vs[r][0])[c4] = vv;
     }
     __syncthreads();
-    const int kn = min(SA_BK, L - k0);
+    const int kn = min(SA_BK, Lk - k0);
     for (int j0 = 0; j0 < kn; j0 += 8) {
       float s[8];
       float bm = -INFINITY;
@@ -157,9 +159,9 @@ attn_time_simt_kernel(const float* __restrict__ qkv, const float* __restrict__ g
 }
 
 void launch_attn_time_simt(const float* qkv, const float* gates, float* out, int seqs, int L,
-                           int heads, cudaStream_t st) {
+                           int heads, cudaStream_t st, const ChunkSrc* chunks, int seqs_per_chunk) {
   dim3 grid(ceil_div(L, SA_BQ), heads, seqs);
-  attn_time_simt_kernel<<<grid, SA_BQ, 0, st>>>(qkv, gates, out, L, heads, 0.17677669529663687f);
+  attn_time_simt_kernel<<<grid, SA_BQ, 0, st>>>(qkv, gates, out, L, heads, 0.17677669529663687f, chunks, seqs_per_chunk);
 }
 
 }  // namespace bt
