@@ -240,16 +240,20 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
           tmem_ld_32x32b_x32(tmem_base + lane_base + c4 * 32, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {  // 4 chunks of 8 hidden units
+          for (int c = 0; c < 4; ++c) {  // 4 chunks of 8 hidden units, bias + GELU on packed fp32 pairs
             const float4 ba = ld_shared_v4_f32(sB + 4 * (h * 128 + c4 * 32 + 8 * c));
             const float4 bb = ld_shared_v4_f32(sB + 4 * (h * 128 + c4 * 32 + 8 * c + 4));
-            const float bq[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-            float g[8];
+            const uint64_t bq[4] = {pack_f32x2(ba.x, ba.y), pack_f32x2(ba.z, ba.w), pack_f32x2(bb.x, bb.y), pack_f32x2(bb.z, bb.w)};
+            uint32_t w[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) g[i] = gelu_tanh_fast(__uint_as_float(r[8 * c + i]) + bq[i]);
+            for (int i = 0; i < 4; ++i) {
+              const uint64_t g = gelu_tanh_f32x2(add_f32x2(pack_f32x2(__uint_as_float(r[8 * c + 2 * i]), __uint_as_float(r[8 * c + 2 * i + 1])), bq[i]));
+              float g0, g1;
+              unpack_f32x2(g, g0, g1);
+              w[i] = pack_h16x2(g0, g1);
+            }
             const int cc = c4 * 4 + c;  // 16-byte chunk index inside the 128-wide row: atom = cc >> 3
-            st_shared_v4(hrow + (cc >> 3) * 16384 + (((cc & 7) << 4) ^ hsw), pack_h16x2(g[0], g[1]), pack_h16x2(g[2], g[3]),
-                         pack_h16x2(g[4], g[5]), pack_h16x2(g[6], g[7]));
+            st_shared_v4(hrow + (cc >> 3) * 16384 + (((cc & 7) << 4) ^ hsw), w[0], w[1], w[2], w[3]);
           }
         }
         fence_proxy_async_smem();
@@ -355,35 +359,47 @@ template <int C>
 struct QkvCfg {
   static constexpr int A_BYTES = 128 * C * 2;
   static constexpr int W_BYTES = 3 * C * C * 2;
-  static constexpr int SMEM = A_BYTES + W_BYTES + 1024 + 128;
+  // per warp: the fp32 rows of its 32 tokens (TMA-loaded, C/32 boxes of 32 rows x 128 B) + four rotating 32 x 32
+  // 16-bit output tiles (TMA-stored).  Threads never issue ld/st.global for the activations: with one row per lane
+  // every 16-byte access touched 32 different lines and the L1 data pipe, not HBM, bounded the kernel (ncu:
+  // l1tex lsu wavefronts 80-85 %, DRAM 37 %; profiles/r2_notes.md).
+  static constexpr int XW_BYTES = 32 * C * 4;
+  static constexpr int WARP_BYTES = XW_BYTES + 4 * 2048;
+  static constexpr int SMEM = A_BYTES + W_BYTES + 4 * WARP_BYTES + 1024 + 128;
   static constexpr int TCOLS = 3 * C <= 128 ? 128 : 256;
   static constexpr int SWZ = C * 2 < 128 ? C * 2 : 128;
 };
 
 template <int C>
 __global__ void __launch_bounds__(FF_THREADS, (C == 32 ? 3 : 2))
-fused_qkv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ X, const float* __restrict__ wg,
+fused_qkv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                 const __grid_constant__ CUtensorMap tmQ, const float* __restrict__ wg,
                  const float* __restrict__ bg, const float* __restrict__ rope_cos, const float* __restrict__ rope_sin,
-                 h16* __restrict__ qkv, float* __restrict__ gates, int64_t M, int L, int F, int posmode, float qscale) {
+                 float* __restrict__ gates, int64_t M, int L, int F, int posmode, float qscale) {
   using Cfg = QkvCfg<C>;
   constexpr int heads = C / 32;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = sbase;
   const uint32_t sW = sA + Cfg::A_BYTES;
-  const uint32_t bar_w = sW + Cfg::W_BYTES;
+  const uint32_t sWarp = sW + Cfg::W_BYTES;  // A_BYTES and W_BYTES are multiples of 1024
+  const uint32_t bar_w = sWarp + 4 * Cfg::WARP_BYTES;
   const uint32_t bar_a = bar_w + 8;
   const uint32_t bar_d = bar_a + 8;
-  const uint32_t tmem_slot = bar_d + 8;
+  const uint32_t bar_x = bar_d + 8;  // [4] one per token warp
+  const uint32_t tmem_slot = bar_x + 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = static_cast<int>((M + 127) / 128);  // PERSISTENT: tiles blockIdx.x, +gridDim.x, ... (W fetched once)
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmQ);
     auto init = [](uint32_t bar, uint32_t count) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
     };
     init(bar_w, 1); init(bar_a, 128); init(bar_d, 1);
+    for (int i = 0; i < 4; ++i) init(bar_x + 8 * i, 1);
     fence_barrier_init();
   }
   if (warp == 4) {
@@ -409,96 +425,117 @@ fused_qkv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
 #pragma unroll
       for (int k = 0; k < C / 16; ++k)
         umma_h16_p(on, tmem_base, make_kmajor_desc<Cfg::SWZ>(sA + k * 32), make_kmajor_desc<Cfg::SWZ>(sW + k * 32), idesc,
-                    k != 0 ? 1u : 0u);
+                   k != 0 ? 1u : 0u);
       umma_commit_p(on, bar_d);
     }
   } else {
     const int row = warp * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    int it = 0;
-    float4 xn[C / 4];  // next tile's row, requested while this tile is in the MMA / epilogue
-    auto load_x = [&](int tile) {
-      const int64_t mm = static_cast<int64_t>(tile) * 128 + row;
-      const float4* xr = reinterpret_cast<const float4*>(X + (mm < M ? mm : 0) * C);
+    const uint32_t xbuf = sWarp + warp * Cfg::WARP_BYTES;  // [C/32 boxes][32 rows][128 B], SW128
+    const uint32_t qbuf = xbuf + Cfg::XW_BYTES;            // 4 x [32 rows][64 B], SW64
+    const uint32_t xbar = bar_x + 8 * warp;
+    const uint32_t sw128 = static_cast<uint32_t>(lane & 7) << 4, sw64 = static_cast<uint32_t>((lane >> 1) & 3) << 4;
+    auto load_x = [&](int tile) {  // this warp's 32 token rows of `tile` (rows beyond M arrive as zeros)
+      if (lane == 0) {
+        mbar_expect_tx_a(xbar, Cfg::XW_BYTES);
 #pragma unroll
-      for (int i = 0; i < C / 4; ++i) xn[i] = mm < M ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int b = 0; b < C / 32; ++b) tma_load_2d_a(xbuf + b * 4096, &tmX, xbar, b * 32, tile * 128 + warp * 32);
+      }
     };
     if (static_cast<int>(blockIdx.x) < ntiles) load_x(blockIdx.x);
+    int it = 0, ck = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int64_t m = static_cast<int64_t>(tile) * 128 + row;
-    const bool valid = m < M;
-    {
-      float x[C];
-      float ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < C / 4; ++i) {
-        const float4 q = xn[i];
-        x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
-        ss = fmaf(q.x, q.x, ss); ss = fmaf(q.y, q.y, ss); ss = fmaf(q.z, q.z, ss); ss = fmaf(q.w, q.w, ss);
-      }
-      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll
-      for (int i = 0; i < C; ++i) x[i] *= inv;
-      // gates = sigmoid(to_gates(x_normed)) (gamma*sqrt(C) folded into wg)
-#pragma unroll
-      for (int h = 0; h < heads; ++h) {
-        const float4* w4 = reinterpret_cast<const float4*>(wg + h * C);
-        float a = 0.f;
+      const int64_t m = static_cast<int64_t>(tile) * 128 + row;
+      const bool valid = m < M;
+      {
+        float x[C];
+        float ss = 0.f;
+        mbar_wait_a(xbar, it & 1);
 #pragma unroll
         for (int i = 0; i < C / 4; ++i) {
-          const float4 w = __ldg(w4 + i);
-          a = fmaf(x[4 * i], w.x, a); a = fmaf(x[4 * i + 1], w.y, a); a = fmaf(x[4 * i + 2], w.z, a); a = fmaf(x[4 * i + 3], w.w, a);
+          const float4 q = ld_shared_v4_f32(xbuf + (i >> 3) * 4096 + lane * 128 + ((static_cast<uint32_t>(i & 7) << 4) ^ sw128));
+          x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
+          ss = fmaf(q.x, q.x, ss); ss = fmaf(q.y, q.y, ss); ss = fmaf(q.z, q.z, ss); ss = fmaf(q.w, q.w, ss);
         }
-        if (valid) gates[m * heads + h] = sigmoidf_(a + __ldg(bg + h));
+        __syncwarp();  // every lane has its row in registers: the buffer can take the next tile's rows
+        if (tile + static_cast<int>(gridDim.x) < ntiles) load_x(tile + gridDim.x);
+        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+        for (int i = 0; i < C; ++i) x[i] *= inv;
+        // gates = sigmoid(to_gates(x_normed)) (gamma*sqrt(C) folded into wg)
+#pragma unroll
+        for (int h = 0; h < heads; ++h) {
+          const float4* w4 = reinterpret_cast<const float4*>(wg + h * C);
+          float a = 0.f;
+#pragma unroll
+          for (int i = 0; i < C / 4; ++i) {
+            const float4 w = __ldg(w4 + i);
+            a = fmaf(x[4 * i], w.x, a); a = fmaf(x[4 * i + 1], w.y, a); a = fmaf(x[4 * i + 2], w.z, a); a = fmaf(x[4 * i + 3], w.w, a);
+          }
+          if (valid) gates[m * heads + h] = sigmoidf_(a + __ldg(bg + h));
+        }
+        constexpr int RB = C * 2;
+        const uint32_t arow = sA + row * RB;
+        const uint32_t sw = C == 32 ? sw64 : sw128;
+#pragma unroll
+        for (int c = 0; c < C / 8; ++c)
+          st_shared_v4(arow + ((c << 4) ^ sw), pack_h16x2(x[8 * c], x[8 * c + 1]), pack_h16x2(x[8 * c + 2], x[8 * c + 3]),
+                       pack_h16x2(x[8 * c + 4], x[8 * c + 5]), pack_h16x2(x[8 * c + 6], x[8 * c + 7]));
+        fence_proxy_async_smem();
+        tc_fence_before();  // TMEM reads of the previous tile are ordered before the next MMA
+        mbar_arrive_a(bar_a);
       }
-      constexpr int RB = C * 2;
-      const uint32_t arow = sA + row * RB;
-      const uint32_t sw = C == 32 ? (static_cast<uint32_t>((row >> 1) & 3) << 4) : (static_cast<uint32_t>(row & 7) << 4);
+      // RoPE row of this token (interleaved pairs, rotary_embedding_torch semantics)
+      float cs[16], sn[16];
+      {
+        const int pos = valid ? (posmode == 0 ? static_cast<int>(m % L) : static_cast<int>((m / L) % F)) : 0;
+        const float4* c4 = reinterpret_cast<const float4*>(rope_cos + pos * 16);
+        const float4* s4 = reinterpret_cast<const float4*>(rope_sin + pos * 16);
 #pragma unroll
-      for (int c = 0; c < C / 8; ++c)
-        st_shared_v4(arow + ((c << 4) ^ sw), pack_h16x2(x[8 * c], x[8 * c + 1]), pack_h16x2(x[8 * c + 2], x[8 * c + 3]),
-                     pack_h16x2(x[8 * c + 4], x[8 * c + 5]), pack_h16x2(x[8 * c + 6], x[8 * c + 7]));
-      fence_proxy_async_smem();
-      tc_fence_before();  // TMEM reads of the previous tile are ordered before the next MMA
-      mbar_arrive_a(bar_a);
-      if (tile + static_cast<int>(gridDim.x) < ntiles) load_x(tile + gridDim.x);
-    }
-    // RoPE row of this token (interleaved pairs, rotary_embedding_torch semantics)
-    float cs[16], sn[16];
-    {
-      const int pos = valid ? (posmode == 0 ? static_cast<int>(m % L) : static_cast<int>((m / L) % F)) : 0;
-      const float4* c4 = reinterpret_cast<const float4*>(rope_cos + pos * 16);
-      const float4* s4 = reinterpret_cast<const float4*>(rope_sin + pos * 16);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 a = __ldg(c4 + i), b = __ldg(s4 + i);
-        cs[4 * i] = a.x; cs[4 * i + 1] = a.y; cs[4 * i + 2] = a.z; cs[4 * i + 3] = a.w;
-        sn[4 * i] = b.x; sn[4 * i + 1] = b.y; sn[4 * i + 2] = b.z; sn[4 * i + 3] = b.w;
-      }
-    }
-    mbar_wait_a(bar_d, it & 1);
-    tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < 3 * C / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_base + c * 32, r);
-      tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-      const int which = (c * 32) / C;  // 0 q, 1 k, 2 v (compile-time after unrolling)
-      if (which < 2) {
-        const float sc = which == 0 ? qscale : 1.0f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float x0 = v[2 * i], x1 = v[2 * i + 1];
-          v[2 * i] = (x0 * cs[i] - x1 * sn[i]) * sc;
-          v[2 * i + 1] = (x1 * cs[i] + x0 * sn[i]) * sc;
+        for (int i = 0; i < 4; ++i) {
+          const float4 a = __ldg(c4 + i), b = __ldg(s4 + i);
+          cs[4 * i] = a.x; cs[4 * i + 1] = a.y; cs[4 * i + 2] = a.z; cs[4 * i + 3] = a.w;
+          sn[4 * i] = b.x; sn[4 * i + 1] = b.y; sn[4 * i + 2] = b.z; sn[4 * i + 3] = b.w;
         }
       }
-      if (valid) store_act<h16, 32>(qkv + m * (3 * C) + c * 32, v);
-    }
+      mbar_wait_a(bar_d, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 3 * C / 32; ++c, ++ck) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_base + c * 32, r);
+        const uint32_t qb = qbuf + 2048u * (ck & 3);
+        if (lane == 0) bulk_wait_read<3>();  // the store that last read this output tile (four chunks ago) is done
+        __syncwarp();
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        const int which = (c * 32) / C;  // 0 q, 1 k, 2 v (compile-time after unrolling)
+        if (which < 2) {
+          const float sc = which == 0 ? qscale : 1.0f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x0 = v[2 * i], x1 = v[2 * i + 1];
+            v[2 * i] = (x0 * cs[i] - x1 * sn[i]) * sc;
+            v[2 * i + 1] = (x1 * cs[i] + x0 * sn[i]) * sc;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          st_shared_v4(qb + lane * 64 + ((static_cast<uint32_t>(i) << 4) ^ sw64), pack_h16x2(v[8 * i], v[8 * i + 1]),
+                       pack_h16x2(v[8 * i + 2], v[8 * i + 3]), pack_h16x2(v[8 * i + 4], v[8 * i + 5]),
+                       pack_h16x2(v[8 * i + 6], v[8 * i + 7]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmQ, qb, c * 32, tile * 128 + warp * 32);  // rows beyond M are clipped
+          bulk_commit();
+        }
+      }
     }  // tile loop
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -509,6 +546,9 @@ struct TcQkvPlan {
   CUtensorMap tmW;
   int C;
   int64_t M;
+  // activation tensor maps, (re)encoded when a launch names other buffers (a call site always passes the same ones)
+  mutable CUtensorMap tmX, tmQ;
+  mutable const void *k_x = nullptr, *k_q = nullptr;
 };
 TcQkvPlan* tc_qkv_plan_create(const void* wqkv_h16, int C, int64_t M, char* err, int errlen) {
   if (C != 32 && C != 64) { snprintf(err, errlen, "fused qkv: C must be 32 or 64"); return nullptr; }
@@ -524,14 +564,24 @@ void tc_qkv_plan_destroy(TcQkvPlan* p) { delete p; }
 int launch_fused_qkv(const TcQkvPlan* p, const float* X, const float* wg, const float* bg, const float* rope_cos,
                      const float* rope_sin, void* qkv, float* gates, int L, int F, int posmode, float qscale,
                      cudaStream_t st) {
+  if (p->k_x != X || p->k_q != qkv) {
+    char err[256];
+    const uint32_t box[2] = {32, 32};
+    const uint64_t dx[2] = {static_cast<uint64_t>(p->C), static_cast<uint64_t>(p->M)};
+    const uint64_t sx[1] = {static_cast<uint64_t>(p->C) * 4};
+    const uint64_t dq[2] = {static_cast<uint64_t>(3 * p->C), static_cast<uint64_t>(p->M)};
+    const uint64_t sq[1] = {static_cast<uint64_t>(3 * p->C) * 2};
+    if (!make_tmap_f32(&p->tmX, X, 2, dx, sx, box, 128, err, sizeof(err)) || !make_tmap(&p->tmQ, qkv, 2, dq, sq, box, 64, err, sizeof(err)))
+      return -1;
+    p->k_x = X; p->k_q = qkv;
+  }
   const unsigned ntiles = static_cast<unsigned>((p->M + 127) / 128);
   const unsigned slots = static_cast<unsigned>(g_num_sms) * (p->C == 32 ? 3u : 2u);
   const unsigned grid = ntiles < slots ? ntiles : slots;  // persistent CTAs
-  h16* q = reinterpret_cast<h16*>(qkv);
   if (p->C == 32)
-    fused_qkv_kernel<32><<<grid, FF_THREADS, QkvCfg<32>::SMEM, st>>>(p->tmW, X, wg, bg, rope_cos, rope_sin, q, gates, p->M, L, F, posmode, qscale);
+    fused_qkv_kernel<32><<<grid, FF_THREADS, QkvCfg<32>::SMEM, st>>>(p->tmW, p->tmX, p->tmQ, wg, bg, rope_cos, rope_sin, gates, p->M, L, F, posmode, qscale);
   else
-    fused_qkv_kernel<64><<<grid, FF_THREADS, QkvCfg<64>::SMEM, st>>>(p->tmW, X, wg, bg, rope_cos, rope_sin, q, gates, p->M, L, F, posmode, qscale);
+    fused_qkv_kernel<64><<<grid, FF_THREADS, QkvCfg<64>::SMEM, st>>>(p->tmW, p->tmX, p->tmQ, wg, bg, rope_cos, rope_sin, gates, p->M, L, F, posmode, qscale);
   return 0;
 }
 int tc_init_fused(char* err, int errlen) {

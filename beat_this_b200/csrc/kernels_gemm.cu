@@ -82,18 +82,6 @@ struct TgCfg {
   static constexpr int SWZ = BK * 2;  // 128 or 64 byte rows
 };
 
-__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int32_t c0, int32_t c1, int32_t c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(tmap)),
-               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {  // at most N of this thread's bulk groups still read shared memory
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-
 // EM: 0 direct epilogue (epilogue.cuh, any EpiParams); TMA epilogues: EM_QKV RoPE + q scale -> 16-bit; EM_ACT bias +
 // GELU -> 16-bit; EM_RESID [bias +] fp32 residual -> fp32 in place [+ 16-bit copy]; EM_F32 bias [+ GELU] -> fp32
 enum { EM_DIRECT = 0, EM_QKV = 1, EM_ACT = 2, EM_RESID = 3, EM_F32 = 4 };
