@@ -373,7 +373,7 @@ int attention_block(bt_ctx* c, float* X, int planes, int L, int C, int F, bool f
     if (launch_fused_qkv(tp->fqkv, X, w.wg->f32, w.bg->f32, c->mw.rope_cos->f32, c->mw.rope_sin->f32,
                          c->QKV, c->GATES, L, F, freq ? 1 : 0, qscale, st) != 0)
       return fail(c, BT_ERR_CUDA, "fused qkv launch failed");
-    BT_LAUNCHED(c, "qkv_fused", st);
+    BT_LAUNCHED(c, C == 32 ? "qkv_fused_c32" : "qkv_fused_c64", st);
   } else {
     // heads 1/2 (unfused fallback of blocks 0/1): gates inside the norm kernel; heads >= 4: padded gates GEMM
     static const int gin_max = getenv("BT_GATES_IN_NORM_MAX") ? atoi(getenv("BT_GATES_IN_NORM_MAX")) : 2;
@@ -427,7 +427,7 @@ int ff_block(bt_ctx* c, float* X, int planes, int L, int C, int mult, const FfW&
   if (tc && tp && tp->fused) {
     if (launch_fused_ff(with_outproj ? tp->fused_op : tp->fused, X, w.b1->f32, w.b2->f32, copy_act, st) != 0)
       return fail(c, BT_ERR_CUDA, "fused ff launch failed");
-    BT_LAUNCHED(c, "ff_fused", st);
+    BT_LAUNCHED(c, C == 32 ? "ff_fused_c32" : "ff_fused_c64", st);
     return BT_OK;
   }
   launch_norm(X, c->XN, M, C, tc, st);

@@ -45,6 +45,7 @@ template <int C, bool OP>
 __global__ void __launch_bounds__(FF_THREADS, FfCfg<C>::CTAS)
 fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWo,
+                const __grid_constant__ CUtensorMap tmXst, const __grid_constant__ CUtensorMap tmXb,
                 float* __restrict__ X, const float* __restrict__ b1, const float* __restrict__ b2,
                 h16* __restrict__ xb_out, int64_t M) {
   // PERSISTENT: each CTA walks over token tiles (stride gridDim.x); W1 (and W2 when it is a single chunk) are
@@ -230,6 +231,10 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
       for (int h = 0; h < NH; ++h, ++idx) {
         mbar_wait_a(bar_h, idx & 1);
         tc_fence_after();
+        if (h == 0) {  // this warp's rows of the H tile staged the previous tile's results: their TMA stores must be done reading
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+        }
         if (h >= 1) {  // the single H tile is free once MMA2_{h-1} has completed (h == 0: waited at the end of the last tile)
           mbar_wait_a(bar_o, (idx - 1) & 1);
           tc_fence_after();
@@ -262,26 +267,63 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
       }
       mbar_wait_a(bar_o, (idx - 1) & 1);
       tc_fence_after();
+      // Results leave through TMA stores staged in this warp's rows of the H tile buffer (free from here until the
+      // next tile's hidden activations are written): with one row per lane, st.global touched 32 lines per
+      // instruction and the L1 data pipe bounded the kernel (ncu: lsu wavefronts 80 %, DRAM 35 %).
+      const uint32_t stg = sH + warp * 4096;  // + c4 * 16384: [32 rows][128 B] SW128 fp32 box of 32 columns
+      const uint32_t sw128 = static_cast<uint32_t>(lane & 7) << 4, sw64 = static_cast<uint32_t>((lane >> 1) & 3) << 4;
+      uint32_t xbp[C / 2];  // the 16-bit copy of the row (for the following convolution), packed
 #pragma unroll
       for (int c4 = 0; c4 < C / 32; ++c4) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + lane_base + Cfg::OUT_COL + c4 * 32, r);
         tmem_ld_wait();
-        if (valid) {
-          float v[32];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 bq = ld_shared_v4_f32(sB + 4 * (4 * C + c4 * 32 + 4 * i));
-            v[4 * i] = __uint_as_float(r[4 * i]) + bq.x + x[c4 * 32 + 4 * i];
-            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bq.y + x[c4 * 32 + 4 * i + 1];
-            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bq.z + x[c4 * 32 + 4 * i + 2];
-            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bq.w + x[c4 * 32 + 4 * i + 3];
-          }
-          store_act<float, 32>(X + m * C + c4 * 32, v);
-          if (xb_out) store_act<h16, 32>(xb_out + m * C + c4 * 32, v);
+        for (int i = 0; i < 8; ++i) {
+          const float4 bq = ld_shared_v4_f32(sB + 4 * (4 * C + c4 * 32 + 4 * i));
+          const float v0 = __uint_as_float(r[4 * i]) + bq.x + x[c4 * 32 + 4 * i];
+          const float v1 = __uint_as_float(r[4 * i + 1]) + bq.y + x[c4 * 32 + 4 * i + 1];
+          const float v2 = __uint_as_float(r[4 * i + 2]) + bq.z + x[c4 * 32 + 4 * i + 2];
+          const float v3 = __uint_as_float(r[4 * i + 3]) + bq.w + x[c4 * 32 + 4 * i + 3];
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + c4 * 16384 + lane * 128 + ((static_cast<uint32_t>(i) << 4) ^ sw128)),
+                       "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+          xbp[c4 * 16 + 2 * i] = pack_h16x2(v0, v1);
+          xbp[c4 * 16 + 2 * i + 1] = pack_h16x2(v2, v3);
+        }
+      }
+      if (C == 32 && xb_out) {  // room for the 16-bit tile next to the fp32 one (second half of this warp's H rows)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          st_shared_v4(stg + 16384 + lane * 64 + ((static_cast<uint32_t>(i) << 4) ^ sw64), xbp[4 * i], xbp[4 * i + 1], xbp[4 * i + 2], xbp[4 * i + 3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int c4 = 0; c4 < C / 32; ++c4) tma_store_2d(&tmXst, stg + c4 * 16384, c4 * 32, tile * 128 + warp * 32);
+        if (C == 32 && xb_out) tma_store_2d(&tmXb, stg + 16384, 0, tile * 128 + warp * 32);
+        bulk_commit();
+      }
+      if (C == 64 && xb_out) {  // no spare room: the 16-bit tiles reuse the staging area once the fp32 stores have read it
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int c4 = 0; c4 < C / 32; ++c4)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            st_shared_v4(stg + c4 * 16384 + lane * 64 + ((static_cast<uint32_t>(i) << 4) ^ sw64), xbp[c4 * 16 + 4 * i],
+                         xbp[c4 * 16 + 4 * i + 1], xbp[c4 * 16 + 4 * i + 2], xbp[c4 * 16 + 4 * i + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int c4 = 0; c4 < C / 32; ++c4) tma_store_2d(&tmXb, stg + c4 * 16384, c4 * 32, tile * 128 + warp * 32);
+          bulk_commit();
         }
       }
     }
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -293,6 +335,9 @@ struct TcFfPlan {
   int C;
   int64_t M;
   bool outproj;
+  // result tensor maps, (re)encoded when a launch names other buffers (a call site always passes the same ones)
+  mutable CUtensorMap tmXst, tmXb;
+  mutable const void *k_x = nullptr, *k_xb = nullptr;
 };
 
 // o_h16 / wout_h16 != nullptr: plan for the variant with the attention out-projection fused in front
@@ -337,13 +382,24 @@ TcFfPlan* tc_ff_plan_create(const void* w1_h16, const void* w2_h16, int C, int64
 void tc_ff_plan_destroy(TcFfPlan* p) { delete p; }
 
 int launch_fused_ff(const TcFfPlan* p, float* X, const float* b1, const float* b2, void* xb_out, cudaStream_t st) {
+  if (p->k_x != X || p->k_xb != xb_out) {
+    char err[256];
+    const uint32_t box[2] = {32, 32};
+    const uint64_t dx[2] = {static_cast<uint64_t>(p->C), static_cast<uint64_t>(p->M)};
+    const uint64_t sx[1] = {static_cast<uint64_t>(p->C) * 4};
+    const uint64_t sb[1] = {static_cast<uint64_t>(p->C) * 2};
+    if (!make_tmap_f32(&p->tmXst, X, 2, dx, sx, box, 128, err, sizeof(err))) return -1;
+    if (xb_out) { if (!make_tmap(&p->tmXb, xb_out, 2, dx, sb, box, 64, err, sizeof(err))) return -1; }
+    else p->tmXb = p->tmXst;  // never dereferenced
+    p->k_x = X; p->k_xb = xb_out;
+  }
   const unsigned ntiles = static_cast<unsigned>((p->M + 127) / 128);
   const unsigned slots = static_cast<unsigned>(g_num_sms) * (p->C == 32 ? FfCfg<32>::CTAS : FfCfg<64>::CTAS);
   const unsigned grid = ntiles < slots ? ntiles : slots;  // persistent CTAs
   h16* xb = reinterpret_cast<h16*>(xb_out);
 #define BT_FF_L(CC, OPP)                                                                                          \
-  fused_ff_kernel<CC, OPP><<<grid, FF_THREADS, FfCfg<CC>::SMEM, st>>>(p->tmW1, p->tmW2, p->tmO, p->tmWo, X, b1, b2, xb, \
-                                                                      p->M)
+  fused_ff_kernel<CC, OPP><<<grid, FF_THREADS, FfCfg<CC>::SMEM, st>>>(p->tmW1, p->tmW2, p->tmO, p->tmWo, p->tmXst, p->tmXb, X, \
+                                                                      b1, b2, xb, p->M)
   if (p->C == 32) { if (p->outproj) BT_FF_L(32, true); else BT_FF_L(32, false); }
   else { if (p->outproj) BT_FF_L(64, true); else BT_FF_L(64, false); }
 #undef BT_FF_L
