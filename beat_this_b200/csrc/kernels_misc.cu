@@ -2,9 +2,11 @@
 // frequency-direction attention, head + aggregation scatter, peak picking.
 #include <cuda_fp16.h>
 #include <cstdlib>
+#include <mutex>
 
 #include "bt_kernels.h"
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace bt {
 
@@ -477,47 +479,46 @@ __device__ __forceinline__ void mma_h16_16816(float (&d)[4], const uint32_t (&a)
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// Tile = FT_TT consecutive frames of one chunk, all F frequency planes, all heads: for a fixed plane the rows of
+// consecutive frames are contiguous in [B, F, L, 3C], so ONE TMA box per (q|k|v, head) brings [F][TT][32] fp16 into
+// shared memory (SWIZZLE_64B) and one box stores the [F][TT][C] output tile.  (Before: every lane fetched its own
+// row, L * 3C elements away from its neighbour's -- 32 lines per ld.global, L1 wavefronts 73-87 % in ncu.)
+constexpr int FT_TT = 4;
+
 template <int F>
 __global__ void __launch_bounds__(128)
-attn_freq_mma_kernel(const h16* __restrict__ qkv, const float* __restrict__ gates, h16* __restrict__ out,
-                     int B, int L, int heads, float scale_log2) {
-  constexpr int GPW = 32 / F;
-  constexpr int RS = 80;  // staged row stride in bytes (64 + 16 pad: conflict-free ldmatrix)
-  constexpr int NT = F == 32 ? 4 : 2;  // 8-key tiles a query tile attends to
-  __shared__ __align__(16) uint8_t stage[4][3][32 * RS];
+attn_freq_mma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut,
+                     const float* __restrict__ gates, int L, int heads, float scale_log2) {
+  constexpr int GPW = 32 / F;             // groups (frame, head) per warp
+  constexpr int NT = F == 32 ? 4 : 2;     // 8-key tiles a query tile attends to
+  constexpr int HEADS = 4 * GPW / FT_TT;  // 1, 2, 4 for F = 32, 16, 8: the four warps cover TT frames x HEADS heads
+  constexpr int C = HEADS * 32;
+  constexpr int PH_BYTES = F * FT_TT * 64;  // one (part, head) box
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sIn = sbase;                                  // [3 parts][HEADS][F * TT rows][64 B]
+  const uint32_t sOut = sIn + 3 * HEADS * PH_BYTES;            // [F * TT rows][C * 2 B], dense
+  const uint32_t bar = sOut + F * FT_TT * C * 2;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t ngrp = static_cast<int64_t>(B) * L * heads;
-  const int64_t grp0 = (static_cast<int64_t>(blockIdx.x) * 4 + wib) * GPW;
-  if (grp0 >= ngrp) return;  // warp-uniform
-  const int C = heads * 32;
-  auto row_token = [&](int r, int64_t& m, int& h) -> bool {  // staged row r -> token row, head; false: padding group
-    const int64_t grp = grp0 + r / F;
-    const bool act = grp < ngrp;
-    const int64_t gg = act ? grp : grp0;
-    h = static_cast<int>(gg % heads);
-    const int64_t bt_ = gg / heads;
-    const int t = static_cast<int>(bt_ % L);
-    const int b = static_cast<int>(bt_ / L);
-    m = (static_cast<int64_t>(b) * F + (r % F)) * L + t;
-    return act;
-  };
-  const uint32_t sQ = smem_u32(&stage[wib][0][0]), sK = smem_u32(&stage[wib][1][0]), sV = smem_u32(&stage[wib][2][0]);
-  {
-    int64_t m; int h;
-    row_token(lane, m, h);
-    const uint4* rp = reinterpret_cast<const uint4*>(qkv + m * 3 * C + h * 32);
-#pragma unroll
-    for (int part = 0; part < 3; ++part) {
-      const uint4* src = rp + part * (C / 8);
-      uint4 v[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = src[i];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        st_shared_v4(sQ + part * (32 * RS) + lane * RS + 16 * i, v[i].x, v[i].y, v[i].z, v[i].w);
-    }
+  const int t0 = blockIdx.x * FT_TT, b = blockIdx.y;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+    fence_barrier_init();
+    mbar_expect_tx_a(bar, 3 * HEADS * PH_BYTES);
+    for (int part = 0; part < 3; ++part)
+      for (int h = 0; h < HEADS; ++h)
+        tma_load_3d_a(sIn + (part * HEADS + h) * PH_BYTES, &tmIn, bar, part * C + h * 32, t0, b * F);
   }
-  __syncwarp();
+  __syncthreads();
+  mbar_wait_a(bar, 0);
+  // this warp's groups: head h, frames tt_base .. tt_base + GPW - 1; "staged row" r = gl * F + f as before
+  const int h = (wib * GPW) / FT_TT;
+  const int tt_base = (wib * GPW) % FT_TT;
+  auto row_addr = [&](uint32_t base, int r, int chunk) -> uint32_t {  // 16-byte chunk `chunk` of staged row r
+    const int row = (r % F) * FT_TT + tt_base + r / F;
+    return base + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+  };
+  const uint32_t sQ = sIn + (0 * HEADS + h) * PH_BYTES, sK = sIn + (1 * HEADS + h) * PH_BYTES, sV = sIn + (2 * HEADS + h) * PH_BYTES;
   const int g = lane >> 2, c = lane & 3;
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
@@ -525,13 +526,13 @@ attn_freq_mma_kernel(const h16* __restrict__ qkv, const float* __restrict__ gate
     uint32_t qa[2][4];
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk)
-      ldsm_x4(sQ + (16 * mt + (lane & 7) + ((lane >> 3) & 1) * 8) * RS + (kk * 16 + (lane >> 4) * 8) * 2, qa[kk]);
+      ldsm_x4(row_addr(sQ, 16 * mt + (lane & 7) + ((lane >> 3) & 1) * 8, kk * 2 + (lane >> 4)), qa[kk]);
     float sc[NT][4];
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
       uint32_t kb[4];
-      ldsm_x4(sK + (key_base + 8 * j + (lane & 7)) * RS + ((lane >> 3) * 8) * 2, kb);
+      ldsm_x4(row_addr(sK, key_base + 8 * j + (lane & 7), lane >> 3), kb);
       mma_h16_16816(sc[j], qa[0], kb[0], kb[1]);
       mma_h16_16816(sc[j], qa[1], kb[2], kb[3]);
     }
@@ -571,23 +572,65 @@ attn_freq_mma_kernel(const h16* __restrict__ qkv, const float* __restrict__ gate
       for (int jd = 0; jd < 4; jd += 2) {
         uint32_t vb[4];
         const int q4 = lane >> 3;
-        ldsm_x4_trans(sV + (key_base + 16 * kk + (q4 & 1) * 8 + (lane & 7)) * RS + (8 * (jd + (q4 >> 1))) * 2, vb);
+        ldsm_x4_trans(row_addr(sV, key_base + 16 * kk + (q4 & 1) * 8 + (lane & 7), jd + (q4 >> 1)), vb);
         mma_h16_16816(o[jd], pa, vb[0], vb[1]);
         mma_h16_16816(o[jd + 1], pa, vb[2], vb[3]);
       }
     }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      int64_t m; int h;
-      if (row_token(16 * mt + g + 8 * half, m, h)) {
-        const float gsc = gates[m * heads + h] / (half == 0 ? l0 : l1);
-        uint32_t* op = reinterpret_cast<uint32_t*>(out + m * C + h * 32);
+      const int r = 16 * mt + g + 8 * half;
+      const int f = r % F, tt = tt_base + r / F;
+      const int t = t0 + tt;
+      const int64_t m = (static_cast<int64_t>(b) * F + f) * L + (t < L ? t : L - 1);
+      const float gsc = gates[m * HEADS + h] / (half == 0 ? l0 : l1);
+      const uint32_t orow = sOut + (f * FT_TT + tt) * (C * 2) + h * 64;
 #pragma unroll
-        for (int jd = 0; jd < 4; ++jd)
-          op[4 * jd + c] = pack_h16x2(o[jd][2 * half] * gsc, o[jd][2 * half + 1] * gsc);
-      }
+      for (int jd = 0; jd < 4; ++jd)
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(orow + (4 * jd + c) * 4), "r"(pack_h16x2(o[jd][2 * half] * gsc, o[jd][2 * half + 1] * gsc)) : "memory");
     }
   }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tma_store_3d(&tmOut, sOut, 0, t0, b * F);  // frames beyond L are clipped
+    bulk_commit();
+    bulk_wait_read<0>();
+  }
+}
+
+template <int F>
+static int attn_freq_mma_launch(const void* qkv, const float* gates, void* out, int B, int L, float sl2, cudaStream_t st) {
+  constexpr int HEADS = 4 * (32 / F) / FT_TT;
+  constexpr int C = HEADS * 32;
+  constexpr int SMEM = 3 * HEADS * F * FT_TT * 64 + F * FT_TT * C * 2 + 1024 + 64;
+  // tensor maps over the activation buffers, cached per (buffers, geometry)
+  struct Key { const void *q, *o; int B, L; CUtensorMap in, outm; };
+  static Key cache[4];
+  static int n_cached = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  Key* k = nullptr;
+  for (int i = 0; i < n_cached; ++i)
+    if (cache[i].q == qkv && cache[i].o == out && cache[i].B == B && cache[i].L == L) k = &cache[i];
+  if (!k) {
+    k = &cache[n_cached < 4 ? n_cached++ : 0];
+    char err[256];
+    const uint64_t din[3] = {static_cast<uint64_t>(3 * C), static_cast<uint64_t>(L), static_cast<uint64_t>(B) * F};
+    const uint64_t sin_[2] = {static_cast<uint64_t>(3 * C) * 2, static_cast<uint64_t>(L) * 3 * C * 2};
+    const uint32_t bin[3] = {32, FT_TT, F};
+    const uint64_t dout[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(L), static_cast<uint64_t>(B) * F};
+    const uint64_t sout[2] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(L) * C * 2};
+    const uint32_t bout[3] = {static_cast<uint32_t>(C), FT_TT, F};
+    if (!make_tmap(&k->in, qkv, 3, din, sin_, bin, 64, err, sizeof(err)) || !make_tmap(&k->outm, out, 3, dout, sout, bout, 0, err, sizeof(err)))
+      return -1;
+    k->q = qkv; k->o = out; k->B = B; k->L = L;
+  }
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(attn_freq_mma_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); attr = true; }
+  dim3 grid(ceil_div(L, FT_TT), B);
+  attn_freq_mma_kernel<F><<<grid, 128, SMEM, st>>>(k->in, k->outm, gates, L, HEADS, sl2);
+  return 0;
 }
 
 template <typename TAct>
@@ -606,15 +649,12 @@ void launch_attn_freq(const void* qkv, const float* gates, void* out, int B, int
                       float scale, int act_h16, cudaStream_t st) {
   static const bool simt = getenv("BT_ATTN_FREQ_SIMT") && atoi(getenv("BT_ATTN_FREQ_SIMT")) != 0;
   if (act_h16 && !simt && (F == 32 || F == 16 || F == 8)) {
-    const int64_t ngrp = static_cast<int64_t>(B) * L * heads;
-    const unsigned grid = static_cast<unsigned>(ceil_div64(ngrp, 4 * (32 / F)));
-    const h16* q = reinterpret_cast<const h16*>(qkv);
-    h16* o = reinterpret_cast<h16*>(out);
     const float sl2 = scale * 1.4426950408889634f;
-    if (F == 32) attn_freq_mma_kernel<32><<<grid, 128, 0, st>>>(q, gates, o, B, L, heads, sl2);
-    else if (F == 16) attn_freq_mma_kernel<16><<<grid, 128, 0, st>>>(q, gates, o, B, L, heads, sl2);
-    else attn_freq_mma_kernel<8><<<grid, 128, 0, st>>>(q, gates, o, B, L, heads, sl2);
-    return;
+    int rc = -1;
+    if (F == 32 && heads == 1) rc = attn_freq_mma_launch<32>(qkv, gates, out, B, L, sl2, st);
+    else if (F == 16 && heads == 2) rc = attn_freq_mma_launch<16>(qkv, gates, out, B, L, sl2, st);
+    else if (F == 8 && heads == 4) rc = attn_freq_mma_launch<8>(qkv, gates, out, B, L, sl2, st);
+    if (rc == 0) return;
   }
   if (act_h16) attn_freq_dispatch<h16>(qkv, gates, out, B, F, L, heads, scale, st);
   else attn_freq_dispatch<float>(qkv, gates, out, B, F, L, heads, scale, st);
@@ -743,26 +783,36 @@ peakpick_kernel(const float* __restrict__ beat, const float* __restrict__ down,
   __syncthreads();
   const int nd_raw = compact_peaks(down + f0, T, dt_, max_peaks, s_warp, &s_base);
   __syncthreads();
+  __shared__ int s_nb, s_nd;
   if (threadIdx.x == 0) {
-    if (nb_raw > max_peaks || nd_raw > max_peaks) {  // overflow: report, host retries bigger
+    if (nb_raw > max_peaks || nd_raw > max_peaks) {  // overflow: report the true counts, keep the first max_peaks
       n_beat[clip] = nb_raw;
       n_down[clip] = nd_raw;
-      return;
+      s_nb = -1;
+    } else {
+      s_nb = dedup_to_times(bt_, nb_raw);
+      s_nd = dedup_to_times(dt_, nd_raw);
     }
-    const int nb = dedup_to_times(bt_, nb_raw);
-    int nd = dedup_to_times(dt_, nd_raw);
-    if (nb > 0) {
-      for (int i = 0; i < nd; ++i) {
-        const double d = dt_[i];
-        int best = 0;
-        double bd = fabs(bt_[0] - d);
-        for (int j = 1; j < nb; ++j) {
-          const double dd = fabs(bt_[j] - d);
-          if (dd < bd) { bd = dd; best = j; }
-        }
-        dt_[i] = bt_[best];
+  }
+  __syncthreads();
+  const int nb = s_nb;
+  if (nb < 0) return;
+  int nd = s_nd;
+  // every downbeat moves to the nearest beat time (first minimum, postprocessor.py:128-134): one downbeat per thread
+  if (nb > 0) {
+    for (int i = threadIdx.x; i < nd; i += blockDim.x) {
+      const double d = dt_[i];
+      int best = 0;
+      double bd = fabs(bt_[0] - d);
+      for (int j = 1; j < nb; ++j) {
+        const double dd = fabs(bt_[j] - d);
+        if (dd < bd) { bd = dd; best = j; }
       }
+      dt_[i] = bt_[best];
     }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
     // np.unique: sort + drop duplicates (snapped downbeats are non-decreasing; insertion sort is a no-op then)
     for (int i = 1; i < nd; ++i) {
       const double v = dt_[i];
