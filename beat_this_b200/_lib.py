@@ -93,6 +93,7 @@ PROTOTYPES = {
     "bt_debug_request_tap": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
     "bt_debug_tap_count": (c_int64, [c_void_p]),
     "bt_debug_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "bt_debug_attention_time": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "bt_debug_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
 }
 

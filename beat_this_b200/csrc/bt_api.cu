@@ -1180,4 +1180,63 @@ int bt_debug_attention(bt_ctx* c, const float* q_dev, const float* k_dev, const 
   return rc;
 }
 
+int bt_debug_attention_time(bt_ctx* c, int32_t seqs, int32_t L, int32_t heads, int32_t variant, int32_t iters,
+                            float* ms_per_launch) {
+  if (!c || !ms_per_launch || iters < 1) return BT_ERR_ARG;
+  if (c->dtype != BT_DTYPE_H16) return fail(c, BT_ERR_ARG, "bt_debug_attention_time needs the 16-bit context");
+  BT_CUDA(c, cudaSetDevice(c->device));
+  const int C = heads * 32;
+  const int64_t M = static_cast<int64_t>(seqs) * L;
+  void *qkv = nullptr, *o = nullptr;
+  float *gates = nullptr, *src = nullptr;
+  BT_CUDA(c, cudaMalloc(&qkv, M * 3 * C * 2));
+  BT_CUDA(c, cudaMalloc(&o, M * C * 2));
+  BT_CUDA(c, cudaMalloc(&gates, M * heads * 4));
+  BT_CUDA(c, cudaMalloc(&src, M * C * 4));
+  std::vector<float> h(M * C);
+  uint32_t x = 12345u;
+  for (auto& v : h) { x = x * 1664525u + 1013904223u; v = (static_cast<float>(x >> 8) / 8388608.0f - 1.0f) * 1.5f; }
+  BT_CUDA(c, cudaMemcpy(src, h.data(), M * C * 4, cudaMemcpyHostToDevice));
+  std::vector<float> ones(M * heads, 1.0f);
+  BT_CUDA(c, cudaMemcpy(gates, ones.data(), M * heads * 4, cudaMemcpyHostToDevice));
+  cudaStream_t st = nullptr;
+  launch_pack_qkv_test(src, src, src, qkv, seqs, L, heads, 0.17677669529663687f * 1.4426950408889634f, 1, st);
+  char err[512] = "";
+  TcAttnPlan* p = tc_attn_plan_create(qkv, seqs, L, heads, err, sizeof(err));
+  int rc = BT_OK;
+  if (!p) rc = fail(c, BT_ERR_CUDA, "%s", err);
+  else {
+    if (variant >= 0) attn_set_variant(variant);
+    unsigned long long prof[40];
+    attn_prof_read(prof, true);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 2 && rc == BT_OK; ++i)
+      if (launch_attn_time_tc(p, gates, o, st) != 0) rc = fail(c, BT_ERR_ARG, "unknown attention variant %d", variant);
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < iters && rc == BT_OK; ++i) launch_attn_time_tc(p, gates, o, st);
+    cudaEventRecord(e1, st);
+    cudaError_t se = cudaStreamSynchronize(st);
+    if (rc == BT_OK && se != cudaSuccess) rc = fail(c, BT_ERR_CUDA, "attention: %s", cudaGetErrorString(se));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_per_launch = ms / iters;
+    if (variant >= 0 && (variant & 64)) {
+      attn_prof_read(prof, true);
+      for (int w = 0; w < 4; ++w) {
+        const unsigned long long* q = prof + 8 * w;
+        const double n = static_cast<double>(q[6] ? q[6] : 1);  // warp-tiles
+        fprintf(stderr, "attention phases, warp %d, cycles per tile: wait S %.0f | ld S %.0f | max %.0f | exp %.0f | wait PV %.0f | st P %.0f\n",
+                w, q[0] / n, q[1] / n, q[2] / n, q[3] / n, q[4] / n, q[5] / n);
+      }
+      if (prof[34]) fprintf(stderr, "issuer warp, cycles per tile: wait P %.0f | rest %.0f\n", prof[32] / double(prof[34]), prof[33] / double(prof[34]));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    tc_attn_plan_destroy(p);
+    if (variant >= 0) attn_set_variant(-1);
+  }
+  cudaFree(qkv); cudaFree(o); cudaFree(gates); cudaFree(src);
+  return rc;
+}
+
 }  // extern "C"

@@ -110,6 +110,8 @@ int launch_gemm_tc(const TcGemmPlan* plan, const EpiParams& e, cudaStream_t st);
 struct TcAttnPlan;
 TcAttnPlan* tc_attn_plan_create(const void* qkv_h16, int seqs, int L, int heads, char* err, int errlen);
 void tc_attn_plan_destroy(TcAttnPlan*);
+void attn_prof_read(unsigned long long* out40, bool reset);  // debug: phase cycle counters of variant bit 64
+void attn_set_variant(int v);  // debug: template parameter V of attn_tc48_kernel (kernels_attn.cu)
 int launch_attn_time_tc(const TcAttnPlan* plan, const float* gates, void* out_h16, cudaStream_t st,
                         const ChunkSrc* chunks = nullptr, int seqs_per_chunk = 1);
 

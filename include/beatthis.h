@@ -252,6 +252,12 @@ int bt_debug_gemm(bt_ctx* ctx, const float* a_dev, const float* w_dev, float* d_
 int bt_debug_attention(bt_ctx* ctx, const float* q_dev, const float* k_dev, const float* v_dev,
                        float* o_dev, int32_t seqs, int32_t L, int32_t heads, void* stream);
 
+/* Profiling hook (tools/attn_ubench.py): time `iters` launches of the 16-bit time-direction attention kernel on
+ * synthetic q|k|v of [seqs, L, heads*32]; variant < 0 keeps the default kernel, otherwise the template parameter V
+ * of attn_tc48_kernel (kernels_attn.cu lists the compiled ones).  *ms_per_launch from CUDA events. */
+int bt_debug_attention_time(bt_ctx* ctx, int32_t seqs, int32_t L, int32_t heads, int32_t variant,
+                            int32_t iters, float* ms_per_launch);
+
 #ifdef __cplusplus
 }
 #endif
