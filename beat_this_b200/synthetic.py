@@ -183,3 +183,14 @@ def tensor_checksum(sd: dict) -> float:
         v = sd[k].double()
         tot += float(v.sum()) + 1e-3 * float((v * v).sum())
     return tot
+
+
+# int16 WAV material of the CLI byte-parity fixture (tests/golden/cli_beats.npz, oracle/make_golden_cli.py):
+# (file name, seed of synth_clip, seconds, channels)
+CLI_CASES = [("one.wav", 301, 10.0, 1), ("sub/two.wav", 302, 31.5, 1), ("sub/stereo.wav", 303, 7.0, 2)]
+
+
+def pcm16(seed: int, secs: float, channels: int) -> np.ndarray:
+    """16-bit PCM of synth_clip(seed, secs); the second channel of a stereo file is the reversed clip at half level."""
+    data = np.round(synth_clip(seed, secs) * 32767).astype(np.int16)
+    return data if channels == 1 else np.stack([data, data[::-1] // 2], axis=1)

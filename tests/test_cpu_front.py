@@ -64,6 +64,19 @@ def test_beats_writer_matches_reference_fixtures(tmp_path):
         assert path.read_bytes() == g[f"text{k}"].tobytes(), k
 
 
+def test_beats_writer_on_the_reference_cli_fixtures(tmp_path):
+    """Writer half of tests/golden/cli_beats.npz (the GPU test runs the whole CLI): the reference's beats -> its bytes."""
+    from beat_this_b200.utils import save_beat_tsv
+
+    g = np.load(os.path.join(GOLDEN, "cli_beats.npz"))
+    for model_name in ("small0", "final0"):
+        for k in range(3):
+            path = tmp_path / f"{model_name}{k}.beats"
+            with contextlib.redirect_stdout(io.StringIO()):
+                save_beat_tsv(g[f"{model_name}_beats{k}"], g[f"{model_name}_downbeats{k}"], str(path))
+            assert path.read_bytes() == g[f"{model_name}_text{k}"].tobytes(), (model_name, k)
+
+
 def _stage(lib, arrays, threads=3):
     from beat_this_b200.pipeline import BeatPipeline
 

@@ -273,6 +273,42 @@ def test_native_dbn_viterbi_equals_dense_bruteforce(lib_built):
             assert abs(logp - ref_logp) < 1e-9 and np.array_equal(path, ref_path[::-1])
 
 
+def test_dbn_state_space_known_answers():
+    """Known answers for the bar-pointer state space, transition and observation model.  madmom is not installable
+    offline, so these are the small examples of madmom's own published documentation (madmom.features.beats_hmm:
+    the docstring examples of BeatStateSpace(1, 4) and BarStateSpace(2, 1, 4), exponential_transition and
+    RNNDownBeatTrackingObservationModel) plus the sizes that follow from the reference's configuration
+    (postprocessor.py:29-37: fps 50, 55..215 BPM -> beat intervals 14..55 frames)."""
+    from beat_this_b200.dbn import DBNDownBeatTracker, _BarModel
+
+    m = _BarModel(1, 1, 4, None, 100, 16)  # BeatStateSpace(1, 4)
+    assert m.num_states == 10 and m.intervals.tolist() == [1, 2, 3, 4]
+    assert m.first_states.tolist() == [[0, 1, 3, 6]] and m.last_states.tolist() == [[0, 2, 5, 9]]
+    assert np.allclose(m.positions, [0, 0, 0.5, 0, 1 / 3, 2 / 3, 0, 0.25, 0.5, 0.75])
+    m = _BarModel(2, 1, 4, None, 100, 16)  # BarStateSpace(2, 1, 4)
+    assert m.num_states == 20
+    assert m.first_states.tolist() == [[0, 1, 3, 6], [10, 11, 13, 16]]
+    assert m.last_states.tolist() == [[0, 2, 5, 9], [10, 12, 15, 19]]
+    assert np.allclose(m.positions[10:], np.asarray([0, 0, 0.5, 0, 1 / 3, 2 / 3, 0, 0.25, 0.5, 0.75]) + 1)
+    # exponential_transition: exp(-lambda |to / from - 1|), values <= eps dropped, rows normalised
+    m = _BarModel(1, 2, 4, None, 2.0, 16)
+    raw = np.exp(-2.0 * np.abs(np.asarray([2, 3, 4])[None, :] / np.asarray([2, 3, 4])[:, None] - 1.0))
+    assert np.allclose(np.exp(m.log_tempo), raw / raw.sum(1, keepdims=True))
+    m = _BarModel(1, 14, 55, None, 100, 16)
+    p = np.exp(m.log_tempo)
+    assert np.allclose(p.sum(1), 1.0) and p[0, -1] == 0.0 and p[20, 20] == p[20].max()
+    # observation pointers: the first 1/16 of every beat observes "beat", of the bar's first beat "downbeat"
+    m = _BarModel(2, 16, 16, None, 100, 16)
+    assert m.pointers.tolist() == [2] + [0] * 15 + [1] + [0] * 15
+    # the reference's configuration
+    trk = DBNDownBeatTracker()
+    assert [mm.beats for mm in trk.models] == [3, 4]
+    for mm in trk.models:
+        assert mm.intervals.tolist() == list(range(14, 56)) and mm.num_states == mm.beats * 1449
+    # num_tempi: log-spaced subset, as few intervals as requested
+    assert len(_BarModel(4, 14, 55, 20, 100, 16).intervals) == 20
+
+
 def test_native_dbn_tracks_synthetic_meters(lib_built):
     """4/4 at 120 BPM and 3/4 at 90 BPM impulse trains: beats on the impulses (after the `correct` step), bar
     positions counted 1..4 / 1..3, the right bar-length model wins, leading/trailing silence is trimmed, silence

@@ -305,6 +305,34 @@ def test_cli_directory_tree(small0_ckpt, lib_built, tmp_path):
     assert (out / "a.beats").stat().st_mtime_ns == stamp and (out / "sub" / "b.beats").exists()
 
 
+@pytest.mark.parametrize("model_name", ["small0", "final0"])
+def test_cli_beats_files_equal_the_reference_bytes(model_name, small0_ckpt, final0_ckpt, lib_built, tmp_path):
+    """`python -m beat_this_b200.cli <tree> -o <out>` on int16 WAV files (mono, stereo, a 2-chunk file) against the
+    bytes of the `.beats` files the UNMODIFIED reference writes for the same material (tests/golden/cli_beats.npz,
+    oracle/make_golden_cli.py: reference Audio2Beats on samples / 32768 + reference save_beat_tsv)."""
+    from scipy.io import wavfile
+
+    from beat_this_b200 import cli, synthetic
+    from oracle import beat_this_oracle as O
+    from beat_this_b200.synthetic import CLI_CASES, pcm16
+
+    g = np.load(os.path.join(GOLDEN, "cli_beats.npz"))
+    ckpt = small0_ckpt if model_name == "small0" else final0_ckpt
+    sd = O.strip_prefix(torch.load(ckpt, weights_only=True)["state_dict"])
+    want = float(g[f"{model_name}_ckpt_sum"])
+    assert abs(synthetic.tensor_checksum(sd) - want) < 1e-6 * abs(want), "checkpoint drifted from the fixture's"
+    src = tmp_path / "in"
+    (src / "sub").mkdir(parents=True)
+    for name, seed, secs, ch in CLI_CASES:
+        wavfile.write(src / name, 22050, pcm16(seed, secs, ch))
+    out = tmp_path / "out"
+    assert cli.main([str(src), "-o", str(out), "--model", ckpt, "--batch", "2"]) == 0
+    for k, (name, seed, secs, ch) in enumerate(CLI_CASES):
+        got = (out / name).with_suffix(".beats").read_bytes()
+        ref = g[f"{model_name}_text{k}"].tobytes()
+        assert got == ref, (model_name, name, len(got), len(ref))
+
+
 def test_config4_audio2beats_dbn_on_host(small0_ckpt, lib_built):
     """BASELINE config 4 shape (Audio2Beats --dbn, DBN on the host): frames from the device, post-processing by the
     host DBN (madmom if installed, else beat_this_b200/dbn.py).  The host side must equal running the same tracker
