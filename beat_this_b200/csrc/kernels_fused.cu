@@ -17,7 +17,17 @@ namespace bt {
 // (converged, one elected lane issues): TMA (weights) + tcgen05.mma.  Hidden units are processed in chunks of 128:
 //   H_h = Xn W1_h^T (N=128, K=C) -> TMEM cols [0,128) -> bias+GELU -> h16 tile in smem ->
 //   OUT (+)= H_h W2_h^T (N=C, K=128) -> TMEM cols [128,128+C).
-constexpr int FF_THREADS = 160;
+constexpr int FF_THREADS = 160;   // fused_qkv_kernel: 4 row warps + issuer
+// fused_ff_kernel: 4 row warps [+ 4 helper warps for C = 64] + issuer.  (C = 32 runs three CTAs per SM: nine warps each
+// would leave 72 registers per thread -- measured slower than four row warps with the next tile's rows prefetched.)
+template <int C> __host__ __device__ constexpr int ffn_threads() { return C == 64 ? 288 : 160; }
+
+#ifdef BT_FF_PROF  // -DBT_FF_PROF: cycles per phase of the row warps (lane 0), printed after every launch
+__device__ unsigned long long g_ff_prof[16];
+#define FF_TICK(i_) { const long long t_ = clock64(); tp[i_] += t_ - tc0; tc0 = t_; }
+#else
+#define FF_TICK(i_)
+#endif
 template <int C>
 struct FfCfg {
   static constexpr int NH = 4 * C / 128;            // hidden chunks
@@ -42,7 +52,7 @@ struct FfCfg {
 // TMA-loaded into the A-tile buffer, which the normalised x' overwrites afterwards), then the FFN runs on x'.
 // Saves the separate out-projection GEMM: one fp32 read + write of the residual stream per element.
 template <int C, bool OP>
-__global__ void __launch_bounds__(FF_THREADS, FfCfg<C>::CTAS)
+__global__ void __launch_bounds__(ffn_threads<C>(), FfCfg<C>::CTAS)
 fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWo,
                 const __grid_constant__ CUtensorMap tmXst, const __grid_constant__ CUtensorMap tmXb,
@@ -53,6 +63,9 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
   // more time on set-up and on re-fetching 16-64 KB of weights per CTA than on its tile.)
   using Cfg = FfCfg<C>;
   constexpr int NH = Cfg::NH;
+  constexpr bool HELP = C == 64;
+  constexpr int FFN_THREADS = ffn_threads<C>();
+  constexpr int FFN_ISSUER = HELP ? 8 : 4;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = sbase;
@@ -73,21 +86,21 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = static_cast<int>((M + 127) / 128);
 
-  if (warp == 4 && lane == 0) {
+  if (warp == FFN_ISSUER && lane == 0) {
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     auto init = [](uint32_t bar, uint32_t count) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
     };
-    init(bar_w1, 1); init(bar_w2, 1); init(bar_a, 128); init(bar_h, 1); init(bar_h2, 128); init(bar_o, 1);
+    init(bar_w1, 1); init(bar_w2, 1); init(bar_a, 128); init(bar_h, 1); init(bar_h2, HELP ? 256 : 128); init(bar_o, 1);
     init(bar_of, 1); init(bar_d0, 1);
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == FFN_ISSUER) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::TCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 5 * C; i += FF_THREADS)
+  for (int i = threadIdx.x; i < 5 * C; i += FFN_THREADS)
     st_shared_f32(sB + 4 * i, i < 4 * C ? __ldg(b1 + i) : __ldg(b2 + i - 4 * C));
   tc_fence_before();
   __syncthreads();
@@ -95,7 +108,7 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  if (warp == 4) {
+  if (warp == FFN_ISSUER) {
     const uint32_t on = elect_one() ? 1u : 0u;  // converged issuer warp, predicated single-lane TMA / MMA (see umma_h16_p)
     constexpr uint32_t idesc1 = make_idesc_h16(128, 128);
     constexpr uint32_t idesc2 = make_idesc_h16(128, C);
@@ -152,7 +165,7 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_h16_p(on, tmem_base + Cfg::OUT_COL, make_kmajor_desc<128>(sH + (k >> 2) * 16384 + (k & 3) * 32),
-                      make_kmajor_desc<128>(sW2 + (k >> 2) * (C * 128) + (k & 3) * 32), idesc2, (h | k) != 0 ? 1u : 0u);
+                      make_kmajor_desc<128>(sW2 + (k >> 2) * (C * 128) + (k & 3) * 32), idesc2, 1u);  // OUT starts from the residual x
         umma_commit_p(on, bar_o);
         if (NH > 1 && (h + 1 < NH || tile + static_cast<int>(gridDim.x) < ntiles)) {
           mbar_wait_a(bar_o, idx & 1);  // MMA2 finished reading this W2 chunk (and the H tile)
@@ -162,85 +175,29 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
       }
     }
   } else {
-    const int row = warp * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    // warps 0-3 own one token row per thread (load, RMSNorm, residual, stores); warps 4-7 share the same rows
+    // (TMEM lane quarter warp & 3) and take the upper half of every hidden chunk's bias + GELU epilogue -- the longest
+    // stretch of per-thread work in a tile, whose latency bounds a kernel with only 2-3 CTAs per SM
+    const int wq = warp & 3;
+    const bool helper = warp >= 4;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
     const uint32_t hrow = sH + row * 128;
     const uint32_t hsw = static_cast<uint32_t>(row & 7) << 4;
     int idx = 0, it = 0;
-    constexpr bool PREFETCH = C == 32;  // next tile's row requested while this tile is in the MMAs (register budget: C = 32 only)
-    float4 xn[PREFETCH ? C / 4 : 1];
-    auto load_x = [&](int tile, float4* dst) {
-      const int64_t mm = static_cast<int64_t>(tile) * 128 + row;
-      const float4* xr = reinterpret_cast<const float4*>(X + (mm < M ? mm : 0) * C);
-#pragma unroll
-      for (int i = 0; i < C / 4; ++i) dst[i] = mm < M ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    if constexpr (PREFETCH) {
-      if (static_cast<int>(blockIdx.x) < ntiles) load_x(blockIdx.x, xn);
-    }
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int64_t m = static_cast<int64_t>(tile) * 128 + row;
-      const bool valid = m < M;
-      // ---- RMSNorm of this token (x stays in registers for the residual) ----
-      float x[C];
-      {
-        float4 xq[C / 4];
-        if constexpr (PREFETCH) {
-#pragma unroll
-          for (int i = 0; i < C / 4; ++i) xq[i] = xn[i];
-        } else {
-          load_x(tile, xq);
-        }
-#pragma unroll
-        for (int i = 0; i < C / 4; ++i) {
-          const float4 q = xq[i];
-          x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
-        }
-        if constexpr (OP) {  // x' = x + O Wo^T (attention residual)
-          mbar_wait_a(bar_d0, it & 1);
+    const int c4_lo = helper ? 2 : 0;  // this thread's 64 of the 128 hidden units of a chunk (HELP)
+    constexpr int c4_n = HELP ? 2 : 4;
+    if (helper) {
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int h = 0; h < NH; ++h, ++idx) {
+          mbar_wait_a(bar_h, idx & 1);
           tc_fence_after();
-#pragma unroll
-          for (int c4 = 0; c4 < C / 32; ++c4) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_base + lane_base + Cfg::D0_COL + c4 * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[c4 * 32 + i] += __uint_as_float(r[i]);
+          if (h >= 1) {
+            mbar_wait_a(bar_o, (idx - 1) & 1);
+            tc_fence_after();
           }
-        }
-        float ss = 0.f;
-#pragma unroll
-        for (int i = 0; i < C; ++i) ss = fmaf(x[i], x[i], ss);
-        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-        constexpr int RB = C * 2;  // bytes per A row
-        const uint32_t arow = sA + row * RB;
-        const uint32_t sw = C == 32 ? (static_cast<uint32_t>((row >> 1) & 3) << 4) : (static_cast<uint32_t>(row & 7) << 4);
-        // the A tile is free: the last MMA1 of the previous tile completed before its bar_h was observed
-#pragma unroll
-        for (int c = 0; c < C / 8; ++c)
-          st_shared_v4(arow + ((c << 4) ^ sw), pack_h16x2(x[8 * c] * inv, x[8 * c + 1] * inv),
-                       pack_h16x2(x[8 * c + 2] * inv, x[8 * c + 3] * inv), pack_h16x2(x[8 * c + 4] * inv, x[8 * c + 5] * inv),
-                       pack_h16x2(x[8 * c + 6] * inv, x[8 * c + 7] * inv));
-        fence_proxy_async_smem();
-        tc_fence_before();  // this thread's TMEM reads of the previous tile are ordered before the next MMAs
-        mbar_arrive_a(bar_a);
-        if constexpr (PREFETCH) {
-          if (tile + static_cast<int>(gridDim.x) < ntiles) load_x(tile + gridDim.x, xn);
-        }
-      }
-      for (int h = 0; h < NH; ++h, ++idx) {
-        mbar_wait_a(bar_h, idx & 1);
-        tc_fence_after();
-        if (h == 0) {  // this warp's rows of the H tile staged the previous tile's results: their TMA stores must be done reading
-          if (lane == 0) bulk_wait_read<0>();
-          __syncwarp();
-        }
-        if (h >= 1) {  // the single H tile is free once MMA2_{h-1} has completed (h == 0: waited at the end of the last tile)
-          mbar_wait_a(bar_o, (idx - 1) & 1);
-          tc_fence_after();
-        }
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
+          #pragma unroll
+        for (int c4 = c4_lo; c4 < c4_lo + c4_n; ++c4) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + lane_base + c4 * 32, r);
           tmem_ld_wait();
@@ -261,16 +218,138 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
             st_shared_v4(hrow + (cc >> 3) * 16384 + (((cc & 7) << 4) ^ hsw), w[0], w[1], w[2], w[3]);
           }
         }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive_a(bar_h2);
+        }
+      }
+    }
+    constexpr bool PREFETCH = C == 32;  // next tile's row requested while this tile is in the MMAs (register budget: C = 32 only)
+    float4 xn[PREFETCH ? C / 4 : 1];
+    auto load_x = [&](int tile, float4* dst) {
+      const int64_t mm = static_cast<int64_t>(tile) * 128 + row;
+      const float4* xr = reinterpret_cast<const float4*>(X + (mm < M ? mm : 0) * C);
+#pragma unroll
+      for (int i = 0; i < C / 4; ++i) dst[i] = mm < M ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if constexpr (PREFETCH) {
+      if (static_cast<int>(blockIdx.x) < ntiles) load_x(blockIdx.x, xn);
+    }
+#ifdef BT_FF_PROF
+    long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc0 = clock64();
+#endif
+    for (int tile = blockIdx.x; tile < (helper ? 0 : ntiles); tile += gridDim.x, ++it) {
+      const int64_t m = static_cast<int64_t>(tile) * 128 + row;
+      const bool valid = m < M;
+      // ---- RMSNorm of this token.  The residual is added by the tensor core: x is written into the OUT accumulator
+      // columns and MMA2 accumulates on top of it, so the row does not stay in registers for the whole tile ----
+      float x[C];
+      {
+        float4 xq[C / 4];
+        if constexpr (PREFETCH) {
+#pragma unroll
+          for (int i = 0; i < C / 4; ++i) xq[i] = xn[i];
+        } else {
+          load_x(tile, xq);
+        }
+#pragma unroll
+        for (int i = 0; i < C / 4; ++i) {
+          const float4 q = xq[i];
+          x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
+        }
+        FF_TICK(0)  // x loaded
+        if constexpr (OP) {  // x' = x + O Wo^T (attention residual)
+          mbar_wait_a(bar_d0, it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c4 = 0; c4 < C / 32; ++c4) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_base + Cfg::D0_COL + c4 * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[c4 * 32 + i] += __uint_as_float(r[i]);
+          }
+        }
+        FF_TICK(1)  // out-projection result added
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < C; ++i) ss = fmaf(x[i], x[i], ss);
+        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+        constexpr int RB = C * 2;  // bytes per A row
+        const uint32_t arow = sA + row * RB;
+        const uint32_t sw = C == 32 ? (static_cast<uint32_t>((row >> 1) & 3) << 4) : (static_cast<uint32_t>(row & 7) << 4);
+        // the A tile is free: the last MMA1 of the previous tile completed before its bar_h was observed
+#pragma unroll
+        for (int c = 0; c < C / 8; ++c)
+          st_shared_v4(arow + ((c << 4) ^ sw), pack_h16x2(x[8 * c] * inv, x[8 * c + 1] * inv),
+                       pack_h16x2(x[8 * c + 2] * inv, x[8 * c + 3] * inv), pack_h16x2(x[8 * c + 4] * inv, x[8 * c + 5] * inv),
+                       pack_h16x2(x[8 * c + 6] * inv, x[8 * c + 7] * inv));
+        if constexpr (NH > 1) {  // OUT has columns of its own: free since this thread read the previous tile's result
+          auto xr = reinterpret_cast<uint32_t (*)[16]>(x);
+#pragma unroll
+          for (int c = 0; c < C / 16; ++c) tmem_st_32x32b_x16(tmem_base + lane_base + Cfg::OUT_COL + 16 * c, xr[c]);
+          tmem_st_wait();
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();  // this thread's TMEM reads of the previous tile are ordered before the next MMAs
+        // this warp's rows of the H tile staged the previous tile's results: the TMA stores must be done reading them
+        // before ANY warp (the helpers too) writes the next hidden activations, i.e. before MMA1 can be issued
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+        mbar_arrive_a(bar_a);
+        FF_TICK(2)  // norm, A tile, x into OUT
+        if constexpr (PREFETCH) {
+          if (tile + static_cast<int>(gridDim.x) < ntiles) load_x(tile + gridDim.x, xn);
+        }
+      }
+      for (int h = 0; h < NH; ++h, ++idx) {
+        mbar_wait_a(bar_h, idx & 1);
+        tc_fence_after();
+        if (h >= 1) {  // the single H tile is free once MMA2_{h-1} has completed (h == 0: waited at the end of the last tile)
+          mbar_wait_a(bar_o, (idx - 1) & 1);
+          tc_fence_after();
+        }
+        FF_TICK(3)  // waited for MMA1 (and MMA2 of the previous chunk)
+#pragma unroll
+        for (int c4 = c4_lo; c4 < c4_lo + c4_n; ++c4) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_base + c4 * 32, r);
+          tmem_ld_wait();
+          if (NH == 1 && c4 == 0) {  // OUT shares the H columns: this thread has read [0,32), x goes there now
+            auto xr = reinterpret_cast<uint32_t (*)[16]>(x);
+#pragma unroll
+            for (int c = 0; c < C / 16; ++c) tmem_st_32x32b_x16(tmem_base + lane_base + Cfg::OUT_COL + 16 * c, xr[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {  // 4 chunks of 8 hidden units, bias + GELU on packed fp32 pairs
+            const float4 ba = ld_shared_v4_f32(sB + 4 * (h * 128 + c4 * 32 + 8 * c));
+            const float4 bb = ld_shared_v4_f32(sB + 4 * (h * 128 + c4 * 32 + 8 * c + 4));
+            const uint64_t bq[4] = {pack_f32x2(ba.x, ba.y), pack_f32x2(ba.z, ba.w), pack_f32x2(bb.x, bb.y), pack_f32x2(bb.z, bb.w)};
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint64_t g = gelu_tanh_f32x2(add_f32x2(pack_f32x2(__uint_as_float(r[8 * c + 2 * i]), __uint_as_float(r[8 * c + 2 * i + 1])), bq[i]));
+              float g0, g1;
+              unpack_f32x2(g, g0, g1);
+              w[i] = pack_h16x2(g0, g1);
+            }
+            const int cc = c4 * 4 + c;  // 16-byte chunk index inside the 128-wide row: atom = cc >> 3
+            st_shared_v4(hrow + (cc >> 3) * 16384 + (((cc & 7) << 4) ^ hsw), w[0], w[1], w[2], w[3]);
+          }
+        }
+        if (NH == 1) tmem_st_wait();
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive_a(bar_h2);
+        FF_TICK(4)  // H epilogue
       }
       mbar_wait_a(bar_o, (idx - 1) & 1);
       tc_fence_after();
+      FF_TICK(5)  // waited for the last MMA2
       // Results leave through TMA stores staged in this warp's rows of the H tile buffer (free from here until the
       // next tile's hidden activations are written): with one row per lane, st.global touched 32 lines per
       // instruction and the L1 data pipe bounded the kernel (ncu: lsu wavefronts 80 %, DRAM 35 %).
-      const uint32_t stg = sH + warp * 4096;  // + c4 * 16384: [32 rows][128 B] SW128 fp32 box of 32 columns
+      const uint32_t stg = sH + wq * 4096;  // + c4 * 16384: [32 rows][128 B] SW128 fp32 box of 32 columns
       const uint32_t sw128 = static_cast<uint32_t>(lane & 7) << 4, sw64 = static_cast<uint32_t>((lane >> 1) & 3) << 4;
       uint32_t xbp[C / 2];  // the 16-bit copy of the row (for the following convolution), packed
 #pragma unroll
@@ -281,10 +360,10 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 bq = ld_shared_v4_f32(sB + 4 * (4 * C + c4 * 32 + 4 * i));
-          const float v0 = __uint_as_float(r[4 * i]) + bq.x + x[c4 * 32 + 4 * i];
-          const float v1 = __uint_as_float(r[4 * i + 1]) + bq.y + x[c4 * 32 + 4 * i + 1];
-          const float v2 = __uint_as_float(r[4 * i + 2]) + bq.z + x[c4 * 32 + 4 * i + 2];
-          const float v3 = __uint_as_float(r[4 * i + 3]) + bq.w + x[c4 * 32 + 4 * i + 3];
+          const float v0 = __uint_as_float(r[4 * i]) + bq.x;
+          const float v1 = __uint_as_float(r[4 * i + 1]) + bq.y;
+          const float v2 = __uint_as_float(r[4 * i + 2]) + bq.z;
+          const float v3 = __uint_as_float(r[4 * i + 3]) + bq.w;
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + c4 * 16384 + lane * 128 + ((static_cast<uint32_t>(i) << 4) ^ sw128)),
                        "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
           xbp[c4 * 16 + 2 * i] = pack_h16x2(v0, v1);
@@ -300,8 +379,8 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
       __syncwarp();
       if (lane == 0) {
 #pragma unroll
-        for (int c4 = 0; c4 < C / 32; ++c4) tma_store_2d(&tmXst, stg + c4 * 16384, c4 * 32, tile * 128 + warp * 32);
-        if (C == 32 && xb_out) tma_store_2d(&tmXb, stg + 16384, 0, tile * 128 + warp * 32);
+        for (int c4 = 0; c4 < C / 32; ++c4) tma_store_2d(&tmXst, stg + c4 * 16384, c4 * 32, tile * 128 + wq * 32);
+        if (C == 32 && xb_out) tma_store_2d(&tmXb, stg + 16384, 0, tile * 128 + wq * 32);
         bulk_commit();
       }
       if (C == 64 && xb_out) {  // no spare room: the 16-bit tiles reuse the staging area once the fp32 stores have read it
@@ -317,17 +396,24 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
         __syncwarp();
         if (lane == 0) {
 #pragma unroll
-          for (int c4 = 0; c4 < C / 32; ++c4) tma_store_2d(&tmXb, stg + c4 * 16384, c4 * 32, tile * 128 + warp * 32);
+          for (int c4 = 0; c4 < C / 32; ++c4) tma_store_2d(&tmXb, stg + c4 * 16384, c4 * 32, tile * 128 + wq * 32);
           bulk_commit();
         }
       }
+      FF_TICK(6)  // out epilogue, staging, TMA stores
     }
-    if (lane == 0) bulk_wait_read<0>();
+    if (!helper && lane == 0) bulk_wait_read<0>();
     __syncwarp();
+#ifdef BT_FF_PROF
+    if (!helper && lane == 0) {
+      for (int i = 0; i < 8; ++i) atomicAdd(&g_ff_prof[i], static_cast<unsigned long long>(tp[i]));
+      atomicAdd(&g_ff_prof[8], static_cast<unsigned long long>(it));
+    }
+#endif
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<Cfg::TCOLS>(tmem_base);
+  if (warp == FFN_ISSUER) tmem_dealloc<Cfg::TCOLS>(tmem_base);
 }
 
 struct TcFfPlan {
@@ -398,11 +484,22 @@ int launch_fused_ff(const TcFfPlan* p, float* X, const float* b1, const float* b
   const unsigned grid = ntiles < slots ? ntiles : slots;  // persistent CTAs
   h16* xb = reinterpret_cast<h16*>(xb_out);
 #define BT_FF_L(CC, OPP)                                                                                          \
-  fused_ff_kernel<CC, OPP><<<grid, FF_THREADS, FfCfg<CC>::SMEM, st>>>(p->tmW1, p->tmW2, p->tmO, p->tmWo, p->tmXst, p->tmXb, X, \
+  fused_ff_kernel<CC, OPP><<<grid, ffn_threads<CC>(), FfCfg<CC>::SMEM, st>>>(p->tmW1, p->tmW2, p->tmO, p->tmWo, p->tmXst, p->tmXb, X, \
                                                                       b1, b2, xb, p->M)
   if (p->C == 32) { if (p->outproj) BT_FF_L(32, true); else BT_FF_L(32, false); }
   else { if (p->outproj) BT_FF_L(64, true); else BT_FF_L(64, false); }
 #undef BT_FF_L
+#ifdef BT_FF_PROF
+  {
+    cudaStreamSynchronize(st);
+    unsigned long long h[16], z[16] = {};
+    cudaMemcpyFromSymbol(h, g_ff_prof, sizeof(h));
+    cudaMemcpyToSymbol(g_ff_prof, z, sizeof(z));
+    const double n = h[8] ? double(h[8]) : 1.0;
+    fprintf(stderr, "fused_ff C=%d op=%d cycles/tile: load %.0f | d0 %.0f | norm %.0f | wait mma1 %.0f | H epi %.0f | wait mma2 %.0f | out %.0f\n", p->C,
+            int(p->outproj), h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n);
+  }
+#endif
   return 0;
 }
 
