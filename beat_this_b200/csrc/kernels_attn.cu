@@ -277,6 +277,7 @@ attn_tc48_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (need) { m_ref = mx; l *= a_corr; }
         exps(m_ref);
         if (j >= 1 && __any_sync(0xffffffffu, need)) {  // O holds tiles 0..j-1 once PV_{j-1} is done
+          if (V & 64) tp[4] += 1000000;  // (counted in the "wait PV" slot: one million per rescaled tile)
           mbar_wait_q(bar_pv + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
           tc_fence_after();
           uint32_t r[32];
@@ -367,6 +368,15 @@ void attn_prof_read(unsigned long long* out40, bool reset) {
   if (reset) { unsigned long long z[40] = {}; cudaMemcpyToSymbol(g_attn_prof, z, 320); }
 }
 
+static void attn_prof_print(cudaStream_t st) {  // variant 101 inside the real pipeline (BT_ATTN_PROF_PRINT=1)
+  cudaStreamSynchronize(st);
+  unsigned long long h[40];
+  attn_prof_read(h, true);
+  const double n = h[6] ? double(h[6]) : 1.0;
+  fprintf(stderr, "attention warp 0, cycles per tile: wait S %.0f | ld S %.0f | max+rescale %.0f | exp %.0f | st P %.0f | rescaled tiles %.1f %%\n",
+          h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[5] / n, 100.0 * (h[4] / 1000000) / n);
+}
+
 //   37 default | 32, 33, 36, 40, 41: 0, 1, 2, 4, 5 of 8 pairs on the polynomial | 5: S_{j+2} only after PV_j has
 //   completed | 39, 34: without exponentials (timing ablation, wrong results) | 101: phase cycle counters
 #define BT_A4_VARIANTS(X) X(37) X(32) X(33) X(36) X(40) X(41) X(5) X(39) X(34) X(101)
@@ -380,6 +390,7 @@ int launch_attn_time_tc(const TcAttnPlan* p, const float* gates, void* out, cuda
   if (g_attn_variant == (V_)) {                                                                                      \
     attn_tc48_kernel<V_><<<grid, AT_THREADS, A4_SMEM, st>>>(p->tmQ, p->tmKV, gates, o, p->L, p->heads, chunks,        \
                                                             seqs_per_chunk);                                         \
+    if (((V_) & 64) && getenv("BT_ATTN_PROF_PRINT")) attn_prof_print(st);                                            \
     return 0;                                                                                                        \
   }
   BT_A4_VARIANTS(BT_A4_L)

@@ -298,6 +298,14 @@ fused_ff_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
         __syncwarp();
         mbar_arrive_a(bar_a);
         FF_TICK(2)  // norm, A tile, x into OUT
+        if constexpr (!PREFETCH) {  // no registers for the next tile's row: at least pull its lines into L2 now
+          const int64_t mn = m + static_cast<int64_t>(gridDim.x) * 128;
+          if (mn < M) {
+#pragma unroll
+            for (int i = 0; i < C * 4 / 128; ++i)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(X + mn * C + i * 32));
+          }
+        }
         if constexpr (PREFETCH) {
           if (tile + static_cast<int>(gridDim.x) < ntiles) load_x(tile + gridDim.x, xn);
         }
