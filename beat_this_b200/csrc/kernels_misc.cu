@@ -479,9 +479,11 @@ __device__ __forceinline__ void mma_h16_16816(float (&d)[4], const uint32_t (&a)
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// Tile = FT_TT consecutive frames of one chunk, all F frequency planes, all heads: for a fixed plane the rows of
-// consecutive frames are contiguous in [B, F, L, 3C], so ONE TMA box per (q|k|v, head) brings [F][TT][32] fp16 into
-// shared memory (SWIZZLE_64B) and one box stores the [F][TT][C] output tile.  (Before: every lane fetched its own
+// Tile = FT_TT consecutive frames of one chunk, all F frequency planes, all heads: ONE TMA box per (q|k|v, head)
+// brings [TT][F][32] fp16 into shared memory (SWIZZLE_64B; the tensor map lists the plane dimension before the frame
+// dimension, so the F rows one attention group reads are CONSECUTIVE 64-byte rows and ldmatrix is conflict free --
+// with [F][TT] order the eight rows of an ldmatrix phase were 256 B apart: 4-way conflicts, L1 data pipe 82 % in
+// ncu) and one box stores the [TT][F][C] output tile.  (Before: every lane fetched its own
 // row, L * 3C elements away from its neighbour's -- 32 lines per ld.global, L1 wavefronts 73-87 % in ncu.)
 constexpr int FT_TT = 4;
 
@@ -507,7 +509,7 @@ attn_freq_mma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_cons
     mbar_expect_tx_a(bar, 3 * HEADS * PH_BYTES);
     for (int part = 0; part < 3; ++part)
       for (int h = 0; h < HEADS; ++h)
-        tma_load_3d_a(sIn + (part * HEADS + h) * PH_BYTES, &tmIn, bar, part * C + h * 32, t0, b * F);
+        tma_load_3d_a(sIn + (part * HEADS + h) * PH_BYTES, &tmIn, bar, part * C + h * 32, b * F, t0);
   }
   __syncthreads();
   mbar_wait_a(bar, 0);
@@ -515,7 +517,7 @@ attn_freq_mma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_cons
   const int h = (wib * GPW) / FT_TT;
   const int tt_base = (wib * GPW) % FT_TT;
   auto row_addr = [&](uint32_t base, int r, int chunk) -> uint32_t {  // 16-byte chunk `chunk` of staged row r
-    const int row = (r % F) * FT_TT + tt_base + r / F;
+    const int row = tt_base * F + r;  // = (tt_base + r / F) * F + r % F
     return base + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
   };
   const uint32_t sQ = sIn + (0 * HEADS + h) * PH_BYTES, sK = sIn + (1 * HEADS + h) * PH_BYTES, sV = sIn + (2 * HEADS + h) * PH_BYTES;
@@ -584,7 +586,7 @@ attn_freq_mma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_cons
       const int t = t0 + tt;
       const int64_t m = (static_cast<int64_t>(b) * F + f) * L + (t < L ? t : L - 1);
       const float gsc = gates[m * HEADS + h] / (half == 0 ? l0 : l1);
-      const uint32_t orow = sOut + (f * FT_TT + tt) * (C * 2) + h * 64;
+      const uint32_t orow = sOut + (tt * F + f) * (C * 2) + h * 64;
 #pragma unroll
       for (int jd = 0; jd < 4; ++jd)
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(orow + (4 * jd + c) * 4), "r"(pack_h16x2(o[jd][2 * half] * gsc, o[jd][2 * half + 1] * gsc)) : "memory");
@@ -593,7 +595,7 @@ attn_freq_mma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_cons
   fence_proxy_async_smem();
   __syncthreads();
   if (threadIdx.x == 0) {
-    tma_store_3d(&tmOut, sOut, 0, t0, b * F);  // frames beyond L are clipped
+    tma_store_3d(&tmOut, sOut, 0, b * F, t0);  // frames beyond L are clipped
     bulk_commit();
     bulk_wait_read<0>();
   }
@@ -616,14 +618,18 @@ static int attn_freq_mma_launch(const void* qkv, const float* gates, void* out, 
   if (!k) {
     k = &cache[n_cached < 4 ? n_cached++ : 0];
     char err[256];
-    const uint64_t din[3] = {static_cast<uint64_t>(3 * C), static_cast<uint64_t>(L), static_cast<uint64_t>(B) * F};
-    const uint64_t sin_[2] = {static_cast<uint64_t>(3 * C) * 2, static_cast<uint64_t>(L) * 3 * C * 2};
-    const uint32_t bin[3] = {32, FT_TT, F};
-    const uint64_t dout[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(L), static_cast<uint64_t>(B) * F};
-    const uint64_t sout[2] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(L) * C * 2};
-    const uint32_t bout[3] = {static_cast<uint32_t>(C), FT_TT, F};
-    if (!make_tmap(&k->in, qkv, 3, din, sin_, bin, 64, err, sizeof(err)) || !make_tmap(&k->outm, out, 3, dout, sout, bout, 0, err, sizeof(err)))
+    // dimension order (channels, planes, frames): the plane stride is the larger one
+    const uint64_t din[3] = {static_cast<uint64_t>(3 * C), static_cast<uint64_t>(B) * F, static_cast<uint64_t>(L)};
+    const uint64_t sin_[2] = {static_cast<uint64_t>(L) * 3 * C * 2, static_cast<uint64_t>(3 * C) * 2};
+    const uint32_t bin[3] = {32, F, FT_TT};
+    const uint64_t dout[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(B) * F, static_cast<uint64_t>(L)};
+    const uint64_t sout[2] = {static_cast<uint64_t>(L) * C * 2, static_cast<uint64_t>(C) * 2};
+    const uint32_t bout[3] = {static_cast<uint32_t>(C), F, FT_TT};
+    if (!make_tmap(&k->in, qkv, 3, din, sin_, bin, 64, err, sizeof(err)) || !make_tmap(&k->outm, out, 3, dout, sout, bout, 0, err, sizeof(err))) {
+      fprintf(stderr, "bt: attn_freq tensor map: %s -- using the scalar kernel\n", err);  // never seen; loud if it happens
+      k->q = nullptr;
       return -1;
+    }
     k->q = qkv; k->o = out; k->B = B; k->L = L;
   }
   static bool attr = false;

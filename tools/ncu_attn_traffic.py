@@ -1,9 +1,9 @@
 """profiles/attn_traffic.json from an `ncu --set full` capture of the time-attention kernel.
 
-  ncu --set full --clock-control none --import-source on -k regex:attn_tc64_kernel -s 2 -c 2 \
-      -o gpurun_out/attn64_full python tools/prof_step.py 64 1
-  ncu -i gpurun_out/attn64_full.ncu-rep --page raw --csv > gpurun_out/attn64_full_raw.csv
-  python tools/ncu_attn_traffic.py gpurun_out/attn64_full_raw.csv
+  ncu --set full --clock-control none --import-source on -k regex:attn_tc48_kernel -s 2 -c 2 \
+      -o gpurun_out/r2_attn_full python tools/prof_step.py 64 1
+  ncu -i gpurun_out/r2_attn_full.ncu-rep --page raw --csv > gpurun_out/r2_attn_full_raw.csv
+  python tools/ncu_attn_traffic.py gpurun_out/r2_attn_full_raw.csv
 
 With 64 x 30 s clips in one wave a step has 3 frontend launches (grid 49152 CTAs) followed by 6 main-layer
 launches (24576 CTAs); `-s 2 -c 2` captures the last frontend launch and the first main-layer launch.
@@ -54,7 +54,7 @@ out = {
     "dram_bytes_per_launch_mean": mean,
     "frontend_launch": front,
     "main_launch": main,
-    "source": "ncu --set full --clock-control none -k regex:attn_tc64_kernel -s 2 -c 2 python tools/prof_step.py 64 1 "
+    "source": "ncu --set full --clock-control none -k regex:attn_tc48_kernel -s 2 -c 2 python tools/prof_step.py 64 1 "
               "(64 x 30 s clips, one 128-chunk wave): dram__bytes_read.sum + dram__bytes_write.sum, mean over the "
               "3 frontend + 6 main-layer launches of a step",
     "algorithmic_bytes_per_launch": {"frontend": 1572864000, "main": 786432000},
