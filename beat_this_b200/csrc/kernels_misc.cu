@@ -14,95 +14,130 @@ namespace bt {
 // log-mel: reference LogMelSpect.forward (beat_this/preprocessing.py:56-59) =
 //   torch.stft(n_fft 1024, hop 441, periodic hann, center reflect, normalized) -> abs ->
 //   mel filterbank (slaney, 128 bins, 30..11000 Hz) -> log1p(1000 x).
-// One CTA (128 threads) per PAIR of frames: windowed frames -> one 1024-point radix-2 FFT in
-// shared memory -> |X|/32 -> sparse triangular filterbank -> log1p.  Algorithmic HBM bytes:
-// 441 new samples * 4 B read + 128 * 4 B written per frame.
+// Algorithmic HBM bytes: 441 new samples * 4 B read + 128 * 4 B written per frame.
+//
+// 64 threads per frame, two frames per CTA.  The real 1024-point transform is ONE complex 512-point FFT of
+// z[n] = x[2n] + i x[2n+1] followed by the usual untangling step, and 512 = 8 * 8 * 8: three radix-8 passes with the
+// eight points of a butterfly in registers,
+//   n = 64 n1 + 8 n2 + n3,  k = k1 + 8 k2 + 64 k3:
+//   A: thread (n2, n3)  DFT8 over n1, times e^{-2 pi i n2 k1 / 64}          -> T1[k1][n2][n3]
+//   B: thread (k1, n3)  DFT8 over n2, times e^{-2 pi i n3 (k1 + 8 k2) / 512} -> T2[n3][k2][k1]
+//   C: thread (k2, k1)  DFT8 over n3                                         -> Z[k1 + 8 k2 + 64 k3]
+// i.e. two exchanges through shared memory (8-byte accesses, padded pitches: at most the natural two wavefronts per
+// warp access) where the radix-2 version of round 1 made ten passes over separate re / im arrays -- that kernel was
+// bound by the shared-memory pipe (ncu: l1tex data-pipe wavefronts 97 %), not by HBM.
 // ------------------------------------------------------------------------------------------
-// Two frames per CTA: frames 2j and 2j+1 of a clip are packed as the real and imaginary part of ONE
-// complex 1024-point FFT (z = x_a + i x_b) and separated afterwards
-//   X_a[k] = (Z[k] + conj(Z[N-k])) / 2,   X_b[k] = (Z[k] - conj(Z[N-k])) / (2i),
-// which halves the butterfly work per frame.  grid = (ceil(max_frames/2), n_clips): no clip search.
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+
+// in-place 8-point DFT (e^{-2 pi i nk/8}), natural order in and out
+__device__ __forceinline__ void dft8(float2 (&v)[8]) {
+  constexpr float R = 0.70710678118654752f;
+  float2 a[4], b[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { a[j] = cadd(v[j], v[j + 4]); b[j] = csub(v[j], v[j + 4]); }
+  b[1] = make_float2(R * (b[1].x + b[1].y), R * (b[1].y - b[1].x));    // * (1 - i) / sqrt 2
+  b[2] = cmul_mi(b[2]);                                                 // * (-i)
+  b[3] = make_float2(R * (b[3].y - b[3].x), -R * (b[3].x + b[3].y));   // * (-1 - i) / sqrt 2
+  auto dft4 = [](const float2 (&c)[4], float2& y0, float2& y1, float2& y2, float2& y3) {
+    const float2 s0 = cadd(c[0], c[2]), s1 = csub(c[0], c[2]), s2 = cadd(c[1], c[3]), s3 = cmul_mi(csub(c[1], c[3]));
+    y0 = cadd(s0, s2); y2 = csub(s0, s2); y1 = cadd(s1, s3); y3 = csub(s1, s3);
+  };
+  dft4(a, v[0], v[2], v[4], v[6]);
+  dft4(b, v[1], v[3], v[5], v[7]);
+}
+
+constexpr int LM_P1 = 72, LM_P2 = 68;  // pitches (float2) of the two exchange buffers
+
 __global__ void __launch_bounds__(128)
 logmel_kernel(const float* __restrict__ audio, const int64_t* __restrict__ sample_off,
               const int64_t* __restrict__ frame_off, const float* __restrict__ window,
               const float2* __restrict__ twiddle, const int32_t* __restrict__ fb_start,
               const int32_t* __restrict__ fb_ptr, const float* __restrict__ fb_w,
               float* __restrict__ spect) {
-  __shared__ float re[1024];
-  __shared__ float im[1024];
-  __shared__ float2 tw[512];
-  __shared__ float ma[516];
-  __shared__ float mb[516];
+  __shared__ float2 tw[512];                 // e^{-2 pi i j / 1024}, j < 512
+  __shared__ float2 t1[2][8 * LM_P1];        // per frame: T1, later Z (512 entries)
+  __shared__ float2 t2[2][8 * LM_P2];
+  __shared__ float mag[2][516];
   const int clip = blockIdx.y;
   const int64_t f0 = frame_off[clip];
   const int T = static_cast<int>(frame_off[clip + 1] - f0);
-  const int ta = 2 * blockIdx.x, tb = ta + 1;
-  if (ta >= T) return;
-  const bool has_b = tb < T;
+  const int tid = threadIdx.x, half = tid >> 6, lt = tid & 63;
+  const int t = 2 * blockIdx.x + half;
+  if (2 * static_cast<int>(blockIdx.x) >= T) return;  // whole CTA beyond the clip
+  const bool active = t < T;
   const int64_t s0 = sample_off[clip];
   const int64_t len = sample_off[clip + 1] - s0;
-  const int tid = threadIdx.x;
   for (int i = tid; i < 512; i += 128) tw[i] = twiddle[i];
-  for (int n = tid; n < 1024; n += 128) {
-    const float w = window[n];
-    int64_t ia = 441ll * ta + n - 512;
-    if (ia < 0) ia = -ia;                      // reflect (no edge repeat), torch pad_mode="reflect"
-    if (ia >= len) ia = 2 * (len - 1) - ia;
-    float vb = 0.f;
-    if (has_b) {
-      int64_t ib = 441ll * tb + n - 512;
-      if (ib < 0) ib = -ib;
-      if (ib >= len) ib = 2 * (len - 1) - ib;
-      vb = audio[s0 + ib] * w;
-    }
-    const int r = __brev(static_cast<unsigned>(n)) >> 22;  // 10-bit reversal
-    re[r] = audio[s0 + ia] * w;
-    im[r] = vb;
-  }
-  __syncthreads();
-  // decimation-in-time butterflies; stage s has half-span h = 2^s, twiddle index (j * 512/h)
-#pragma unroll 1
-  for (int s = 0; s < 10; ++s) {
-    const int h = 1 << s;
+  auto TW = [&](int j) -> float2 {  // e^{-2 pi i j / 1024}, 0 <= j < 1024
+    const float2 w = tw[j & 511];
+    return (j & 512) ? make_float2(-w.x, -w.y) : w;
+  };
+  float2 v[8];
+  float2* T1 = t1[half];
+  float2* T2 = t2[half];
+  {  // ---- pass A: thread (n2, n3) = lt, points z[64 n1 + lt] ----
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int idx = tid + b * 128;          // butterfly id 0..511
-      const int j = idx & (h - 1);
-      const int i0 = ((idx >> s) << (s + 1)) + j;
-      const int i1 = i0 + h;
-      const float2 w = tw[j << (9 - s)];      // (cos, -sin)
-      const float xr = re[i1], xi = im[i1];
-      const float tr = xr * w.x - xi * w.y;
-      const float ti = xr * w.y + xi * w.x;
-      const float ur = re[i0], ui = im[i0];
-      re[i0] = ur + tr; im[i0] = ui + ti;
-      re[i1] = ur - tr; im[i1] = ui - ti;
+    for (int n1 = 0; n1 < 8; ++n1) {
+      const int n = 2 * (64 * n1 + lt);
+      float xs[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int64_t i = 441ll * t + (n + e) - 512;
+        if (i < 0) i = -i;                      // reflect (no edge repeat), torch pad_mode="reflect"
+        if (i >= len) i = 2 * (len - 1) - i;
+        xs[e] = active ? audio[s0 + i] * __ldg(window + n + e) : 0.f;
+      }
+      v[n1] = make_float2(xs[0], xs[1]);
     }
-    __syncthreads();
   }
-  // split the packed spectrum, magnitudes of bins 0..512 (normalized=True -> 1/sqrt(1024))
-  for (int k = tid; k <= 512; k += 128) {
-    const int nk = (1024 - k) & 1023;
-    const float zr = re[k], zi = im[k], yr = re[nk], yi = im[nk];
-    const float ar = 0.5f * (zr + yr), ai = 0.5f * (zi - yi);   // X_a[k]
-    const float br = 0.5f * (zi + yi), bi = 0.5f * (yr - zr);   // X_b[k]
-    ma[k] = sqrtf(ar * ar + ai * ai) * 0.03125f;
-    mb[k] = sqrtf(br * br + bi * bi) * 0.03125f;
+  __syncthreads();  // twiddle table
+  {
+    dft8(v);
+    const int n2 = lt >> 3;
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) T1[k1 * LM_P1 + lt] = k1 == 0 ? v[0] : cmul(v[k1], TW(16 * n2 * k1));
   }
   __syncthreads();
-  {
-    const int m = tid;  // mel bin
-    const int p0 = fb_ptr[m], p1 = fb_ptr[m + 1];
-    const int k0 = fb_start[m];
-    float acc_a = 0.f, acc_b = 0.f;
-    for (int p = p0; p < p1; ++p) {
-      const int k = k0 + (p - p0);
-      const float w = fb_w[p];
-      acc_a = fmaf(ma[k], w, acc_a);
-      acc_b = fmaf(mb[k], w, acc_b);
+  {  // ---- pass B: thread (k1, n3) = lt ----
+    const int k1 = lt >> 3, n3 = lt & 7;
+#pragma unroll
+    for (int n2 = 0; n2 < 8; ++n2) v[n2] = T1[k1 * LM_P1 + n2 * 8 + n3];
+    dft8(v);
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) T2[n3 * LM_P2 + k2 * 8 + k1] = cmul(v[k2], TW(2 * n3 * (k1 + 8 * k2)));
+  }
+  __syncthreads();
+  {  // ---- pass C: thread (k2, k1) = lt -> Z[lt + 64 k3] (into T1's storage) ----
+#pragma unroll
+    for (int n3 = 0; n3 < 8; ++n3) v[n3] = T2[n3 * LM_P2 + lt];
+    dft8(v);
+#pragma unroll
+    for (int k3 = 0; k3 < 8; ++k3) T1[lt + 64 * k3] = v[k3];
+  }
+  __syncthreads();
+  // untangle: X[k] = E[k] + e^{-2 pi i k / 1024} O[k], E = (Z[k] + conj Z[512 - k]) / 2, O = -i (Z[k] - conj Z[512 - k]) / 2;
+  // magnitudes of bins 0..512 (normalized=True -> 1 / sqrt(1024))
+  for (int k = lt; k <= 512; k += 64) {
+    const float2 zk = T1[k & 511], zc = T1[(512 - k) & 511];
+    const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+    const float2 o = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+    const float2 x = cadd(e, cmul(TW(k), o));
+    mag[half][k] = sqrtf(x.x * x.x + x.y * x.y) * 0.03125f;
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int mm = 0; mm < 2; ++mm) {
+      const int m = lt + 64 * mm;  // mel bin
+      const int p0 = fb_ptr[m], p1 = fb_ptr[m + 1];
+      const int k0 = fb_start[m];
+      float acc = 0.f;
+      for (int p = p0; p < p1; ++p) acc = fmaf(mag[half][k0 + (p - p0)], fb_w[p], acc);
+      spect[(f0 + t) * 128 + m] = log1pf(1000.0f * acc);
     }
-    spect[(f0 + ta) * 128 + m] = log1pf(1000.0f * acc_a);
-    if (has_b) spect[(f0 + tb) * 128 + m] = log1pf(1000.0f * acc_b);
   }
 }
 
