@@ -255,7 +255,7 @@ stem_kernel(const float* __restrict__ spect, const ChunkSrc* __restrict__ chunks
       for (int df = 0; df < 4; ++df)
 #pragma unroll
         for (int dt = 0; dt < 3; ++dt) a = fmaf(in[df][dt], ws[co * 12 + df * 3 + dt], a);
-      r[i] = gelu_erf(a);
+      r[i] = gelu_fast(a);  // erf to 1.5e-7 on rcp + ex2 (erff: ~35 instructions, 32 of them per thread here)
     }
     reinterpret_cast<float4*>(op)[c4] = make_float4(r[0], r[1], r[2], r[3]);
   }
