@@ -13,10 +13,12 @@ namespace bt {
 // x += W2 gelu(W1 rmsnorm(x) + b1) + b2 for the narrow frontend FFNs (C = 32 / 64, hidden 4C) in ONE
 // kernel (reference roformer.py:38-61): the hidden activations never leave the SM.  Unfused, this
 // block streams 32 bytes per element through HBM (norm 6 + ff1 10 + ff2 16); fused it is 8.
-// CTA = 128 tokens; warps 0-3: one token row per thread (RMSNorm, bias+GELU, residual), warp 4
-// (converged, one elected lane issues): TMA (weights) + tcgen05.mma.  Hidden units are processed in chunks of 128:
+// CTA = 128 tokens; warps 0-3: one token row per thread (RMSNorm, bias+GELU, output), for C = 64 warps 4-7 share those
+// rows and take half of every GELU epilogue, the last warp (converged, one elected lane issues): TMA (weights) +
+// tcgen05.mma.  Hidden units are processed in chunks of 128:
 //   H_h = Xn W1_h^T (N=128, K=C) -> TMEM cols [0,128) -> bias+GELU -> h16 tile in smem ->
-//   OUT (+)= H_h W2_h^T (N=C, K=128) -> TMEM cols [128,128+C).
+//   OUT += H_h W2_h^T (N=C, K=128) -> TMEM cols [128,128+C), which start from the residual x (written there by the
+//   row's thread): the tensor core adds the residual, the row does not stay in registers.
 constexpr int FF_THREADS = 160;   // fused_qkv_kernel: 4 row warps + issuer
 // fused_ff_kernel: 4 row warps [+ 4 helper warps for C = 64] + issuer.  (C = 32 runs three CTAs per SM: nine warps each
 // would leave 72 registers per thread -- measured slower than four row warps with the next tile's rows prefetched.)
